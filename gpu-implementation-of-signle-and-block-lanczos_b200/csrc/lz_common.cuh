@@ -1,0 +1,189 @@
+// lz_common.cuh -- shared internals of liblanczos_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/lanczos_b200.h"
+
+#define LZ_SM_COUNT_DEFAULT 148
+#define LZ_WARP 32
+
+// ---- error plumbing ------------------------------------------------------------------
+void lz_set_error(const char *fmt, ...);
+
+#define LZ_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            lz_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return (e__ == cudaErrorMemoryAllocation) ? LZ_ERR_ALLOC : LZ_ERR_CUDA;            \
+        }                                                                                      \
+    } while (0)
+
+#define LZ_CHECK(cond, code, ...)                                                              \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            lz_set_error(__VA_ARGS__);                                                         \
+            return (code);                                                                     \
+        }                                                                                      \
+    } while (0)
+
+#define LZ_TRY(call)                                                                           \
+    do {                                                                                       \
+        int s__ = (call);                                                                      \
+        if (s__ != LZ_OK) return s__;                                                          \
+    } while (0)
+
+// launch check: reference never checks launches; we do, cheaply (no sync).
+#define LZ_LAUNCH_CHECK(ctx)                                                                   \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t e__ = cudaPeekAtLastError();                                               \
+        if (e__ != cudaSuccess) {                                                              \
+            lz_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return LZ_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+// ---- context -------------------------------------------------------------------------
+struct lz_comm;   // lz_multi.cu
+
+struct lz_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    int64_t launches;
+    // reduction scratch: per-CTA partials + ticket counters for the last-block-done pattern
+    double *partials;       // LZ_PARTIALS_CAP doubles
+    unsigned int *tickets;  // LZ_TICKETS ints, zero-initialised, self-resetting
+    double *scalars;        // device scalar bank (LZ_SCALARS doubles)
+    int *flags;             // device int flags (LZ_FLAGS)
+    // generic workspace (grown on demand, outside timed regions after the first call)
+    void *work;
+    size_t work_bytes;
+    // Krylov basis slab kept by the full-reorth drivers
+    double *basis;
+    size_t basis_bytes;
+    int64_t basis_ld;
+    int basis_cols;
+    lz_comm *comm;
+};
+
+#define LZ_PARTIALS_CAP (1 << 20)
+#define LZ_TICKETS 64
+#define LZ_SCALARS 4096
+#define LZ_FLAGS 64
+
+int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out);   // grow-only scratch
+int lz_ctx_basis(lz_ctx *ctx, int64_t ld, int cols, double **out);
+
+// ---- sparse operator -----------------------------------------------------------------
+enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
+
+// row-aligned nnz chunks: chunk c covers rows [chunk_row[c], chunk_row[c+1])
+#define LZ_SPMV_THREADS 256
+#define LZ_SPMV_TILE 3072        // target nnz per chunk
+#define LZ_SPMV_CAP 4096         // shared-memory product slots per CTA (32 KB)
+
+struct lz_matrix {
+    lz_ctx *ctx;
+    int format;
+    int64_t n_rows, n_cols, nnz;
+    const int32_t *rowptr;   // CSR
+    const int32_t *colidx;
+    const double *vals;
+    const double *ell_data;  // ELL4 row-interleaved
+    const uint32_t *ell_idx;
+    int owns;                // arrays owned by the library (freed on destroy)
+    int n_chunks;
+    int32_t *chunk_row;      // n_chunks + 1
+    int max_row_nnz;
+    // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
+    int64_t halo_lo, halo_hi;        // halo entries below / above the local range
+    int64_t global_rows, row_begin;  // position in the global operator
+};
+
+// ---- device helpers -------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double lz_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; result valid in thread 0.  `red` is >= 32 doubles of shared memory.
+template <int THREADS>
+__device__ __forceinline__ double lz_block_sum(double v, double *red)
+{
+    v = lz_warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < THREADS / 32) ? red[lane] : 0.0;
+        v = lz_warp_sum(v);
+    }
+    return v;
+}
+
+// Deterministic grid reduction, last-block-done: thread 0 of every CTA stores its NS partials, the
+// last CTA to arrive sums all partials in a fixed order (independent of arrival order) and gets
+// `true` back in all its threads with the totals valid in thread 0.  The ticket resets itself, so
+// kernels that run one after another on a stream can share it.
+template <int THREADS, int NS>
+__device__ __forceinline__ bool lz_grid_sum(const double *mine, double *partials, unsigned int *ticket,
+                                            double *red, double *total)
+{
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) partials[(size_t)blockIdx.x * NS + s] = mine[s];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        double acc = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) acc += __ldcg(&partials[(size_t)i * NS + s]);
+        acc = lz_block_sum<THREADS>(acc, red);
+        if (threadIdx.x == 0) total[s] = acc;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+    return true;
+}
+
+__device__ __forceinline__ uint64_t lz_splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ double lz_u01(uint64_t x) { return (double)(x >> 11) * (1.0 / 9007199254740992.0); }
+
+// 256-bit global load of four doubles (sm_100: LDG.E.ENL2.256); pointer must be 32-byte aligned
+__device__ __forceinline__ void lz_ld256(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// streaming variant for data that is read exactly once (the Krylov basis): evict-first
+__device__ __forceinline__ void lz_ld256_stream(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void lz_st256(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,421 @@
+// lz_csr.cu -- sparse operator objects: CSR (new, in the reference's container style), the
+// reference's ELLPACK (objects/ell_matrix.hpp:10-21), the row-block schedule used by the SpMV /
+// SpMM kernels, and the on-device generators of BASELINE.json's synthetic operators.
+#include <cub/device/device_scan.cuh>
+
+#include "lz_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// schedule: chunk c covers rows [chunk_row[c], chunk_row[c+1]) where chunk_row[c] is the first
+// row whose rowptr is >= c * LZ_SPMV_TILE.  Chunks hold < TILE + max_row_nnz non-zeros.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_chunk_rows(int64_t n_rows, int64_t nnz, const int32_t *__restrict__ rowptr, int n_chunks,
+                             int32_t *__restrict__ chunk_row)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_chunks) return;
+    if (c == n_chunks) { chunk_row[c] = (int32_t)n_rows; return; }
+    int64_t target = (int64_t)c * LZ_SPMV_TILE;
+    int64_t lo = 0, hi = n_rows;   // first r in [0, n_rows] with rowptr[r] >= target
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    chunk_row[c] = (int32_t)lo;
+}
+
+__global__ void k_max_row(int64_t n_rows, const int32_t *__restrict__ rowptr, int *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int len = 0;
+    if (i < n_rows) len = rowptr[i + 1] - rowptr[i];
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_down_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
+}
+
+static int build_schedule(lz_ctx *ctx, lz_matrix *A)
+{
+    int64_t nch = (A->nnz + LZ_SPMV_TILE - 1) / LZ_SPMV_TILE;
+    if (nch < 1) nch = 1;
+    LZ_CHECK(nch * 2 <= LZ_PARTIALS_CAP, LZ_ERR_UNSUPPORTED, "matrix too large for the reduction scratch (%lld chunks)", (long long)nch);
+    A->n_chunks = (int)nch;
+    LZ_CUDA(cudaMalloc(&A->chunk_row, sizeof(int32_t) * (nch + 1)));
+    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->nnz, A->rowptr, (int)nch, A->chunk_row);
+    LZ_LAUNCH_CHECK(ctx);
+    int *d_max = ctx->flags + 8;
+    LZ_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
+    k_max_row<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->rowptr, d_max);
+    LZ_LAUNCH_CHECK(ctx);
+    LZ_CUDA(cudaMemcpyAsync(&A->max_row_nnz, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+static lz_matrix *new_matrix(lz_ctx *ctx, int fmt, int64_t n_rows, int64_t n_cols, int64_t nnz)
+{
+    lz_matrix *A = new lz_matrix();
+    memset(A, 0, sizeof(*A));
+    A->ctx = ctx;
+    A->format = fmt;
+    A->n_rows = n_rows;
+    A->n_cols = n_cols;
+    A->nnz = nnz;
+    A->global_rows = n_rows;
+    return A;
+}
+
+static int check_dims(int64_t n_rows, int64_t n_cols, int64_t nnz)
+{
+    LZ_CHECK(n_rows > 0 && n_cols > 0 && nnz >= 0, LZ_ERR_INVALID, "bad matrix dimensions %lld x %lld, nnz %lld",
+             (long long)n_rows, (long long)n_cols, (long long)nnz);
+    LZ_CHECK(n_rows < 2147483647LL && n_cols < 2147483647LL && nnz < 2147483647LL, LZ_ERR_UNSUPPORTED,
+             "int32 index space exceeded (rows %lld, nnz %lld)", (long long)n_rows, (long long)nnz);
+    return LZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ELL helpers
+// ---------------------------------------------------------------------------------------------
+// count the structurally non-zero entries of every ELL row (layout 0: data[r + k*n], 1: data[w*r + k])
+__global__ void k_ell_count(int64_t n, int width, int layout, const double *__restrict__ data, int32_t *__restrict__ cnt)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int c = 0;
+    for (int k = 0; k < width; ++k) {
+        double v = layout == 0 ? data[r + (int64_t)k * n] : data[(int64_t)width * r + k];
+        c += (v != 0.0);
+    }
+    cnt[r] = c;
+}
+
+__global__ void k_ell_fill(int64_t n, int width, int layout, const double *__restrict__ data,
+                           const uint32_t *__restrict__ idx, const int32_t *__restrict__ rowptr,
+                           int32_t *__restrict__ colidx, double *__restrict__ vals)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int p = rowptr[r];
+    for (int k = 0; k < width; ++k) {
+        int64_t src = layout == 0 ? r + (int64_t)k * n : (int64_t)width * r + k;
+        double v = data[src];
+        if (v != 0.0) { colidx[p] = (int32_t)idx[src]; vals[p] = v; ++p; }
+    }
+}
+
+// column-major width-4 ELL -> row-interleaved (the job of lm::change_major, ell_kernels.hpp:99-121)
+__global__ void k_ell4_interleave(int64_t n, const double *__restrict__ data, const uint32_t *__restrict__ idx,
+                                  double *__restrict__ odata, uint32_t *__restrict__ oidx)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        odata[4 * r + k] = data[r + (int64_t)k * n];
+        oidx[4 * r + k] = idx[r + (int64_t)k * n];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generators
+// ---------------------------------------------------------------------------------------------
+__global__ void k_lap2d(int64_t nx, int64_t ny, int32_t *__restrict__ rowptr, int32_t *__restrict__ colidx,
+                        double *__restrict__ vals)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = nx * ny;
+    if (i > n) return;
+    int64_t y = i / nx, x = i - y * nx;
+    if (i == n) { y = ny; x = 0; }
+    // entries before row i = 5 i - (#rows<i on each of the four boundaries)
+    int64_t before = 5 * i - min(i, nx) - max((int64_t)0, i - (ny - 1) * nx) - (y + (x > 0)) - y;
+    rowptr[i] = (int32_t)before;
+    if (i == n) return;
+    int64_t p = before;
+    if (y > 0)      { colidx[p] = (int32_t)(i - nx); vals[p++] = -1.0; }
+    if (x > 0)      { colidx[p] = (int32_t)(i - 1);  vals[p++] = -1.0; }
+    colidx[p] = (int32_t)i; vals[p++] = 4.0;
+    if (x < nx - 1) { colidx[p] = (int32_t)(i + 1);  vals[p++] = -1.0; }
+    if (y < ny - 1) { colidx[p] = (int32_t)(i + nx); vals[p++] = -1.0; }
+}
+
+// rows [row0, row0 + n_local) of the nx*ny*nz 7-point Laplacian.  Column ids are written as
+// (global - col_shift) so a shard sees [lower halo | local | upper halo] as one index space.
+__global__ void k_lap3d(int64_t nx, int64_t ny, int64_t nz, int64_t row0, int64_t n_local, int64_t col_shift,
+                        int32_t *__restrict__ rowptr, int32_t *__restrict__ colidx, double *__restrict__ vals)
+{
+    int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li > n_local) return;
+    const int64_t sxy = nx * ny;
+    auto before = [&](int64_t i) -> int64_t {
+        int64_t z = i / sxy, rem = i - z * sxy, y = rem / nx, x = rem - y * nx;
+        if (i >= sxy * nz) { z = nz; y = 0; x = 0; }
+        int64_t bz0 = min(i, sxy), bz1 = max((int64_t)0, i - (nz - 1) * sxy);
+        int64_t by0 = z * nx + (y > 0 ? nx : x);
+        int64_t by1 = z * nx + (y == ny - 1 ? x : 0);
+        int64_t bx0 = z * ny + y + (x > 0), bx1 = z * ny + y;
+        return 7 * i - bz0 - bz1 - by0 - by1 - bx0 - bx1;
+    };
+    const int64_t i = row0 + li;
+    const int64_t base = before(row0);
+    int64_t p = before(i) - base;
+    rowptr[li] = (int32_t)p;
+    if (li == n_local) return;
+    int64_t z = i / sxy, rem = i - z * sxy, y = rem / nx, x = rem - y * nx;
+    const int64_t c = i - col_shift;
+    if (z > 0)      { colidx[p] = (int32_t)(c - sxy); vals[p++] = -1.0; }
+    if (y > 0)      { colidx[p] = (int32_t)(c - nx);  vals[p++] = -1.0; }
+    if (x > 0)      { colidx[p] = (int32_t)(c - 1);   vals[p++] = -1.0; }
+    colidx[p] = (int32_t)c; vals[p++] = 6.0;
+    if (x < nx - 1) { colidx[p] = (int32_t)(c + 1);   vals[p++] = -1.0; }
+    if (y < ny - 1) { colidx[p] = (int32_t)(c + nx);  vals[p++] = -1.0; }
+    if (z < nz - 1) { colidx[p] = (int32_t)(c + sxy); vals[p++] = -1.0; }
+}
+
+__global__ void k_start_vector(int64_t n, uint64_t seed, int64_t offset, double *__restrict__ v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = 2.0 * lz_u01(lz_splitmix64(seed ^ (uint64_t)(i + offset))) - 1.0;
+}
+
+__global__ void k_start_block(int64_t n, int b, int64_t ld, uint64_t seed, double *__restrict__ V)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < b; ++c) V[i + (int64_t)c * ld] = 2.0 * lz_u01(lz_splitmix64(seed ^ (uint64_t)(i * b + c))) - 1.0;
+}
+
+__global__ void k_fill(int64_t n, double value, double *__restrict__ x)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = value;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int finish_csr(lz_ctx *ctx, lz_matrix *A, lz_matrix **out)
+{
+    int s = build_schedule(ctx, A);
+    if (s != LZ_OK) { lz_matrix_destroy(A); return s; }
+    *out = A;
+    return LZ_OK;
+}
+
+int lz_gen_lap3d_rows(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int64_t row0, int64_t n_local,
+                      int64_t col_shift, int64_t n_cols, lz_matrix **out)
+{
+    const int64_t sxy = nx * ny;
+    // nnz of the slab, from the same closed form the kernel uses (host mirror)
+    auto before = [&](int64_t i) -> int64_t {
+        int64_t z = i / sxy, rem = i - z * sxy, y = rem / nx, x = rem - y * nx;
+        if (i >= sxy * nz) { z = nz; y = 0; x = 0; }
+        int64_t bz0 = i < sxy ? i : sxy, bz1 = i - (nz - 1) * sxy > 0 ? i - (nz - 1) * sxy : 0;
+        int64_t by0 = z * nx + (y > 0 ? nx : x);
+        int64_t by1 = z * nx + (y == ny - 1 ? x : 0);
+        int64_t bx0 = z * ny + y + (x > 0), bx1 = z * ny + y;
+        return 7 * i - bz0 - bz1 - by0 - by1 - bx0 - bx1;
+    };
+    const int64_t nnz = before(row0 + n_local) - before(row0);
+    LZ_TRY(check_dims(n_local, n_cols, nnz));
+    lz_matrix *A = new_matrix(ctx, LZ_FMT_CSR, n_local, n_cols, nnz);
+    A->owns = 1;
+    int32_t *rp, *ci;
+    double *va;
+    LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n_local + 1)));
+    LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * (nnz + 8)));
+    LZ_CUDA(cudaMalloc(&va, sizeof(double) * (nnz + 8)));
+    A->rowptr = rp; A->colidx = ci; A->vals = va;
+    k_lap3d<<<(unsigned)((n_local + 1 + 255) / 256), 256, 0, ctx->stream>>>(nx, ny, nz, row0, n_local, col_shift, rp, ci, va);
+    LZ_LAUNCH_CHECK(ctx);
+    return finish_csr(ctx, A, out);
+}
+
+extern "C" {
+
+int lz_csr_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *rowptr,
+                  const int32_t *colidx, const double *vals, lz_matrix **out)
+{
+    LZ_CHECK(ctx && out && rowptr && (nnz == 0 || (colidx && vals)), LZ_ERR_INVALID, "lz_csr_create: NULL argument");
+    LZ_TRY(check_dims(n_rows, n_cols, nnz));
+    LZ_CHECK(((uintptr_t)vals % 16 == 0) && ((uintptr_t)colidx % 8 == 0) && ((uintptr_t)rowptr % 4 == 0), LZ_ERR_INVALID,
+             "lz_csr_create: vals must be 16-byte and colidx 8-byte aligned (vectorised loads)");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    lz_matrix *A = new_matrix(ctx, LZ_FMT_CSR, n_rows, n_cols, nnz);
+    A->rowptr = rowptr; A->colidx = colidx; A->vals = vals;
+    return finish_csr(ctx, A, out);
+}
+
+int lz_csr_create_host(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *rowptr_host,
+                       const int32_t *colidx_host, const double *vals_host, lz_matrix **out)
+{
+    LZ_CHECK(ctx && out && rowptr_host && (nnz == 0 || (colidx_host && vals_host)), LZ_ERR_INVALID, "lz_csr_create_host: NULL argument");
+    LZ_TRY(check_dims(n_rows, n_cols, nnz));
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    lz_matrix *A = new_matrix(ctx, LZ_FMT_CSR, n_rows, n_cols, nnz);
+    A->owns = 1;
+    int32_t *rp, *ci;
+    double *va;
+    LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n_rows + 1)));
+    LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * (nnz + 8)));
+    LZ_CUDA(cudaMalloc(&va, sizeof(double) * (nnz + 8)));
+    A->rowptr = rp; A->colidx = ci; A->vals = va;
+    LZ_CUDA(cudaMemcpyAsync(rp, rowptr_host, sizeof(int32_t) * (n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(ci, colidx_host, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(va, vals_host, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    return finish_csr(ctx, A, out);
+}
+
+int lz_ell_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int width, int layout, const double *data,
+                  const uint32_t *idx, lz_matrix **out)
+{
+    LZ_CHECK(ctx && out && data && idx, LZ_ERR_INVALID, "lz_ell_create: NULL argument");
+    LZ_CHECK(width >= 1 && width <= 1024 && (layout == 0 || layout == 1), LZ_ERR_INVALID, "lz_ell_create: width %d layout %d", width, layout);
+    LZ_TRY(check_dims(n_rows, n_cols, n_rows * width));
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    const unsigned grid = (unsigned)((n_rows + 255) / 256);
+    if (width == 4) {
+        lz_matrix *A = new_matrix(ctx, LZ_FMT_ELL4, n_rows, n_cols, n_rows * 4);
+        if (layout == 1 && ((uintptr_t)data % 32 == 0) && ((uintptr_t)idx % 16 == 0)) {
+            A->ell_data = data; A->ell_idx = idx;
+        } else {
+            A->owns = 1;
+            double *od; uint32_t *oi;
+            LZ_CUDA(cudaMalloc(&od, sizeof(double) * n_rows * 4));
+            LZ_CUDA(cudaMalloc(&oi, sizeof(uint32_t) * n_rows * 4));
+            A->ell_data = od; A->ell_idx = oi;
+            if (layout == 0) {
+                k_ell4_interleave<<<grid, 256, 0, ctx->stream>>>(n_rows, data, idx, od, oi);
+                LZ_LAUNCH_CHECK(ctx);
+            } else {
+                LZ_CUDA(cudaMemcpyAsync(od, data, sizeof(double) * n_rows * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                LZ_CUDA(cudaMemcpyAsync(oi, idx, sizeof(uint32_t) * n_rows * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+        A->max_row_nnz = 4;
+        *out = A;
+        return LZ_OK;
+    }
+    // generic width: compact to CSR on the device (explicit zeros dropped, ELL column order kept)
+    lz_matrix *A = new_matrix(ctx, LZ_FMT_CSR, n_rows, n_cols, 0);
+    A->owns = 1;
+    int32_t *cnt, *rp;
+    LZ_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * (n_rows + 1)));
+    LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n_rows + 1)));
+    LZ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (n_rows + 1), ctx->stream));
+    k_ell_count<<<grid, 256, 0, ctx->stream>>>(n_rows, width, layout, data, cnt);
+    LZ_LAUNCH_CHECK(ctx);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
+    void *tmp;
+    LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
+    ctx->launches++;
+    int32_t nnz32 = 0;
+    LZ_CUDA(cudaMemcpyAsync(&nnz32, rp + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    LZ_CUDA(cudaFree(tmp));
+    LZ_CUDA(cudaFree(cnt));
+    A->nnz = nnz32;
+    A->rowptr = rp;
+    int32_t *ci; double *va;
+    LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * ((size_t)nnz32 + 8)));
+    LZ_CUDA(cudaMalloc(&va, sizeof(double) * ((size_t)nnz32 + 8)));
+    A->colidx = ci; A->vals = va;
+    k_ell_fill<<<grid, 256, 0, ctx->stream>>>(n_rows, width, layout, data, idx, rp, ci, va);
+    LZ_LAUNCH_CHECK(ctx);
+    return finish_csr(ctx, A, out);
+}
+
+int lz_matrix_destroy(lz_matrix *A)
+{
+    if (!A) return LZ_OK;
+    cudaSetDevice(A->ctx->device);
+    cudaStreamSynchronize(A->ctx->stream);
+    if (A->owns) {
+        cudaFree((void *)A->rowptr);
+        cudaFree((void *)A->colidx);
+        cudaFree((void *)A->vals);
+        cudaFree((void *)A->ell_data);
+        cudaFree((void *)A->ell_idx);
+    }
+    cudaFree(A->chunk_row);
+    delete A;
+    return LZ_OK;
+}
+
+int lz_matrix_info(const lz_matrix *A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz)
+{
+    LZ_CHECK(A, LZ_ERR_INVALID, "lz_matrix_info: A is NULL");
+    if (n_rows) *n_rows = A->n_rows;
+    if (n_cols) *n_cols = A->n_cols;
+    if (nnz) *nnz = A->nnz;
+    return LZ_OK;
+}
+
+int lz_matrix_csr_view(const lz_matrix *A, const int32_t **rowptr, const int32_t **colidx, const double **vals)
+{
+    LZ_CHECK(A, LZ_ERR_INVALID, "lz_matrix_csr_view: A is NULL");
+    if (rowptr) *rowptr = A->rowptr;
+    if (colidx) *colidx = A->colidx;
+    if (vals) *vals = A->vals;
+    return LZ_OK;
+}
+
+int lz_gen_laplacian2d(lz_ctx *ctx, int64_t nx, int64_t ny, lz_matrix **out)
+{
+    LZ_CHECK(ctx && out && nx >= 2 && ny >= 2, LZ_ERR_INVALID, "lz_gen_laplacian2d: bad arguments");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = nx * ny, nnz = 5 * n - 2 * nx - 2 * ny;
+    LZ_TRY(check_dims(n, n, nnz));
+    lz_matrix *A = new_matrix(ctx, LZ_FMT_CSR, n, n, nnz);
+    A->owns = 1;
+    int32_t *rp, *ci; double *va;
+    LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n + 1)));
+    LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * (nnz + 8)));
+    LZ_CUDA(cudaMalloc(&va, sizeof(double) * (nnz + 8)));
+    A->rowptr = rp; A->colidx = ci; A->vals = va;
+    k_lap2d<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(nx, ny, rp, ci, va);
+    LZ_LAUNCH_CHECK(ctx);
+    return finish_csr(ctx, A, out);
+}
+
+int lz_gen_laplacian3d(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, lz_matrix **out)
+{
+    LZ_CHECK(ctx && out && nx >= 2 && ny >= 2 && nz >= 2, LZ_ERR_INVALID, "lz_gen_laplacian3d: bad arguments");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    return lz_gen_lap3d_rows(ctx, nx, ny, nz, 0, nx * ny * nz, 0, nx * ny * nz, out);
+}
+
+int lz_gen_start_vector(lz_ctx *ctx, int64_t n, uint64_t seed, double *v)
+{
+    LZ_CHECK(ctx && v && n > 0, LZ_ERR_INVALID, "lz_gen_start_vector: bad arguments");
+    k_start_vector<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed, 0, v);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_gen_start_block(lz_ctx *ctx, int64_t n, int b, int64_t ld, uint64_t seed, double *V)
+{
+    LZ_CHECK(ctx && V && n > 0 && b > 0 && ld >= n, LZ_ERR_INVALID, "lz_gen_start_block: bad arguments");
+    k_start_block<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, b, ld, seed, V);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_fill(lz_ctx *ctx, int64_t n, double value, double *x)
+{
+    LZ_CHECK(ctx && (x || n == 0) && n >= 0, LZ_ERR_INVALID, "lz_fill: bad arguments");
+    if (n == 0) return LZ_OK;
+    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, value, x);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+}  // extern "C"
+
+// used by lz_multi.cu for the sharded start vector
+int lz_gen_start_vector_offset(lz_ctx *ctx, int64_t n, uint64_t seed, int64_t offset, double *v)
+{
+    k_start_vector<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed, offset, v);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}

@@ -1,0 +1,152 @@
+// lz_ctx.cu -- context, error state, raw memory entry points of the C-ABI.
+#include <stdarg.h>
+
+#include "lz_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void lz_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int lz_version(void) { return 100; }
+const char *lz_last_error(void) { return g_err; }
+
+int lz_ctx_create(int device, void *stream, lz_ctx **out)
+{
+    LZ_CHECK(out != nullptr, LZ_ERR_INVALID, "lz_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        lz_set_error("lz_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return LZ_ERR_CUDA;
+    }
+    LZ_CHECK(device >= 0 && device < count, LZ_ERR_INVALID, "lz_ctx_create: device %d out of range", device);
+    LZ_CUDA(cudaSetDevice(device));
+    lz_ctx *c = new lz_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    LZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        lz_set_error("lz_ctx_create: device %d is sm_%d%d; this build targets sm_100a only", device,
+                     prop.major, prop.minor);
+        delete c;
+        return LZ_ERR_UNSUPPORTED;
+    }
+    LZ_CUDA(cudaMalloc(&c->partials, sizeof(double) * LZ_PARTIALS_CAP));
+    LZ_CUDA(cudaMalloc(&c->tickets, sizeof(unsigned int) * LZ_TICKETS));
+    LZ_CUDA(cudaMalloc(&c->scalars, sizeof(double) * LZ_SCALARS));
+    LZ_CUDA(cudaMalloc(&c->flags, sizeof(int) * LZ_FLAGS));
+    LZ_CUDA(cudaMemset(c->tickets, 0, sizeof(unsigned int) * LZ_TICKETS));
+    LZ_CUDA(cudaMemset(c->scalars, 0, sizeof(double) * LZ_SCALARS));
+    LZ_CUDA(cudaMemset(c->flags, 0, sizeof(int) * LZ_FLAGS));
+    *out = c;
+    return LZ_OK;
+}
+
+int lz_ctx_destroy(lz_ctx *ctx)
+{
+    if (!ctx) return LZ_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) lz_comm_destroy(ctx);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->tickets);
+    cudaFree(ctx->scalars);
+    cudaFree(ctx->flags);
+    cudaFree(ctx->work);
+    cudaFree(ctx->basis);
+    delete ctx;
+    return LZ_OK;
+}
+
+int lz_ctx_sync(lz_ctx *ctx)
+{
+    LZ_CHECK(ctx, LZ_ERR_INVALID, "lz_ctx_sync: ctx is NULL");
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+int lz_ctx_device(const lz_ctx *ctx) { return ctx ? ctx->device : -1; }
+int64_t lz_ctx_launch_count(const lz_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lz_malloc(lz_ctx *ctx, size_t bytes, void **dptr)
+{
+    LZ_CHECK(ctx && dptr, LZ_ERR_INVALID, "lz_malloc: NULL argument");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    *dptr = nullptr;
+    if (bytes == 0) return LZ_OK;
+    LZ_CUDA(cudaMalloc(dptr, bytes));
+    return LZ_OK;
+}
+
+int lz_free(lz_ctx *ctx, void *dptr)
+{
+    LZ_CHECK(ctx, LZ_ERR_INVALID, "lz_free: ctx is NULL");
+    LZ_CUDA(cudaFree(dptr));
+    return LZ_OK;
+}
+
+int lz_memcpy(lz_ctx *ctx, void *dst, const void *src, size_t bytes, int kind)
+{
+    LZ_CHECK(ctx, LZ_ERR_INVALID, "lz_memcpy: ctx is NULL");
+    cudaMemcpyKind k = kind == LZ_H2D ? cudaMemcpyHostToDevice
+                       : kind == LZ_D2H ? cudaMemcpyDeviceToHost
+                                        : cudaMemcpyDeviceToDevice;
+    LZ_CHECK(kind >= LZ_H2D && kind <= LZ_D2D, LZ_ERR_INVALID, "lz_memcpy: bad kind %d", kind);
+    if (bytes == 0) return LZ_OK;
+    LZ_CUDA(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+int lz_memset(lz_ctx *ctx, void *dptr, int value, size_t bytes)
+{
+    LZ_CHECK(ctx, LZ_ERR_INVALID, "lz_memset: ctx is NULL");
+    LZ_CUDA(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return LZ_OK;
+}
+
+}  // extern "C"
+
+int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out)
+{
+    if (bytes > ctx->work_bytes) {
+        LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->work) LZ_CUDA(cudaFree(ctx->work));
+        ctx->work = nullptr;
+        ctx->work_bytes = 0;
+        size_t want = bytes + (bytes >> 3);
+        LZ_CUDA(cudaMalloc(&ctx->work, want));
+        ctx->work_bytes = want;
+    }
+    *out = ctx->work;
+    return LZ_OK;
+}
+
+int lz_ctx_basis(lz_ctx *ctx, int64_t ld, int cols, double **out)
+{
+    size_t bytes = sizeof(double) * (size_t)ld * (size_t)cols;
+    if (bytes > ctx->basis_bytes) {
+        LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->basis) LZ_CUDA(cudaFree(ctx->basis));
+        ctx->basis = nullptr;
+        ctx->basis_bytes = 0;
+        LZ_CUDA(cudaMalloc(&ctx->basis, bytes));
+        ctx->basis_bytes = bytes;
+    }
+    ctx->basis_ld = ld;
+    ctx->basis_cols = cols;
+    *out = ctx->basis;
+    return LZ_OK;
+}

@@ -1,0 +1,433 @@
+// lz_vector.cu -- single-vector path: SpMV entry point, BLAS-1 style reductions/updates, the
+// classical Gram-Schmidt sweeps against the stored Krylov basis, and the vector_lanczos driver.
+//
+// Reference being replaced: kernels/vector_kernels.hpp (do_dot, vector_update), objects/vector.hpp
+// (dot, l2_norm, sadd), utils/lib_utils.hpp:431-538 (cuBLAS level-1 wrappers) and
+// methods/vector_lanczos.hpp:8-67.  Everything here keeps its scalars on the device: no
+// cudaMalloc, no D2H copy and no host synchronisation inside the iteration loop.
+#include <math.h>
+
+#include "lz_spmv.cuh"
+
+#define VT 256                 // threads of the streaming kernels
+#define V_ROWS_PER_THREAD 8    // two 256-bit loads per thread per column
+
+// indices into ctx->scalars used by the drivers
+enum { S_NRM2 = 0, S_NRM2_BEFORE = 1, S_ALPHA_LOCAL = 2, S_TMP = 3, S_BETA_LAST = 4 };
+// indices into ctx->flags
+enum { F_BREAKDOWN = 0, F_SECOND_SWEEP = 1 };
+// tickets
+enum { T_SPMV = 0, T_DOT = 1, T_UPD = 2, T_PROJ = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// dot / nrm2 / axpby
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VT) k_dot(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                                            double *partials, unsigned int *ticket, double *out)
+{
+    __shared__ double red[32];
+    double acc = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * VT;
+    for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += stride) acc += x[i] * y[i];
+    acc = lz_block_sum<VT>(acc, red);
+    double total;
+    if (lz_grid_sum<VT, 1>(&acc, partials, ticket, red, &total) && threadIdx.x == 0) *out = total;
+}
+
+__global__ void __launch_bounds__(VT) k_axpby(int64_t n, double a, double *__restrict__ y, double b, const double *__restrict__ x)
+{
+    const int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x;
+    if (i < n) y[i] = __dadd_rn(__dmul_rn(a, y[i]), __dmul_rn(b, x[i]));   // vector_kernels.hpp:22-33
+}
+
+static inline unsigned stream_grid(const lz_ctx *ctx, int64_t n, int per_cta)
+{
+    int64_t want = (n + per_cta - 1) / per_cta;
+    int64_t cap = (int64_t)ctx->sm_count * 8;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+static int dot_async(lz_ctx *ctx, int64_t n, const double *x, const double *y, double *out_dev)
+{
+    k_dot<<<stream_grid(ctx, n, VT * 4), VT, 0, ctx->stream>>>(n, x, y, ctx->partials, ctx->tickets + T_DOT, out_dev);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lanczos pass B:  w -= alpha_j * q_j  (q_j = u_cur * invb[j]);  nrm2 = ||w||^2 in the epilogue
+// (methods/vector_lanczos.hpp:60 and :44 of the next trip, fused).
+// The last CTA finalises beta_{j+1} = sqrt(nrm2), invb[j+1] and the breakdown flag.
+// ---------------------------------------------------------------------------------------------
+struct LzFinal {
+    double *beta;        // beta[j+1] <- sqrt(total)            (NULL: skip)
+    double *invb;        // invb[j+1] <- 1 / beta[j+1]
+    double *nrm2_out;    // raw total
+    int *flags;
+    int jn;              // j + 1
+    int finalize;        // 0: only publish the raw local total (sharded runs all-reduce it first)
+};
+
+__device__ __forceinline__ void lz_finalize_beta(const LzFinal &f, double total)
+{
+    *f.nrm2_out = total;
+    if (!f.finalize) return;
+    const double b = sqrt(total);
+    if (f.beta) f.beta[f.jn] = b;
+    f.invb[f.jn] = 1.0 / b;
+    if (!(isfinite(total)) || total == 0.0) atomicMin(f.flags + F_BREAKDOWN, f.jn);   // vector.hpp:233-244
+}
+
+__global__ void __launch_bounds__(VT)
+k_pass_b(int64_t n, double *__restrict__ w, const double *__restrict__ u_cur, const double *__restrict__ alpha,
+         const double *__restrict__ invb, int j, double *partials, unsigned int *ticket, const LzFinal fin)
+{
+    __shared__ double red[32];
+    const double na = -alpha[j], sx = invb[j];
+    double acc = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * VT;
+    for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += stride) {
+        const double v = __dadd_rn(w[i], __dmul_rn(na, __dmul_rn(u_cur[i], sx)));
+        w[i] = v;
+        acc += v * v;
+    }
+    acc = lz_block_sum<VT>(acc, red);
+    double total;
+    if (lz_grid_sum<VT, 1>(&acc, partials, ticket, red, &total) && threadIdx.x == 0) lz_finalize_beta(fin, total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Classical Gram-Schmidt against the stored basis V (column j at V + j*ld, ld % 4 == 0).
+//   k_cgs_project : c[k] = V[:,k] . w      for k < K   (deterministic two-stage reduction)
+//   k_cgs_update  : w -= V[:, :K] c ;  ||w||^2 in the epilogue
+// Both stream V exactly once with 256-bit loads; each thread keeps 8 rows of w in registers and
+// walks the K columns, so w itself is read once per sweep.
+// ---------------------------------------------------------------------------------------------
+#define CGS_TILE (VT * V_ROWS_PER_THREAD)   // rows per CTA trip
+#define CGS_UNROLL 4
+
+__global__ void __launch_bounds__(VT)
+k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ld, const double *__restrict__ w,
+              double *__restrict__ cpart /* gridDim.x * K */, const int *__restrict__ flags, int need_flag)
+{
+    extern __shared__ double csm[];           // [VT/32][K] per-warp partial coefficients
+    if (need_flag && flags[F_SECOND_SWEEP] == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *mine = csm + (size_t)warp * K;
+    for (int k = lane; k < K; k += 32) mine[k] = 0.0;
+    __syncwarp();
+    const int64_t n_tiles = (n + CGS_TILE - 1) / CGS_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * CGS_TILE + (int64_t)warp * (32 * V_ROWS_PER_THREAD) + lane * 4;
+        // rows base..base+3 and base+128..base+131 of this warp's 256-row slice
+        const int64_t ra = base, rb = base + 128;
+        double wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+        const bool fa = ra + 3 < n, fb = rb + 3 < n;
+        if (fa) lz_ld256(w + ra, wa[0], wa[1], wa[2], wa[3]);
+        else for (int t = 0; t < 4; ++t) if (ra + t < n) wa[t] = w[ra + t];
+        if (fb) lz_ld256(w + rb, wb[0], wb[1], wb[2], wb[3]);
+        else for (int t = 0; t < 4; ++t) if (rb + t < n) wb[t] = w[rb + t];
+        int k = 0;
+        if (fa && fb) {
+            for (; k + CGS_UNROLL <= K; k += CGS_UNROLL) {
+                double va[CGS_UNROLL][4], vb[CGS_UNROLL][4];
+#pragma unroll
+                for (int u = 0; u < CGS_UNROLL; ++u) {
+                    const double *col = V + (int64_t)(k + u) * ld;
+                    lz_ld256_stream(col + ra, va[u][0], va[u][1], va[u][2], va[u][3]);
+                    lz_ld256_stream(col + rb, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
+                }
+#pragma unroll
+                for (int u = 0; u < CGS_UNROLL; ++u) {
+                    double s = va[u][0] * wa[0];
+                    s = fma(va[u][1], wa[1], s); s = fma(va[u][2], wa[2], s); s = fma(va[u][3], wa[3], s);
+                    s = fma(vb[u][0], wb[0], s); s = fma(vb[u][1], wb[1], s);
+                    s = fma(vb[u][2], wb[2], s); s = fma(vb[u][3], wb[3], s);
+                    s = lz_warp_sum(s);
+                    if (lane == 0) mine[k + u] += s;
+                }
+            }
+        }
+        for (; k < K; ++k) {
+            const double *col = V + (int64_t)k * ld;
+            double s = 0.0;
+            for (int t = 0; t < 4; ++t) {
+                if (ra + t < n) s = fma(col[ra + t], wa[t], s);
+                if (rb + t < n) s = fma(col[rb + t], wb[t], s);
+            }
+            s = lz_warp_sum(s);
+            if (lane == 0) mine[k] += s;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += VT) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < VT / 32; ++wv) s += csm[(size_t)wv * K + k];
+        cpart[(size_t)blockIdx.x * K + k] = s;
+    }
+}
+
+// c[k] = sum over CTAs of cpart[cta][k]  (fixed order); optionally all K in one small launch
+__global__ void __launch_bounds__(VT)
+k_cgs_reduce(int K, int n_parts, const double *__restrict__ cpart, double *__restrict__ c,
+             const int *__restrict__ flags, int need_flag)
+{
+    if (need_flag && flags[F_SECOND_SWEEP] == 0) return;
+    __shared__ double red[32];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (int p = threadIdx.x; p < n_parts; p += VT) s += cpart[(size_t)p * K + k];
+    s = lz_block_sum<VT>(s, red);
+    if (threadIdx.x == 0) c[k] = s;
+}
+
+__global__ void __launch_bounds__(VT)
+k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ld, double *__restrict__ w,
+             const double *__restrict__ c, double *partials, unsigned int *ticket, const LzFinal fin,
+             int *flags, int need_flag, int dgks_test, const double *nrm2_before)
+{
+    extern __shared__ double csm[];           // c[K]
+    __shared__ double red[32];
+    if (need_flag && flags[F_SECOND_SWEEP] == 0) return;
+    for (int k = threadIdx.x; k < K; k += VT) csm[k] = c[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    const int64_t n_tiles = (n + CGS_TILE - 1) / CGS_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * CGS_TILE + (int64_t)warp * (32 * V_ROWS_PER_THREAD) + lane * 4;
+        const int64_t ra = base, rb = base + 128;
+        double wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+        const bool fa = ra + 3 < n, fb = rb + 3 < n;
+        if (fa) lz_ld256(w + ra, wa[0], wa[1], wa[2], wa[3]);
+        else for (int t = 0; t < 4; ++t) if (ra + t < n) wa[t] = w[ra + t];
+        if (fb) lz_ld256(w + rb, wb[0], wb[1], wb[2], wb[3]);
+        else for (int t = 0; t < 4; ++t) if (rb + t < n) wb[t] = w[rb + t];
+        int k = 0;
+        if (fa && fb) {
+            for (; k + CGS_UNROLL <= K; k += CGS_UNROLL) {
+                double va[CGS_UNROLL][4], vb[CGS_UNROLL][4];
+#pragma unroll
+                for (int u = 0; u < CGS_UNROLL; ++u) {
+                    const double *col = V + (int64_t)(k + u) * ld;
+                    lz_ld256_stream(col + ra, va[u][0], va[u][1], va[u][2], va[u][3]);
+                    lz_ld256_stream(col + rb, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
+                }
+#pragma unroll
+                for (int u = 0; u < CGS_UNROLL; ++u) {
+                    const double ck = -csm[k + u];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { wa[t] = fma(ck, va[u][t], wa[t]); wb[t] = fma(ck, vb[u][t], wb[t]); }
+                }
+            }
+        }
+        for (; k < K; ++k) {
+            const double *col = V + (int64_t)k * ld;
+            const double ck = -csm[k];
+            for (int t = 0; t < 4; ++t) {
+                if (ra + t < n) wa[t] = fma(ck, col[ra + t], wa[t]);
+                if (rb + t < n) wb[t] = fma(ck, col[rb + t], wb[t]);
+            }
+        }
+        if (fa) lz_st256(w + ra, wa[0], wa[1], wa[2], wa[3]);
+        else for (int t = 0; t < 4; ++t) if (ra + t < n) w[ra + t] = wa[t];
+        if (fb) lz_st256(w + rb, wb[0], wb[1], wb[2], wb[3]);
+        else for (int t = 0; t < 4; ++t) if (rb + t < n) w[rb + t] = wb[t];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { acc = fma(wa[t], wa[t], acc); acc = fma(wb[t], wb[t], acc); }
+    }
+    acc = lz_block_sum<VT>(acc, red);
+    double total;
+    if (lz_grid_sum<VT, 1>(&acc, partials, ticket, red, &total) && threadIdx.x == 0) {
+        lz_finalize_beta(fin, total);
+        // DGKS: a second sweep is needed only if this one removed a large part of w
+        if (dgks_test) flags[F_SECOND_SWEEP] = (total < 0.5 * (*nrm2_before)) ? 1 : 0;
+    }
+}
+
+// beta0 = ||b||: finalises beta[0], invb[0]
+__global__ void k_finalize_first(const double *nrm2, double *beta, double *invb, int *flags)
+{
+    const double t = *nrm2, b = sqrt(t);
+    beta[0] = b;
+    invb[0] = 1.0 / b;
+    flags[F_BREAKDOWN] = (!isfinite(t) || t == 0.0) ? 0 : 0x7fffffff;
+    flags[F_SECOND_SWEEP] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct LzCgs {
+    double *V; int64_t ld; double *cpart; double *c; unsigned grid;
+};
+
+// one CGS sweep of w against the first K basis columns; the update's epilogue finalises beta[jn]
+static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin,
+                     int need_flag, int dgks_test)
+{
+    const size_t smem_p = sizeof(double) * (VT / 32) * (size_t)K;
+    k_cgs_project<<<g.grid, VT, smem_p, ctx->stream>>>(n, K, g.V, g.ld, w, g.cpart, ctx->flags, need_flag);
+    LZ_LAUNCH_CHECK(ctx);
+    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)g.grid, g.cpart, g.c, ctx->flags, need_flag);
+    LZ_LAUNCH_CHECK(ctx);
+    k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
+        n, K, g.V, g.ld, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test,
+        ctx->scalars + S_NRM2_BEFORE);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+__global__ void k_copy_scalar(const double *src, double *dst) { *dst = *src; }
+
+// The single-vector driver.  Device arrays: alpha[m], beta[m+1], invb[m+1].
+static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
+                               double *alpha, double *beta, double *invb, double *q)
+{
+    const int64_t n = A->n_rows;
+    LZ_CHECK(A->n_cols == n, LZ_ERR_INVALID, "lz_vector_lanczos: operator must be square (%lld x %lld)", (long long)n, (long long)A->n_cols);
+    LZ_CHECK(lc >= 0 && lc < n, LZ_ERR_INVALID, "lz_vector_lanczos: lc %lld out of range", (long long)lc);
+    LZ_CHECK(reorth >= LZ_REORTH_NONE && reorth <= LZ_REORTH_FULL_DGKS, LZ_ERR_INVALID, "lz_vector_lanczos: reorth mode %d", reorth);
+    const int64_t ld = round_up(n, 4);
+    // three rotating work vectors (the reference's q0, q1, w: test_lanczos.cu:57-59)
+    LzCgs g = {nullptr, ld, nullptr, nullptr, 0};
+    const unsigned cgs_grid = stream_grid(ctx, n, CGS_TILE) < (unsigned)(ctx->sm_count * 2)
+                                  ? stream_grid(ctx, n, CGS_TILE) : (unsigned)(ctx->sm_count * 2);
+    size_t work_bytes = sizeof(double) * (size_t)ld * 3;
+    if (reorth) work_bytes += sizeof(double) * ((size_t)cgs_grid * m + m + 8);
+    void *work;
+    LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
+    double *u_prev = (double *)work, *u_cur = u_prev + ld, *w = u_cur + ld;
+    if (reorth) {
+        LZ_CHECK(sizeof(double) * (VT / 32) * (size_t)m <= 200 * 1024, LZ_ERR_UNSUPPORTED,
+                 "lz_vector_lanczos: m = %d too large for the projection kernel's shared memory", m);
+        g.cpart = w + ld;
+        g.c = g.cpart + (size_t)cgs_grid * m;
+        g.grid = cgs_grid;
+        LZ_TRY(lz_ctx_basis(ctx, ld, m, &g.V));
+        static bool attr_set = false;
+        if (!attr_set) {
+            LZ_CUDA(cudaFuncSetAttribute(k_cgs_project, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+    }
+    LZ_CUDA(cudaMemcpyAsync(u_cur, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // beta[0] = ||b||  (vector_lanczos.hpp:21)
+    LZ_TRY(dot_async(ctx, n, b, b, ctx->scalars + S_NRM2));
+    k_finalize_first<<<1, 1, 0, ctx->stream>>>(ctx->scalars + S_NRM2, beta, invb, ctx->flags);
+    LZ_LAUNCH_CHECK(ctx);
+
+    for (int j = 0; j < m; ++j) {
+        LzPassA pa;
+        pa.x_own = u_cur; pa.u_prev = u_prev; pa.invb = invb; pa.beta = beta;
+        pa.alpha_out = alpha + j; pa.alpha_partial = ctx->scalars + S_ALPHA_LOCAL;
+        pa.vcol = reorth ? g.V + (size_t)j * ld : nullptr;
+        pa.qout = q ? q + j : nullptr;
+        pa.lc = lc; pa.j = j; pa.first = (j == 0);
+        pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
+        LZ_TRY(lz_launch_spmv<LZ_EPI_LANCZOS>(ctx, A, u_cur, w, pa));          // :51,:54,:57
+        LzFinal fin = {beta, invb, ctx->scalars + (reorth ? S_NRM2_BEFORE : S_NRM2), ctx->flags, j + 1, 1};
+        k_pass_b<<<stream_grid(ctx, n, VT * 4), VT, 0, ctx->stream>>>(n, w, u_cur, alpha, invb, j, ctx->partials,
+                                                                      ctx->tickets + T_DOT, fin);   // :60,:44
+        LZ_LAUNCH_CHECK(ctx);
+        if (reorth) {
+            LzFinal f2 = {beta, invb, ctx->scalars + S_NRM2, ctx->flags, j + 1, 1};
+            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, reorth == LZ_REORTH_FULL_DGKS));
+            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, reorth == LZ_REORTH_FULL_DGKS, 0));
+        }
+        double *t = u_prev; u_prev = u_cur; u_cur = w; w = t;                  // :62 (pointer rotation, no copy)
+    }
+    k_copy_scalar<<<1, 1, 0, ctx->stream>>>(beta + m, ctx->scalars + S_BETA_LAST);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+extern "C" {
+
+int lz_spmv(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y)
+{
+    LZ_CHECK(ctx && A && x && y, LZ_ERR_INVALID, "lz_spmv: NULL argument");
+    LZ_CHECK(x != y, LZ_ERR_INVALID, "lz_spmv: x and y must not alias");
+    LzPassA none;
+    memset(&none, 0, sizeof(none));
+    return lz_launch_spmv<LZ_EPI_PLAIN>(ctx, A, x, y, none);
+}
+
+int lz_dot(lz_ctx *ctx, int64_t n, const double *x, const double *y, double *result_host)
+{
+    LZ_CHECK(ctx && x && y && result_host && n > 0, LZ_ERR_INVALID, "lz_dot: bad arguments");
+    LZ_TRY(dot_async(ctx, n, x, y, ctx->scalars + S_TMP));
+    LZ_CUDA(cudaMemcpyAsync(result_host, ctx->scalars + S_TMP, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+int lz_nrm2(lz_ctx *ctx, int64_t n, const double *x, double *result_host)
+{
+    double s = 0.0;
+    LZ_TRY(lz_dot(ctx, n, x, x, &s));
+    if (!isfinite(s)) {
+        lz_set_error("lz_nrm2: the norm is not finite");     // vector.hpp:239-241 aborts here
+        return LZ_ERR_BREAKDOWN;
+    }
+    *result_host = sqrt(s);
+    return LZ_OK;
+}
+
+int lz_axpby(lz_ctx *ctx, int64_t n, double a, double *y, double b, const double *x)
+{
+    LZ_CHECK(ctx && x && y && n > 0, LZ_ERR_INVALID, "lz_axpby: bad arguments");
+    k_axpby<<<(unsigned)((n + VT - 1) / VT), VT, 0, ctx->stream>>>(n, a, y, b, x);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_vector_lanczos_async(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
+                            double *alpha_dev, double *beta_dev, double *q)
+{
+    LZ_CHECK(ctx && A && b && alpha_dev && beta_dev && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos_async: bad arguments");
+    LZ_CHECK(2 * m + 2 + 16 <= LZ_SCALARS, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    // beta needs m+1 slots and invb m+1 slots: keep them in the context's scalar bank
+    double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1);
+    LZ_TRY(vector_lanczos_core(ctx, A, b, m, lc, reorth, alpha_dev, beta_i, invb, q));
+    LZ_CUDA(cudaMemcpyAsync(beta_dev, beta_i, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    return LZ_OK;
+}
+
+int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
+                      double *alpha_host, double *beta_host, double *q, int *steps_done)
+{
+    LZ_CHECK(ctx && A && b && alpha_host && beta_host && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos: bad arguments");
+    LZ_CHECK(3 * m + 3 + 16 <= LZ_SCALARS, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1), *alpha_i = invb + (m + 1);
+    LZ_TRY(vector_lanczos_core(ctx, A, b, m, lc, reorth, alpha_i, beta_i, invb, q));
+    int flag = 0;
+    LZ_CUDA(cudaMemcpyAsync(alpha_host, alpha_i, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(beta_host, beta_i, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(&flag, ctx->flags + F_BREAKDOWN, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    // flag = first j whose beta_j is zero / non-finite: coefficients alpha[0..j-1], beta[0..j-1] are valid
+    int done = (flag < m) ? flag : m;
+    if (steps_done) *steps_done = done;
+    if (done < m) {
+        lz_set_error("lz_vector_lanczos: breakdown, beta[%d] is zero or not finite", done);
+        return LZ_ERR_BREAKDOWN;
+    }
+    return LZ_OK;
+}
+
+int lz_vector_basis(lz_ctx *ctx, const double **V, int64_t *ld, int *cols)
+{
+    LZ_CHECK(ctx && ctx->basis, LZ_ERR_INVALID, "lz_vector_basis: no basis has been built on this context");
+    if (V) *V = ctx->basis;
+    if (ld) *ld = ctx->basis_ld;
+    if (cols) *cols = ctx->basis_cols;
+    return LZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+"""ctypes binding of liblanczos_b200.so (include/lanczos_b200.h) for tests, bench.py and smoke().
+
+The product is the C-ABI library and the C++ mirror under host/; this module only hands torch
+device pointers to it.  There is no CPU fallback: if the CUDA library has not been built the import
+of `lib()` raises, and every compute entry point fails without a B200.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblanczos_b200.so")
+_LIB = None
+
+LZ_OK = 0
+REORTH_NONE, REORTH_FULL, REORTH_FULL_DGKS = 0, 1, 2
+H2D, D2H, D2D = 1, 2, 3
+
+
+class LanczosError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("lanczos_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("liblanczos_b200.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u64, dbl, sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_double, C.c_size_t
+    P = C.POINTER
+    sig = {
+        "lz_version": (i32, []),
+        "lz_last_error": (C.c_char_p, []),
+        "lz_ctx_create": (i32, [i32, vp, P(vp)]),
+        "lz_ctx_destroy": (i32, [vp]),
+        "lz_ctx_sync": (i32, [vp]),
+        "lz_ctx_device": (i32, [vp]),
+        "lz_ctx_launch_count": (i64, [vp]),
+        "lz_malloc": (i32, [vp, sz, P(vp)]),
+        "lz_free": (i32, [vp, vp]),
+        "lz_memcpy": (i32, [vp, vp, vp, sz, i32]),
+        "lz_memset": (i32, [vp, vp, i32, sz]),
+        "lz_fill": (i32, [vp, i64, dbl, vp]),
+        "lz_csr_create": (i32, [vp, i64, i64, i64, vp, vp, vp, P(vp)]),
+        "lz_csr_create_host": (i32, [vp, i64, i64, i64, vp, vp, vp, P(vp)]),
+        "lz_ell_create": (i32, [vp, i64, i64, i32, i32, vp, vp, P(vp)]),
+        "lz_matrix_destroy": (i32, [vp]),
+        "lz_matrix_info": (i32, [vp, P(i64), P(i64), P(i64)]),
+        "lz_matrix_csr_view": (i32, [vp, P(vp), P(vp), P(vp)]),
+        "lz_gen_laplacian2d": (i32, [vp, i64, i64, P(vp)]),
+        "lz_gen_laplacian3d": (i32, [vp, i64, i64, i64, P(vp)]),
+        "lz_gen_start_vector": (i32, [vp, i64, u64, vp]),
+        "lz_gen_start_block": (i32, [vp, i64, i32, i64, u64, vp]),
+        "lz_spmv": (i32, [vp, vp, vp, vp]),
+        "lz_spmm": (i32, [vp, vp, i32, vp, i64, vp, i64]),
+        "lz_dot": (i32, [vp, i64, vp, vp, P(dbl)]),
+        "lz_nrm2": (i32, [vp, i64, vp, P(dbl)]),
+        "lz_axpby": (i32, [vp, i64, dbl, vp, dbl, vp]),
+        "lz_mm_tt": (i32, [vp, i64, i32, vp, i64, vp]),
+        "lz_mm_tt2": (i32, [vp, i64, i32, vp, i64, vp, i64, vp]),
+        "lz_mm_ts": (i32, [vp, i64, i32, dbl, dbl, vp, i64, vp, vp, i64]),
+        "lz_sqrtm": (i32, [vp, i32, vp, vp]),
+        "lz_copy_row": (i32, [vp, i64, i32, vp, i64, vp, i64]),
+        "lz_assemble_T": (i32, [vp, i32, i32, vp, vp, vp]),
+        "lz_vector_lanczos": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp, P(i32)]),
+        "lz_vector_lanczos_async": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp]),
+        "lz_vector_basis": (i32, [vp, P(vp), P(i64), P(i32)]),
+        "lz_block_lanczos": (i32, [vp, vp, vp, i64, i32, i32, i64, i32, vp, vp, vp]),
+        "lz_ritz": (i32, [i32, i32, vp, vp, vp, i32, vp, vp]),
+        "lz_comm_unique_id": (i32, [vp]),
+        "lz_comm_init": (i32, [vp, i32, i32, vp]),
+        "lz_comm_destroy": (i32, [vp]),
+        "lz_partition_rows": (i32, [i64, i32, i32, P(i64), P(i64)]),
+        "lz_gen_laplacian3d_shard": (i32, [vp, i64, i64, i64, i32, i32, P(vp)]),
+        "lz_gen_laplacian2d_shard": (i32, [vp, i64, i64, i32, i32, P(vp)]),
+        "lz_vector_lanczos_sharded": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._signatures = sig
+    _LIB = L
+    return L
+
+
+def check(status):
+    if status != LZ_OK:
+        raise LanczosError(status, lib().lz_last_error().decode(errors="replace"))
+
+
+def _ptr(t):
+    """device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        check(lib().lz_ctx_create(int(device), stream, C.byref(self.h)))
+        self.device = device
+
+    def sync(self):
+        check(lib().lz_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(lib().lz_ctx_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            lib().lz_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Matrix:
+    """A sparse operator resident on the device (lz_matrix)."""
+
+    def __init__(self, ctx, handle, keep=()):
+        self.ctx, self.h, self._keep = ctx, handle, keep
+        nr, nc, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().lz_matrix_info(self.h, C.byref(nr), C.byref(nc), C.byref(nnz)))
+        self.n_rows, self.n_cols, self.nnz = nr.value, nc.value, nnz.value
+
+    @classmethod
+    def from_csr(cls, ctx, rowptr, colidx, vals, n_cols=None):
+        """torch CUDA tensors (int32, int32, float64): borrowed."""
+        n = rowptr.numel() - 1
+        h = C.c_void_p()
+        check(lib().lz_csr_create(ctx.h, n, n_cols or n, vals.numel(), _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(h)))
+        return cls(ctx, h, (rowptr, colidx, vals))
+
+    @classmethod
+    def from_csr_host(cls, ctx, rowptr, colidx, vals, n_cols=None):
+        """numpy arrays (or pinned torch CPU tensors): copied to the device by the library."""
+        n = len(rowptr) - 1
+        h = C.c_void_p()
+        check(lib().lz_csr_create_host(ctx.h, n, n_cols or n, len(vals), _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_ell(cls, ctx, n_rows, n_cols, width, layout, data, idx):
+        """torch CUDA tensors: data float64, idx int32/uint32 storage (reference Ell_matrix arrays)."""
+        h = C.c_void_p()
+        check(lib().lz_ell_create(ctx.h, n_rows, n_cols, width, layout, _ptr(data), _ptr(idx), C.byref(h)))
+        return cls(ctx, h, (data, idx))
+
+    @classmethod
+    def laplacian2d(cls, ctx, nx, ny):
+        h = C.c_void_p()
+        check(lib().lz_gen_laplacian2d(ctx.h, nx, ny, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def laplacian3d(cls, ctx, nx, ny, nz):
+        h = C.c_void_p()
+        check(lib().lz_gen_laplacian3d(ctx.h, nx, ny, nz, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def laplacian3d_shard(cls, ctx, nx, ny, nz, world_size, rank):
+        h = C.c_void_p()
+        check(lib().lz_gen_laplacian3d_shard(ctx.h, nx, ny, nz, world_size, rank, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def laplacian2d_shard(cls, ctx, nx, ny, world_size, rank):
+        h = C.c_void_p()
+        check(lib().lz_gen_laplacian2d_shard(ctx.h, nx, ny, world_size, rank, C.byref(h)))
+        return cls(ctx, h)
+
+    def csr_to_host(self):
+        """(rowptr, colidx, vals) numpy copies of the device CSR arrays."""
+        rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().lz_matrix_csr_view(self.h, C.byref(rp), C.byref(ci), C.byref(va)))
+        out = (np.empty(self.n_rows + 1, np.int32), np.empty(self.nnz, np.int32), np.empty(self.nnz, np.float64))
+        for dst, src in zip(out, (rp, ci, va)):
+            if dst.nbytes:
+                check(lib().lz_memcpy(self.ctx.h, dst.ctypes.data, src, dst.nbytes, D2H))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().lz_matrix_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ thin operator wrappers
+
+def spmv(ctx, A, x, y):
+    check(lib().lz_spmv(ctx.h, A.h, _ptr(x), _ptr(y)))
+
+
+def spmm(ctx, A, b, X, ldx, Y, ldy):
+    check(lib().lz_spmm(ctx.h, A.h, b, _ptr(X), ldx, _ptr(Y), ldy))
+
+
+def dot(ctx, x, y):
+    r = C.c_double()
+    check(lib().lz_dot(ctx.h, x.numel(), _ptr(x), _ptr(y), C.byref(r)))
+    return r.value
+
+
+def nrm2(ctx, x):
+    r = C.c_double()
+    check(lib().lz_nrm2(ctx.h, x.numel(), _ptr(x), C.byref(r)))
+    return r.value
+
+
+def axpby(ctx, a, y, b, x):
+    check(lib().lz_axpby(ctx.h, y.numel(), a, _ptr(y), b, _ptr(x)))
+
+
+def vector_lanczos(ctx, A, b, m, lc=0, reorth=REORTH_NONE, q=None):
+    """Returns (alpha, beta) as numpy arrays (host, like test_lanczos.cu:66-67) and steps done."""
+    alpha, beta = np.zeros(m), np.zeros(m)
+    steps = C.c_int(0)
+    st = lib().lz_vector_lanczos(ctx.h, A.h, _ptr(b), m, lc, reorth, alpha.ctypes.data, beta.ctypes.data, _ptr(q), C.byref(steps))
+    if st != LZ_OK and st != -4:
+        check(st)
+    return alpha, beta, steps.value
+
+
+def vector_lanczos_async(ctx, A, b, m, alpha_dev, beta_dev, lc=0, reorth=REORTH_NONE, q=None):
+    check(lib().lz_vector_lanczos_async(ctx.h, A.h, _ptr(b), m, lc, reorth, _ptr(alpha_dev), _ptr(beta_dev), _ptr(q)))
+
+
+def block_lanczos(ctx, A, B, ldb, bw, m, alpha, beta, q, lc=0, reorth=REORTH_NONE):
+    check(lib().lz_block_lanczos(ctx.h, A.h, _ptr(B), ldb, bw, m, lc, reorth, _ptr(alpha), _ptr(beta), _ptr(q)))
+
+
+def ritz(alpha, beta, k, bw=1, beta_last=None):
+    alpha = np.ascontiguousarray(alpha, np.float64)
+    beta = np.ascontiguousarray(beta, np.float64)
+    m = alpha.size // (bw * bw)
+    theta, resid = np.zeros(k), np.zeros(k)
+    bl = None if beta_last is None else np.ascontiguousarray(beta_last, np.float64)
+    check(lib().lz_ritz(m, bw, alpha.ctypes.data, beta.ctypes.data, None if bl is None else bl.ctypes.data, k,
+                        theta.ctypes.data, resid.ctypes.data))
+    return theta, resid

@@ -1,0 +1,196 @@
+/*
+ * lanczos_b200.h -- C-ABI of the B200-native (sm_100a) single-vector / block Lanczos path.
+ *
+ * Drop-in boundary for the hot path of ibrohimmn1994/GPU-implementation-of-signle-and-block-Lanczos:
+ * every entry point names the reference interface (file:line under source/) it replaces.  The
+ * reference has no FFI of its own (one nvcc translation unit of headers); the C++ mirror under
+ * gpu-implementation-of-signle-and-block-lanczos_b200/host/ keeps the reference's class and function
+ * names and forwards raw pointers here.  See INTEGRATION.md for the binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; all array arguments are DEVICE pointers unless the name ends in _host;
+ *   - buffers passed in are BORROWED (never freed, never reallocated); scratch belongs to the
+ *     lz_ctx and is (re)sized outside timed regions by the *_workspace / first call;
+ *   - dense blocks use the reference layout: column-major, leading dimension ld (dense_matrix.hpp:9);
+ *   - every call returns LZ_OK (0) or a negative status; lz_last_error() gives the message
+ *     (reference policy: AssertCuda aborts, CUBLAS_CHECK throws -- utils/common.hpp:83-112; the C++
+ *     mirror maps non-zero statuses back onto abort/throw);
+ *   - calls enqueue on the context's stream and return without synchronising unless they hand a
+ *     result back in host memory; one host thread per context;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     LZ_ERR_CUDA.
+ */
+#ifndef LANCZOS_B200_H
+#define LANCZOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZ_OK 0
+#define LZ_ERR_INVALID (-1)   /* bad argument                                   */
+#define LZ_ERR_CUDA (-2)      /* CUDA runtime / launch failure (AssertCuda)     */
+#define LZ_ERR_ALLOC (-3)     /* device allocation failed                       */
+#define LZ_ERR_BREAKDOWN (-4) /* non-finite norm (vector.hpp:233-244 aborts)    */
+#define LZ_ERR_COMM (-5)      /* NCCL / rendezvous failure                      */
+#define LZ_ERR_UNSUPPORTED (-6)
+
+/* reorthogonalisation modes (extension: the reference has none) */
+#define LZ_REORTH_NONE 0
+#define LZ_REORTH_FULL 1      /* classical Gram-Schmidt, always two sweeps (CGS2)             */
+#define LZ_REORTH_FULL_DGKS 2 /* second sweep only when the first one removed > 1 - 1/sqrt2   */
+
+/* lz_memcpy kinds */
+#define LZ_H2D 1
+#define LZ_D2H 2
+#define LZ_D2D 3
+
+typedef struct lz_ctx lz_ctx;       /* device, stream, scratch, (optional) communicator */
+typedef struct lz_matrix lz_matrix; /* a sparse operator resident on the device         */
+
+/* ---- library / context ---------------------------------------------------------------- */
+int lz_version(void);
+const char *lz_last_error(void);
+/* stream: a cudaStream_t cast to void* (NULL = the legacy default stream the reference uses,
+ * test_lanczos.cu:74-91) */
+int lz_ctx_create(int device, void *stream, lz_ctx **out);
+int lz_ctx_destroy(lz_ctx *ctx);
+int lz_ctx_sync(lz_ctx *ctx);                       /* cudaDeviceSynchronize role, test_lanczos.cu:239 */
+int lz_ctx_device(const lz_ctx *ctx);
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+int64_t lz_ctx_launch_count(const lz_ctx *ctx);
+
+/* raw device memory for the C++ containers (objects/vector.hpp:24-39 cudaMalloc/cudaFree) */
+int lz_malloc(lz_ctx *ctx, size_t bytes, void **dptr);
+int lz_free(lz_ctx *ctx, void *dptr);
+int lz_memcpy(lz_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);  /* synchronous */
+int lz_memset(lz_ctx *ctx, void *dptr, int value, size_t bytes);
+int lz_fill(lz_ctx *ctx, int64_t n, double value, double *x);   /* v::set_entries, vector_kernels.hpp:11-20 */
+
+/* ---- sparse operators ------------------------------------------------------------------ */
+/* CSR (new container in the reference's style).  Arrays are borrowed device
+ * pointers: rowptr[n_rows+1], colidx[nnz] (int32), vals[nnz] (fp64).  Builds the row-block
+ * schedule (short rows streamed through shared memory, long rows split). */
+int lz_csr_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *rowptr,
+                  const int32_t *colidx, const double *vals, lz_matrix **out);
+/* same from HOST arrays: the library owns the device copy (Csr_matrix::copy_to_device role) */
+int lz_csr_create_host(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                       const int32_t *rowptr_host, const int32_t *colidx_host,
+                       const double *vals_host, lz_matrix **out);
+/* ELLPACK as the reference stores it (objects/ell_matrix.hpp:14-21): data[T], idx[unsigned].
+ * layout 0 = column-major data[r + k*n_rows]; layout 1 = row-interleaved data[width*r + k]
+ * (what change_order(4) is meant to produce, ell_matrix.hpp:362-403).  Borrowed device arrays;
+ * width 4 row-interleaved runs the dedicated kernel that replaces ell::SpMV / ell::SpMM
+ * (kernels/spmv_spmm.hpp:105-199); anything else is converted to CSR on the device. */
+int lz_ell_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int width, int layout,
+                  const double *data, const uint32_t *idx, lz_matrix **out);
+int lz_matrix_destroy(lz_matrix *A);
+int lz_matrix_info(const lz_matrix *A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
+/* borrowed views of the CSR arrays held by A (NULL for a native ELL4 operator) */
+int lz_matrix_csr_view(const lz_matrix *A, const int32_t **rowptr, const int32_t **colidx,
+                       const double **vals);
+
+/* synthetic operators generated on the device (BASELINE.json configs 2-5) */
+int lz_gen_laplacian2d(lz_ctx *ctx, int64_t nx, int64_t ny, lz_matrix **out);
+int lz_gen_laplacian3d(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, lz_matrix **out);
+/* v[i] = 2*u(splitmix64(seed ^ i)) - 1 ; block: V[i + c*ld] = 2*u(splitmix64(seed ^ (i*b+c))) - 1 */
+int lz_gen_start_vector(lz_ctx *ctx, int64_t n, uint64_t seed, double *v);
+int lz_gen_start_block(lz_ctx *ctx, int64_t n, int b, int64_t ld, uint64_t seed, double *V);
+
+/* y = A x          replaces spmv(Ell_matrix&,Vector&,Vector&)  kernels/spmv_spmm.hpp:209-260
+ *                  and Ell_matrix::spmv                        objects/ell_matrix.hpp:228-245 */
+int lz_spmv(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y);
+/* Y = A X (b columns, column-major)   replaces spmm(...)       kernels/spmv_spmm.hpp:262-333
+ *                  and Ell_matrix::spmm                        objects/ell_matrix.hpp:267-286 */
+int lz_spmm(lz_ctx *ctx, const lz_matrix *A, int b, const double *X, int64_t ldx, double *Y, int64_t ldy);
+
+/* ---- vector reductions / updates (kernels/vector_kernels.hpp, utils/lib_utils.hpp:431-538) ---- */
+/* result to HOST (synchronises, as Vector::dot does: objects/vector.hpp:249-275) */
+int lz_dot(lz_ctx *ctx, int64_t n, const double *x, const double *y, double *result_host);
+/* l2 norm; LZ_ERR_BREAKDOWN when not finite (objects/vector.hpp:233-244) */
+int lz_nrm2(lz_ctx *ctx, int64_t n, const double *x, double *result_host);
+/* y = a*y + b*x     Vector::sadd / v::vector_update   vector_kernels.hpp:22-33 */
+int lz_axpby(lz_ctx *ctx, int64_t n, double a, double *y, double b, const double *x);
+
+/* ---- tall-skinny dense products (kernels/mm_tt.hpp, mm_tt2.hpp, mm_ts.hpp; lib_utils.hpp:28-202) ---- */
+/* R = T^T T            (b x b, column-major, device)   mm_tt / mm_tt_cublas */
+int lz_mm_tt(lz_ctx *ctx, int64_t n, int b, const double *T, int64_t ld, double *R);
+/* R = 0.5 (T1^T T2 + T2^T T1)                          mm_tt2 / mm_tt2_cublas */
+int lz_mm_tt2(lz_ctx *ctx, int64_t n, int b, const double *T1, int64_t ld1, const double *T2,
+              int64_t ld2, double *R);
+/* R = beta R + alpha T S   (T,R: n x b; S: b x b device) mm_ts / mm_cublas; R may alias T */
+int lz_mm_ts(lz_ctx *ctx, int64_t n, int b, double beta, double alpha, const double *T, int64_t ldt,
+             const double *S, double *R, int64_t ldr);
+/* S <- S^{1/2}, Sinv <- S^{-1/2} (SPD b x b, reads the lower triangle, abs of eigenvalues)
+ *                     my_sqrtm_cusolver / sqrtm_cusolver  kernels/my_sqrtm_cusolver.hpp:366-376,
+ *                                                         utils/lib_utils.hpp:650-745 */
+int lz_sqrtm(lz_ctx *ctx, int b, double *S, double *Sinv);
+/* q[off + c] = Q[lc + c*ld], c < b     copy_row_to_vector  methods/copy_functions.hpp:31-46 */
+int lz_copy_row(lz_ctx *ctx, int64_t lc, int b, const double *Q, int64_t ld, double *q, int64_t off);
+/* dense block-tridiagonal T ((m*b)^2, column-major, device) from alpha[m], beta[1..m-1] blocks
+ * stored back to back            Assemble_T  objects/tridiagonal_matrix.hpp:90-127 */
+int lz_assemble_T(lz_ctx *ctx, int m, int b, const double *alpha, const double *beta, double *T);
+
+/* ---- drivers ---------------------------------------------------------------------------- */
+/* vector_lanczos<double>  methods/vector_lanczos.hpp:8-67.
+ *   b      : start vector (device, n), not modified
+ *   m      : steps;  lc: receiver row (copy_vector_element, copy_functions.hpp:116-133)
+ *   reorth : LZ_REORTH_*  (full modes keep an n x m basis slab inside the context)
+ *   alpha_host[m], beta_host[m] (beta[0] = ||b||): HOST arrays as in test_lanczos.cu:66-67
+ *   q      : device, m entries (row lc of the Krylov basis)
+ *   steps_done: number of valid coefficients (< m after a breakdown; then LZ_ERR_BREAKDOWN)
+ * One fused SpMV pass (w = A q_j - beta_j q_{j-1}, alpha_j in the epilogue) and one fused update
+ * pass (w -= alpha_j q_j, ||w||^2 in the epilogue) per step; scalars stay on the device. */
+int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
+                      double *alpha_host, double *beta_host, double *q, int *steps_done);
+/* same, but coefficients stay in DEVICE arrays and nothing synchronises (bench / graph use) */
+int lz_vector_lanczos_async(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc,
+                            int reorth, double *alpha_dev, double *beta_dev, double *q);
+/* basis kept by the last full-reorth run: column j at V + j*ld (device, borrowed from ctx) */
+int lz_vector_basis(lz_ctx *ctx, const double **V, int64_t *ld, int *cols);
+
+/* block_lanczos_blas<double>  methods/block_lanczos.hpp:88-167 (and block_lanczos :13-80).
+ *   B      : n x bw start block, column-major, leading dimension ldb (device), not modified
+ *   alpha  : device, m blocks of bw*bw (column-major each), alpha[j] at alpha + j*bw*bw
+ *   beta   : device, (m+1) blocks; beta[0] = (B^T B)^{1/2}, beta[m] = last inverse square root
+ *            (scratch slot exactly as the reference uses it, block_lanczos.hpp:111,142)
+ *   q      : device, m*bw entries (row lc of every Q_j)
+ * bw in {1..32}. */
+int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t ldb, int bw, int m,
+                     int64_t lc, int reorth, double *alpha, double *beta, double *q);
+
+/* ---- Ritz extraction (the syevd(T) inside expm_cusolver, lib_utils.hpp:542-590) ---- */
+/* alpha_host/beta_host: m blocks of bw*bw each (bw = 1: the scalar series; beta[0] is ignored, the
+ * coupling blocks are beta[1..m-1]); beta_last_host: the bw*bw block beta_m coupling to the next
+ * (unbuilt) block, or NULL.  k extremal Ritz values: k/2 smallest then k-k/2 largest, ascending;
+ * resid[i] = || beta_last * Y[last block, i] ||  (0 when beta_last is NULL). Host computation on
+ * the tiny projected matrix. */
+int lz_ritz(int m, int bw, const double *alpha_host, const double *beta_host,
+            const double *beta_last_host, int k, double *theta_host, double *resid_host);
+
+/* ---- multi-GPU: one process per GPU, rows of A and of every Krylov vector sharded ---- */
+/* opaque 128-byte NCCL id minted by rank 0 and broadcast by the launcher (torch.distributed) */
+int lz_comm_unique_id(void *id128_host);
+int lz_comm_init(lz_ctx *ctx, int world_size, int rank, const void *id128_host);
+int lz_comm_destroy(lz_ctx *ctx);
+/* contiguous row-block partition: rows [begin,end) of rank r out of world_size (host logic) */
+int lz_partition_rows(int64_t n_rows, int world_size, int rank, int64_t *begin, int64_t *end);
+/* local slab of the 7-/5-point Laplacian: rows [begin,end) with columns remapped to
+ * [local | lower halo | upper halo]; halo = one xy-plane (3-D) / one x-line (2-D) per side */
+int lz_gen_laplacian3d_shard(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int world_size,
+                             int rank, lz_matrix **out);
+int lz_gen_laplacian2d_shard(lz_ctx *ctx, int64_t nx, int64_t ny, int world_size, int rank,
+                             lz_matrix **out);
+/* sharded single-vector Lanczos: b_local holds this rank's rows; halo exchange with the two
+ * neighbouring ranks before every SpMV, packed all-reduce of the alpha / beta^2 partials.
+ * alpha/beta (device, m) are identical on every rank. */
+int lz_vector_lanczos_sharded(lz_ctx *ctx, const lz_matrix *A_local, const double *b_local, int m,
+                              int reorth, double *alpha_dev, double *beta_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANCZOS_B200_H */

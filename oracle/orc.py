@@ -1,0 +1,253 @@
+"""ctypes front-end of oracle/liboracle.so (the CPU restatement in lanczos_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Import this from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py -- never from the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+
+
+def build():
+    """(Re)build liboracle.so and, when the reference tree is present, oracle/_ref."""
+    subprocess.run(["make", "-s", "-C", _HERE, "all"], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "liboracle.so")
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    i64, i32, u64, dbl = C.c_int64, C.c_int, C.c_uint64, C.c_double
+    vp = C.c_void_p
+    L.orc_splitmix64.restype = u64
+    L.orc_splitmix64.argtypes = [u64]
+    L.orc_start_vector.argtypes = [i64, u64, _f64p]
+    L.orc_start_block.argtypes = [i64, i32, i64, u64, _f64p]
+    L.orc_lap2d_nnz.restype = i64
+    L.orc_lap2d_nnz.argtypes = [i64, i64]
+    L.orc_lap2d_csr.argtypes = [i64, i64, _i32p, _i32p, _f64p]
+    L.orc_lap3d_nnz.restype = i64
+    L.orc_lap3d_nnz.argtypes = [i64, i64, i64]
+    L.orc_lap3d_csr.argtypes = [i64, i64, i64, _i32p, _i32p, _f64p]
+    L.orc_rmat_edges.argtypes = [i32, i64, u64, _i32p, _i32p]
+    L.orc_ell_to_csr.restype = i64
+    L.orc_ell_to_csr.argtypes = [i64, i32, _f64p, _u32p, _i32p, _i32p, _f64p]
+    L.orc_csr_spmv.argtypes = [i64, _i32p, _i32p, _f64p, _f64p, _f64p]
+    L.orc_csr_spmm.argtypes = [i64, _i32p, _i32p, _f64p, i32, _f64p, i64, _f64p, i64]
+    L.orc_dot.restype = dbl
+    L.orc_dot.argtypes = [i64, _f64p, _f64p]
+    L.orc_mm_tt.argtypes = [i64, i32, _f64p, i64, _f64p]
+    L.orc_mm_tt2.argtypes = [i64, i32, _f64p, i64, _f64p, i64, _f64p]
+    L.orc_mm_ts.argtypes = [i64, i32, dbl, dbl, _f64p, i64, _f64p, _f64p, i64]
+    L.orc_jacobi_eig.restype = i32
+    L.orc_jacobi_eig.argtypes = [i32, _f64p, _f64p, _f64p]
+    L.orc_sqrtm.argtypes = [i32, _f64p, _f64p]
+    L.orc_vector_lanczos.restype = i32
+    L.orc_vector_lanczos.argtypes = [i64, _i32p, _i32p, _f64p, _f64p, i32, i64, i32, _f64p, _f64p, _f64p, vp]
+    L.orc_block_lanczos.restype = i32
+    L.orc_block_lanczos.argtypes = [i64, _i32p, _i32p, _f64p, _f64p, i32, i32, i64, i32, _f64p, _f64p, _f64p, vp]
+    L.orc_assemble_T.argtypes = [i32, i32, _f64p, _f64p, _f64p]
+    L.orc_set_threads.argtypes = [i32]
+    L.orc_get_threads.restype = i32
+    _LIB = L
+    return L
+
+
+# ------------------------------------------------------------------------------- generators
+
+def set_threads(t):
+    lib().orc_set_threads(int(t))
+
+
+def start_vector(n, seed=0x5EED):
+    v = np.empty(n, dtype=np.float64)
+    lib().orc_start_vector(n, seed, v)
+    return v
+
+
+def start_block(n, b, seed=0x5EED):
+    """column-major n x b (returned as an (n, b) Fortran-ordered array)."""
+    buf = np.empty(n * b, dtype=np.float64)
+    lib().orc_start_block(n, b, n, seed, buf)
+    return buf.reshape(b, n).T
+
+
+def lap2d(nx, ny):
+    n, nnz = nx * ny, lib().orc_lap2d_nnz(nx, ny)
+    rp, ci, va = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+    lib().orc_lap2d_csr(nx, ny, rp, ci, va)
+    return rp, ci, va
+
+
+def lap3d(nx, ny, nz):
+    n, nnz = nx * ny * nz, lib().orc_lap3d_nnz(nx, ny, nz)
+    rp, ci, va = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+    lib().orc_lap3d_csr(nx, ny, nz, rp, ci, va)
+    return rp, ci, va
+
+
+def rmat_edges(scale, n_edges, seed=0x5EED):
+    s, d = np.empty(n_edges, np.int32), np.empty(n_edges, np.int32)
+    lib().orc_rmat_edges(scale, n_edges, seed, s, d)
+    return s, d
+
+
+def rmat_laplacian(scale, edge_factor=16, seed=0x5EED):
+    """Symmetrised, de-duplicated, loop-free R-MAT graph Laplacian L = D - A as CSR (SURVEY 8d cfg 4)."""
+    n = 1 << scale
+    s, d = rmat_edges(scale, n * edge_factor, seed)
+    keep = s != d
+    s, d = s[keep].astype(np.int64), d[keep].astype(np.int64)
+    key = np.unique(np.concatenate([s * n + d, d * n + s]))
+    r, c = key // n, key % n
+    deg = np.bincount(r, minlength=n)
+    # off-diagonal -1 plus one diagonal entry per row, columns ascending
+    rows = np.concatenate([r, np.arange(n)])
+    cols = np.concatenate([c, np.arange(n)])
+    vals = np.concatenate([-np.ones(len(r)), deg.astype(np.float64)])
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    rp = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=n), out=rp[1:])
+    return rp.astype(np.int32), cols.astype(np.int32), np.ascontiguousarray(vals)
+
+
+def ell_to_csr(n, width, ell_data, ell_idx):
+    rp = np.empty(n + 1, np.int32)
+    ci = np.empty(n * width, np.int32)
+    va = np.empty(n * width, np.float64)
+    nnz = lib().orc_ell_to_csr(n, width, np.ascontiguousarray(ell_data, np.float64),
+                               np.ascontiguousarray(ell_idx, np.uint32), rp, ci, va)
+    return rp, ci[:nnz].copy(), va[:nnz].copy()
+
+
+# ------------------------------------------------------------------------------- operators
+
+def spmv(csr, x):
+    rp, ci, va = csr
+    y = np.empty(len(rp) - 1, np.float64)
+    lib().orc_csr_spmv(len(rp) - 1, rp, ci, va, np.ascontiguousarray(x, np.float64), y)
+    return y
+
+
+def spmm(csr, X):
+    """X: (n, b) array; returns (n, b) Fortran-ordered."""
+    rp, ci, va = csr
+    n, b = X.shape
+    Xf = np.ascontiguousarray(X.T, np.float64).reshape(-1)     # column-major storage
+    Y = np.empty(n * b, np.float64)
+    lib().orc_csr_spmm(n, rp, ci, va, b, Xf, n, Y, n)
+    return Y.reshape(b, n).T
+
+
+def sqrtm(S):
+    b = S.shape[0]
+    s = np.ascontiguousarray(S.T, np.float64).reshape(-1).copy()
+    si = np.empty_like(s)
+    lib().orc_sqrtm(b, s, si)
+    return s.reshape(b, b).T, si.reshape(b, b).T
+
+
+def vector_lanczos(csr, b, m, lc=0, reorth=0, want_basis=False):
+    rp, ci, va = csr
+    n = len(rp) - 1
+    alpha, beta, q = np.zeros(m), np.zeros(m), np.zeros(m)
+    V = np.empty(n * m, np.float64) if want_basis else None
+    done = lib().orc_vector_lanczos(n, rp, ci, va, np.ascontiguousarray(b, np.float64), m, lc, reorth,
+                                    alpha, beta, q, V.ctypes.data if V is not None else None)
+    out = dict(alpha=alpha, beta=beta, q=q, steps=done)
+    if V is not None:
+        out["V"] = V.reshape(m, n).T
+    return out
+
+
+def block_lanczos(csr, B, m, lc=0, reorth=0, want_basis=False):
+    """B: (n, bw).  alpha: (m, bw, bw) with alpha[j][r, c]; beta: (m+1, bw, bw)."""
+    rp, ci, va = csr
+    n, bw = B.shape
+    Bf = np.ascontiguousarray(B.T, np.float64).reshape(-1)
+    alpha = np.zeros(m * bw * bw)
+    beta = np.zeros((m + 1) * bw * bw)
+    q = np.zeros(m * bw)
+    V = np.empty(n * m * bw, np.float64) if want_basis else None
+    done = lib().orc_block_lanczos(n, rp, ci, va, Bf, bw, m, lc, reorth, alpha, beta, q,
+                                   V.ctypes.data if V is not None else None)
+    out = dict(alpha=alpha.reshape(m, bw, bw).transpose(0, 2, 1),
+               beta=beta.reshape(m + 1, bw, bw).transpose(0, 2, 1), q=q, steps=done)
+    if V is not None:
+        out["V"] = V.reshape(m * bw, n).T
+    return out
+
+
+def assemble_T(alpha, beta):
+    """alpha (m,bw,bw), beta (>=m,bw,bw) as returned by block_lanczos (or 1-D for bw = 1)."""
+    alpha, beta = np.asarray(alpha, np.float64), np.asarray(beta, np.float64)
+    if alpha.ndim == 1:
+        alpha, beta = alpha.reshape(-1, 1, 1), beta.reshape(-1, 1, 1)
+    m, bw = alpha.shape[0], alpha.shape[1]
+    a = np.ascontiguousarray(alpha.transpose(0, 2, 1)).reshape(-1)
+    b = np.ascontiguousarray(beta[:m].transpose(0, 2, 1)).reshape(-1)
+    T = np.empty((m * bw) ** 2, np.float64)
+    lib().orc_assemble_T(m, bw, a, b, T)
+    return T.reshape(m * bw, m * bw).T
+
+
+def ritz(alpha, beta, k, beta_last=None):
+    """k extremal Ritz values (k//2 smallest, k - k//2 largest) of eig(T) and residual estimates
+    |beta_m * y_last| (scalar case) / ||beta_m Y_lastblock|| (block case) when beta_last is given."""
+    T = assemble_T(alpha, beta)
+    w, Y = np.linalg.eigh(T)
+    lo = k // 2
+    sel = np.r_[np.arange(lo), np.arange(len(w) - (k - lo), len(w))]
+    res = None
+    if beta_last is not None:
+        bl = np.atleast_2d(np.asarray(beta_last, np.float64))
+        bw = bl.shape[0]
+        res = np.linalg.norm(bl @ Y[-bw:, sel], axis=0)
+    return w[sel], res
+
+
+# ------------------------------------------------------------------------------- _ref dumps
+
+def read_dump(path):
+    """Reader for the record container written by oracle/_ref/ref_host_dump_*."""
+    out = {}
+    with open(path, "rb") as f:
+        raw = f.read()
+    off = 0
+    dts = {0: np.float64, 1: np.uint32, 2: np.int64}
+    while off < len(raw):
+        ln = int(np.frombuffer(raw, np.uint32, 1, off)[0]); off += 4
+        name = raw[off:off + ln].decode(); off += ln
+        dt = dts[raw[off]]; off += 1
+        cnt = int(np.frombuffer(raw, np.uint64, 1, off)[0]); off += 8
+        arr = np.frombuffer(raw, dt, cnt, off).copy(); off += cnt * arr.itemsize
+        out[name] = arr if not (dt is np.int64 and cnt == 1) else int(arr[0])
+    return out
+
+
+def ref_dump_path(n_col=4):
+    return os.path.join(_HERE, "_ref", "ref_host_dump_%d" % n_col)
+
+
+def run_ref(mode, N, m, n_col=4, out=None):
+    """Run the reference-derived dump tool (needs oracle/_ref built from /root/reference)."""
+    import tempfile
+    exe = ref_dump_path(n_col)
+    if out is None:
+        out = os.path.join(tempfile.mkdtemp(), "dump.bin")
+    subprocess.run([exe, mode, str(N), str(m), out], check=True)
+    return read_dump(out)
