@@ -69,6 +69,8 @@ struct lz_ctx {
     int64_t basis_ld;
     int basis_cols;
     lz_comm *comm;
+    int spmv_variant;       // dev-time tuning knobs (env LZ_SPMV_VARIANT / LZ_SPMV_TILE)
+    int spmv_tile;
 };
 
 #define LZ_PARTIALS_CAP (1 << 20)
@@ -84,7 +86,7 @@ enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
 
 // row-aligned nnz chunks: chunk c covers rows [chunk_row[c], chunk_row[c+1])
 #define LZ_SPMV_THREADS 256
-#define LZ_SPMV_TILE 3072        // target nnz per chunk
+#define LZ_SPMV_TILE 1536        // target nnz per chunk (default; see profiles/ for the sweep)
 #define LZ_SPMV_CAP 4096         // shared-memory product slots per CTA (32 KB)
 
 struct lz_matrix {
@@ -99,6 +101,9 @@ struct lz_matrix {
     int owns;                // arrays owned by the library (freed on destroy)
     int n_chunks;
     int32_t *chunk_row;      // n_chunks + 1
+    int32_t *chunk_ptr;      // rowptr[chunk_row[c]], n_chunks + 1
+    int tile, cap;           // nnz per chunk (target) and shared-memory product slots per CTA
+    int tma_ok;              // vals / colidx 16-byte aligned: bulk-copy staged kernel usable
     int max_row_nnz;
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
     int64_t halo_lo, halo_hi;        // halo entries below / above the local range

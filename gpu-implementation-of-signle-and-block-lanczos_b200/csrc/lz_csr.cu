@@ -9,19 +9,20 @@
 // schedule: chunk c covers rows [chunk_row[c], chunk_row[c+1]) where chunk_row[c] is the first
 // row whose rowptr is >= c * LZ_SPMV_TILE.  Chunks hold < TILE + max_row_nnz non-zeros.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_chunk_rows(int64_t n_rows, int64_t nnz, const int32_t *__restrict__ rowptr, int n_chunks,
-                             int32_t *__restrict__ chunk_row)
+__global__ void k_chunk_rows(int64_t n_rows, int64_t nnz, const int32_t *__restrict__ rowptr, int n_chunks, int tile,
+                             int32_t *__restrict__ chunk_row, int32_t *__restrict__ chunk_ptr)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_chunks) return;
-    if (c == n_chunks) { chunk_row[c] = (int32_t)n_rows; return; }
-    int64_t target = (int64_t)c * LZ_SPMV_TILE;
+    if (c == n_chunks) { chunk_row[c] = (int32_t)n_rows; chunk_ptr[c] = (int32_t)nnz; return; }
+    int64_t target = (int64_t)c * tile;
     int64_t lo = 0, hi = n_rows;   // first r in [0, n_rows] with rowptr[r] >= target
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
         if (rowptr[mid] >= target) hi = mid; else lo = mid + 1;
     }
     chunk_row[c] = (int32_t)lo;
+    chunk_ptr[c] = rowptr[lo];
 }
 
 __global__ void k_max_row(int64_t n_rows, const int32_t *__restrict__ rowptr, int *out)
@@ -35,12 +36,16 @@ __global__ void k_max_row(int64_t n_rows, const int32_t *__restrict__ rowptr, in
 
 static int build_schedule(lz_ctx *ctx, lz_matrix *A)
 {
-    int64_t nch = (A->nnz + LZ_SPMV_TILE - 1) / LZ_SPMV_TILE;
+    A->tile = ctx->spmv_tile > 0 ? ctx->spmv_tile : LZ_SPMV_TILE;
+    A->cap = A->tile <= 1536 ? 2048 : 4096;
+    int64_t nch = (A->nnz + A->tile - 1) / A->tile;
     if (nch < 1) nch = 1;
     LZ_CHECK(nch * 2 <= LZ_PARTIALS_CAP, LZ_ERR_UNSUPPORTED, "matrix too large for the reduction scratch (%lld chunks)", (long long)nch);
     A->n_chunks = (int)nch;
     LZ_CUDA(cudaMalloc(&A->chunk_row, sizeof(int32_t) * (nch + 1)));
-    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->nnz, A->rowptr, (int)nch, A->chunk_row);
+    LZ_CUDA(cudaMalloc(&A->chunk_ptr, sizeof(int32_t) * (nch + 1)));
+    A->tma_ok = ((uintptr_t)A->vals % 16 == 0) && ((uintptr_t)A->colidx % 16 == 0);
+    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->nnz, A->rowptr, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
     int *d_max = ctx->flags + 8;
     LZ_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
@@ -338,6 +343,7 @@ int lz_matrix_destroy(lz_matrix *A)
         cudaFree((void *)A->ell_idx);
     }
     cudaFree(A->chunk_row);
+    cudaFree(A->chunk_ptr);
     delete A;
     return LZ_OK;
 }

@@ -1,5 +1,6 @@
 // lz_ctx.cu -- context, error state, raw memory entry points of the C-ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "lz_common.cuh"
 
@@ -50,6 +51,8 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     LZ_CUDA(cudaMemset(c->tickets, 0, sizeof(unsigned int) * LZ_TICKETS));
     LZ_CUDA(cudaMemset(c->scalars, 0, sizeof(double) * LZ_SCALARS));
     LZ_CUDA(cudaMemset(c->flags, 0, sizeof(int) * LZ_FLAGS));
+    if (const char *e = getenv("LZ_SPMV_VARIANT")) c->spmv_variant = atoi(e);
+    if (const char *e = getenv("LZ_SPMV_TILE")) c->spmv_tile = atoi(e);
     *out = c;
     return LZ_OK;
 }

@@ -53,17 +53,32 @@ struct LzRowEpi {
     }
     // scale applied to every gathered x value
     __device__ __forceinline__ double xs(double xv) const { return MODE == LZ_EPI_LANCZOS ? __dmul_rn(xv, sx) : xv; }
+    // epilogue operands of row i (fetched early by the pipelined kernels)
+    __device__ __forceinline__ void load(int64_t i, double &xo, double &up) const
+    {
+        xo = 0.0; up = 0.0;
+        if (MODE == LZ_EPI_LANCZOS) {
+            xo = a.x_own[i];
+            if (!a.first) up = a.u_prev[i];
+        }
+    }
     // finish row i whose raw sum is t; returns the row's contribution to alpha
-    __device__ __forceinline__ double finish(int64_t i, double t, double *__restrict__ y) const
+    __device__ __forceinline__ double finish(int64_t i, double t, double *__restrict__ y, double xo, double up) const
     {
         if (MODE == LZ_EPI_PLAIN) { y[i] = t; return 0.0; }
-        const double qi = __dmul_rn(a.x_own[i], sx);
+        const double qi = __dmul_rn(xo, sx);
         double w = t;
-        if (!a.first) w = __dadd_rn(t, __dmul_rn(-beta, __dmul_rn(a.u_prev[i], sprev)));
+        if (!a.first) w = __dadd_rn(t, __dmul_rn(-beta, __dmul_rn(up, sprev)));
         y[i] = w;
         if (a.vcol) a.vcol[i] = qi;
         if (i == a.lc && a.qout) *a.qout = qi;
         return __dmul_rn(w, qi);
+    }
+    __device__ __forceinline__ double finish(int64_t i, double t, double *__restrict__ y) const
+    {
+        double xo, up;
+        load(i, xo, up);
+        return finish(i, t, y, xo, up);
     }
 };
 
@@ -142,6 +157,418 @@ k_csr_spmv(const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ ro
     lz_spmv_finalize<MODE>(acc, args, red);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-pipelined persistent CSR kernel (the default path).
+//
+// grid = a multiple of the SM count; CTA c walks chunks c, c + grid, ...  The contiguous vals /
+// colidx slice of a chunk is brought into a shared-memory ring by two bulk async copies
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) issued by one elected thread STAGES-1
+// chunks ahead, so HBM streaming never waits on the compute threads.  Consumers turn the staged
+// values into products in place (x gathered with LDG, mostly L1/L2 hits), then one thread per row
+// adds its products left to right and runs the epilogue.  Per-row operands of the epilogue
+// (rowptr pair, u_prev, x_own) are fetched into registers before the wait on the ring.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lz_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void lz_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lz_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void lz_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lz_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LZ_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LZ_DONE_%=;\n\t"
+        "bra LZ_WAIT_%=;\n\t"
+        "LZ_DONE_%=:\n\t}"
+        ::"r"(lz_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void lz_bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(lz_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(lz_smem_u32(bar)) : "memory");
+}
+
+#define LZ_TMA_ROWS_PER_THREAD 4
+
+template <int MODE, int THREADS, int STAGES, int CAP>
+__global__ void __launch_bounds__(THREADS)
+k_csr_spmv_tma(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
+               const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+               const LzPassA args)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // ring: STAGES x { double vals[CAP]; int cols[CAP]; }  then the mbarriers
+    double *vals_s = reinterpret_cast<double *>(smem_raw);
+    int *cols_s = reinterpret_cast<int *>(smem_raw + sizeof(double) * (size_t)CAP * STAGES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(double) + sizeof(int)) * (size_t)CAP * STAGES);
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    const LzRowEpi<MODE> epi(args);
+    double acc = 0.0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) lz_mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer: slice [a0, a0+cnt4) of a chunk (nnz range [p0,p1)) into ring slot `slot`
+    auto issue = [&](int p0, int p1, int slot) {
+        const int a0 = p0 & ~3;
+        if (p1 - a0 > CAP) return;                     // long-row chunk: no staging
+        const int cnt4 = (p1 - a0) & ~3;
+        if (cnt4 == 0) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        lz_mbar_expect_tx(&full[slot], (uint32_t)cnt4 * 12u);
+        lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
+        lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
+    };
+
+    const int first = blockIdx.x, step = gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES - 1; ++s) {
+            const int c = first + s * step;
+            if (c < n_chunks) issue(chunk_ptr[c], chunk_ptr[c + 1], s);
+        }
+    }
+    // chunk metadata runs one trip ahead in registers so its load latency is never exposed
+    int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0, ip0 = 0, ip1 = 0;
+    if (first < n_chunks) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
+    if (tid == 0) {
+        const int cn = first + (STAGES - 1) * step;
+        if (cn < n_chunks) { ip0 = chunk_ptr[cn]; ip1 = chunk_ptr[cn + 1]; }
+    }
+    uint32_t phase_bits = 0;                            // one parity bit per slot
+    int it = 0;
+    for (int c = first; c < n_chunks; c += step, ++it) {
+        const int slot = it % STAGES;
+        const int r0 = nr0, r1 = nr1, p0 = np0, p1 = np1;
+        // keep the ring full: chunk c + (STAGES-1)*step goes into the slot freed last trip
+        if (tid == 0) {
+            const int cn = c + (STAGES - 1) * step;
+            if (cn < n_chunks) issue(ip0, ip1, (it + STAGES - 1) % STAGES);
+            const int cnn = cn + step;
+            if (cnn < n_chunks) { ip0 = chunk_ptr[cnn]; ip1 = chunk_ptr[cnn + 1]; }
+        }
+        if (c + step < n_chunks) {
+            nr0 = chunk_row[c + step]; nr1 = chunk_row[c + step + 1];
+            np0 = chunk_ptr[c + step]; np1 = chunk_ptr[c + step + 1];
+        }
+        const int a0 = p0 & ~3;
+        if (r1 > r0) {
+            if (p1 - a0 <= CAP) {
+                double *vs = vals_s + (size_t)slot * CAP;
+                const int *cs = cols_s + (size_t)slot * CAP;
+                // per-row operands first: their latency overlaps the wait and the product phase
+                int rs[LZ_TMA_ROWS_PER_THREAD], re[LZ_TMA_ROWS_PER_THREAD];
+#pragma unroll
+                for (int u = 0; u < LZ_TMA_ROWS_PER_THREAD; ++u) {
+                    const int r = r0 + tid + u * THREADS;
+                    rs[u] = re[u] = 0;
+                    if (r < r1) { rs[u] = rowptr[r] - a0; re[u] = rowptr[r + 1] - a0; }
+                }
+                const int cnt = p1 - a0, cnt4 = cnt & ~3;
+                if (cnt4 > 0) {
+                    lz_mbar_wait(&full[slot], (phase_bits >> slot) & 1u);
+                    phase_bits ^= 1u << slot;
+                }
+                // tail (< 4 entries) that the 16-byte-granular bulk copies cannot carry
+                if (tid < cnt - cnt4) {
+                    const int k = cnt4 + tid;
+                    vs[k] = __dmul_rn(vals[a0 + k], epi.xs(__ldg(x + colidx[a0 + k])));
+                }
+                // products in place: all gathers of a thread are issued before the first use
+                constexpr int GPT = (CAP + THREADS - 1) / THREADS;     // gathers per thread, upper bound
+                double xv[GPT];
+#pragma unroll
+                for (int u = 0; u < GPT; ++u) {
+                    const int k = tid + u * THREADS;
+                    xv[u] = 0.0;
+                    if (k < cnt4) xv[u] = __ldg(x + cs[k]);
+                }
+#pragma unroll
+                for (int u = 0; u < GPT; ++u) {
+                    const int k = tid + u * THREADS;
+                    if (k < cnt4) vs[k] = __dmul_rn(vs[k], epi.xs(xv[u]));
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < LZ_TMA_ROWS_PER_THREAD; ++u) {
+                    const int r = r0 + tid + u * THREADS;
+                    if (r < r1) {
+                        const int s0 = rs[u], len = re[u] - rs[u];
+                        // short rows: up to 8 products fetched at once, summed left to right
+                        double pr[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) pr[k] = (k < len) ? vs[s0 + k] : 0.0;
+                        double t = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) if (k < len) t = __dadd_rn(t, pr[k]);
+                        for (int k = s0 + 8; k < re[u]; ++k) t = __dadd_rn(t, vs[k]);
+                        acc += epi.finish(r, t, y);
+                    }
+                }
+                for (int r = r0 + tid + LZ_TMA_ROWS_PER_THREAD * THREADS; r < r1; r += THREADS) {   // many short/empty rows
+                    const int s = rowptr[r] - a0, e = rowptr[r + 1] - a0;
+                    double t = 0.0;
+                    for (int k = s; k < e; ++k) t = __dadd_rn(t, vs[k]);
+                    acc += epi.finish(r, t, y);
+                }
+            } else {
+                // long-row chunk: walk global memory (warp per row, CTA per very long row)
+                const int lane = tid & 31, warp = tid >> 5;
+                for (int r = r0 + warp; r < r1; r += THREADS / 32) {
+                    const int s = rowptr[r], e = rowptr[r + 1];
+                    if (e - s > 4096) continue;
+                    double t = 0.0;
+                    for (int k = s + lane; k < e; k += 32) t += vals[k] * epi.xs(__ldg(x + colidx[k]));
+                    t = lz_warp_sum(t);
+                    if (lane == 0) acc += epi.finish(r, t, y);
+                }
+                for (int r = r0; r < r1; ++r) {
+                    const int s = rowptr[r], e = rowptr[r + 1];
+                    if (e - s <= 4096) continue;
+                    double t = 0.0;
+                    for (int k = s + tid; k < e; k += THREADS) t += vals[k] * epi.xs(__ldg(x + colidx[k]));
+                    t = lz_block_sum<THREADS>(t, red);
+                    if (tid == 0) acc += epi.finish(r, t, y);
+                }
+            }
+        }
+        __syncthreads();                               // slot may be refilled from here on
+    }
+    if (MODE == LZ_EPI_LANCZOS) {
+        acc = lz_block_sum<THREADS>(acc, red);
+        double total;
+        if (lz_grid_sum<THREADS, 1>(&acc, args.partials, args.ticket, red, &total)) {
+            if (tid == 0) {
+                *args.alpha_partial = total;
+                if (args.alpha_out) *args.alpha_out = total;
+            }
+        }
+    }
+}
+
+static inline size_t lz_tma_smem_bytes(int stages, int cap) { return (size_t)stages * cap * 12 + 8 * stages; }
+
+template <int MODE, int THREADS, int STAGES, int CAP>
+static inline int lz_launch_tma_variant(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int ctas_per_sm)
+{
+    static bool attr_set = false;
+    const size_t smem = lz_tma_smem_bytes(STAGES, CAP);
+    if (!attr_set) {
+        LZ_CUDA(cudaFuncSetAttribute(k_csr_spmv_tma<MODE, THREADS, STAGES, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = ctx->sm_count * ctas_per_sm;
+    if (grid > A->n_chunks) grid = A->n_chunks;
+    k_csr_spmv_tma<MODE, THREADS, STAGES, CAP><<<grid, THREADS, smem, ctx->stream>>>(
+        A->n_chunks, A->chunk_row, A->chunk_ptr, A->rowptr, A->colidx, A->vals, x, y, args);
+    return LZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised variant of the TMA kernel: no CTA-wide barrier inside the chunk loop.
+//   warp 0          : producer -- waits for a free ring slot, issues the two bulk copies
+//   warps 1..GW     : gather   -- wait for the slice, turn it into products in place (x via LDG)
+//   warps GW+1..    : rows     -- wait for the products, add them per row, run the epilogue
+// Slots cycle through three mbarriers (full -> prod -> free), so the three roles work on
+// different chunks at the same time and every role's global-load latency overlaps the others'.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lz_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lz_smem_u32(bar)) : "memory");
+}
+
+template <int MODE, int GW, int RW, int STAGES, int CAP>
+__global__ void __launch_bounds__((1 + GW + RW) * 32)
+k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
+              const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+              const LzPassA args)
+{
+    constexpr int THREADS = (1 + GW + RW) * 32, GT = GW * 32, RT = RW * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *vals_s = reinterpret_cast<double *>(smem_raw);
+    int *cols_s = reinterpret_cast<int *>(smem_raw + sizeof(double) * (size_t)CAP * STAGES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 12 * (size_t)CAP * STAGES);
+    uint64_t *prod = full + STAGES, *freeb = prod + STAGES;
+    __shared__ double red[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const LzRowEpi<MODE> epi(args);
+    double acc = 0.0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { lz_mbar_init(&full[s], 1); lz_mbar_init(&prod[s], GW); lz_mbar_init(&freeb[s], RW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int first = blockIdx.x, step = gridDim.x;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            int p0 = 0, p1 = 0;
+            if (first < n_chunks) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
+            int it = 0;
+            for (int c = first; c < n_chunks; c += step, ++it) {
+                const int slot = it % STAGES;
+                const int cp0 = p0, cp1 = p1;
+                if (c + step < n_chunks) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
+                lz_mbar_wait(&freeb[slot], ((it / STAGES) & 1) ^ 1);
+                const int a0 = cp0 & ~3;
+                const int cnt4 = (cp1 - a0) & ~3;
+                if (cp1 - a0 > CAP || cnt4 == 0) { lz_mbar_arrive(&full[slot]); continue; }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                lz_mbar_expect_tx(&full[slot], (uint32_t)cnt4 * 12u);
+                lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
+                lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
+            }
+        }
+    } else if (warp <= GW) {
+        // ------------------------------------------------------------------ gather warps
+        const int gtid = tid - 32;
+        int p0 = 0, p1 = 0;
+        if (first < n_chunks) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
+        int it = 0;
+        for (int c = first; c < n_chunks; c += step, ++it) {
+            const int slot = it % STAGES;
+            const int cp0 = p0, cp1 = p1;
+            if (c + step < n_chunks) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
+            const int a0 = cp0 & ~3, cnt = cp1 - a0, cnt4 = cnt & ~3;
+            double *vs = vals_s + (size_t)slot * CAP;
+            const int *cs = cols_s + (size_t)slot * CAP;
+            lz_mbar_wait(&full[slot], (it / STAGES) & 1);
+            if (cnt <= CAP) {
+                if (gtid < cnt - cnt4) {       // tail the 16-byte-granular bulk copies cannot carry
+                    const int k = cnt4 + gtid;
+                    vs[k] = __dmul_rn(vals[a0 + k], epi.xs(__ldg(x + colidx[a0 + k])));
+                }
+                for (int base = gtid; base < cnt4; base += 8 * GT) {
+                    double xv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = base + u * GT;
+                        xv[u] = 0.0;
+                        if (k < cnt4) xv[u] = __ldg(x + cs[k]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = base + u * GT;
+                        if (k < cnt4) vs[k] = __dmul_rn(vs[k], epi.xs(xv[u]));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) lz_mbar_arrive(&prod[slot]);
+        }
+    } else {
+        // ------------------------------------------------------------------ row warps
+        const int rtid = tid - 32 * (1 + GW), rwarp = rtid >> 5;
+        int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
+        if (first < n_chunks) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
+        int it = 0;
+        for (int c = first; c < n_chunks; c += step, ++it) {
+            const int slot = it % STAGES;
+            const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
+            if (c + step < n_chunks) {
+                nr0 = chunk_row[c + step]; nr1 = chunk_row[c + step + 1];
+                np0 = chunk_ptr[c + step]; np1 = chunk_ptr[c + step + 1];
+            }
+            const int a0 = cp0 & ~3, cnt = cp1 - a0;
+            const double *vs = vals_s + (size_t)slot * CAP;
+            // operands of this thread's first row before the wait: their latency is hidden by it
+            const int rf = r0 + rtid;
+            int s0 = 0, e0 = 0;
+            double xo = 0.0, up = 0.0;
+            if (rf < r1) { s0 = rowptr[rf] - a0; e0 = rowptr[rf + 1] - a0; epi.load(rf, xo, up); }
+            lz_mbar_wait(&prod[slot], (it / STAGES) & 1);
+            if (cnt <= CAP) {
+                if (rf < r1) {
+                    const int len = e0 - s0;
+                    double pr[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) pr[k] = (k < len) ? vs[s0 + k] : 0.0;
+                    double t = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (k < len) t = __dadd_rn(t, pr[k]);
+                    for (int k = s0 + 8; k < e0; ++k) t = __dadd_rn(t, vs[k]);
+                    acc += epi.finish(rf, t, y, xo, up);
+                }
+                for (int r = rf + RT; r < r1; r += RT) {
+                    const int s = rowptr[r] - a0, e = rowptr[r + 1] - a0;
+                    double t = 0.0;
+                    for (int k = s; k < e; ++k) t = __dadd_rn(t, vs[k]);
+                    acc += epi.finish(r, t, y);
+                }
+            } else {
+                // long-row chunk: the row warps walk global memory (warp per row; all of them per huge row)
+                for (int r = r0 + rwarp; r < r1; r += RW) {
+                    const int s = rowptr[r], e = rowptr[r + 1];
+                    if (e - s > 4096) continue;
+                    double t = 0.0;
+                    for (int k = s + lane; k < e; k += 32) t += vals[k] * epi.xs(__ldg(x + colidx[k]));
+                    t = lz_warp_sum(t);
+                    if (lane == 0) acc += epi.finish(r, t, y);
+                }
+                for (int r = r0; r < r1; ++r) {
+                    const int s = rowptr[r], e = rowptr[r + 1];
+                    if (e - s <= 4096) continue;
+                    double t = 0.0;
+                    for (int k = s + rtid; k < e; k += RT) t += vals[k] * epi.xs(__ldg(x + colidx[k]));
+                    t = lz_warp_sum(t);
+                    // combine the RW warp partials through the (idle) product slots of this stage
+                    double *scratch = vals_s + (size_t)slot * CAP;
+                    asm volatile("bar.sync 1, %0;" ::"n"(RT));
+                    if (lane == 0) scratch[rwarp] = t;
+                    asm volatile("bar.sync 1, %0;" ::"n"(RT));
+                    if (rtid == 0) {
+                        double tt = 0.0;
+                        for (int wv = 0; wv < RW; ++wv) tt += scratch[wv];
+                        acc += epi.finish(r, tt, y);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) lz_mbar_arrive(&freeb[slot]);
+        }
+    }
+    if (MODE == LZ_EPI_LANCZOS) {
+        acc = lz_block_sum<THREADS>(acc, red);
+        double total;
+        if (lz_grid_sum<THREADS, 1>(&acc, args.partials, args.ticket, red, &total)) {
+            if (tid == 0) {
+                *args.alpha_partial = total;
+                if (args.alpha_out) *args.alpha_out = total;
+            }
+        }
+    }
+}
+
+template <int MODE, int GW, int RW, int STAGES, int CAP>
+static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int ctas_per_sm)
+{
+    static bool attr_set = false;
+    const size_t smem = (size_t)STAGES * CAP * 12 + 24 * STAGES;
+    if (!attr_set) {
+        LZ_CUDA(cudaFuncSetAttribute(k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = ctx->sm_count * ctas_per_sm;
+    if (grid > A->n_chunks) grid = A->n_chunks;
+    k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
+        A->n_chunks, A->chunk_row, A->chunk_ptr, A->rowptr, A->colidx, A->vals, x, y, args);
+    return LZ_OK;
+}
+
 // width-4 row-interleaved ELL (data[4r+k], idx[4r+k]); zero padding entries carry idx 0
 template <int MODE>
 __global__ void __launch_bounds__(LZ_SPMV_THREADS)
@@ -172,6 +599,17 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
     if (A->format == LZ_FMT_ELL4) {
         const unsigned grid = (unsigned)((A->n_rows + LZ_SPMV_THREADS - 1) / LZ_SPMV_THREADS);
         k_ell4_spmv<MODE><<<grid, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->n_rows, A->ell_data, A->ell_idx, x, y, args);
+    } else if (A->tma_ok) {
+        // A->cap is fixed when the schedule is built (lz_csr.cu); variant = dev-time tuning knob
+        const int v = ctx->spmv_variant;
+        if (A->cap == 2048) {
+            if (v == 1) LZ_TRY((lz_launch_ws_variant<MODE, 6, 5, 3, 2048>(ctx, A, x, y, args, 3)));
+            else if (v == 2) LZ_TRY((lz_launch_ws_variant<MODE, 4, 3, 2, 2048>(ctx, A, x, y, args, 4)));
+            else if (v == 3) LZ_TRY((lz_launch_tma_variant<MODE, 384, 2, 2048>(ctx, A, x, y, args, 4)));
+            else LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 3)));      // default
+        } else {
+            LZ_TRY((lz_launch_tma_variant<MODE, 1024, 2, 4096>(ctx, A, x, y, args, 2)));
+        }
     } else {
         k_csr_spmv<MODE><<<A->n_chunks, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->chunk_row, A->rowptr, A->colidx, A->vals, x, y, args);
     }

@@ -78,6 +78,7 @@ __device__ __forceinline__ void lz_finalize_beta(const LzFinal &f, double total)
     if (!(isfinite(total)) || total == 0.0) atomicMin(f.flags + F_BREAKDOWN, f.jn);   // vector.hpp:233-244
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(VT)
 k_pass_b(int64_t n, double *__restrict__ w, const double *__restrict__ u_cur, const double *__restrict__ alpha,
          const double *__restrict__ invb, int j, double *partials, unsigned int *ticket, const LzFinal fin)
@@ -85,15 +86,46 @@ k_pass_b(int64_t n, double *__restrict__ w, const double *__restrict__ u_cur, co
     __shared__ double red[32];
     const double na = -alpha[j], sx = invb[j];
     double acc = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * VT;
-    for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += stride) {
-        const double v = __dadd_rn(w[i], __dmul_rn(na, __dmul_rn(u_cur[i], sx)));
-        w[i] = v;
-        acc += v * v;
+    const int64_t stride = (int64_t)gridDim.x * VT, t0 = (int64_t)blockIdx.x * VT + threadIdx.x;
+    if (VEC) {   // both pointers 32-byte aligned: 256-bit loads/stores
+        const int64_t n4 = n >> 2;
+        for (int64_t g = t0; g < n4; g += stride) {
+            double a[4], u[4];
+            lz_ld256(w + 4 * g, a[0], a[1], a[2], a[3]);
+            lz_ld256(u_cur + 4 * g, u[0], u[1], u[2], u[3]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                a[t] = __dadd_rn(a[t], __dmul_rn(na, __dmul_rn(u[t], sx)));
+                acc = fma(a[t], a[t], acc);
+            }
+            lz_st256(w + 4 * g, a[0], a[1], a[2], a[3]);
+        }
+        for (int64_t i = (n4 << 2) + t0; i < n; i += stride) {
+            const double v = __dadd_rn(w[i], __dmul_rn(na, __dmul_rn(u_cur[i], sx)));
+            w[i] = v;
+            acc = fma(v, v, acc);
+        }
+    } else {
+        for (int64_t i = t0; i < n; i += stride) {
+            const double v = __dadd_rn(w[i], __dmul_rn(na, __dmul_rn(u_cur[i], sx)));
+            w[i] = v;
+            acc = fma(v, v, acc);
+        }
     }
     acc = lz_block_sum<VT>(acc, red);
     double total;
     if (lz_grid_sum<VT, 1>(&acc, partials, ticket, red, &total) && threadIdx.x == 0) lz_finalize_beta(fin, total);
+}
+
+static int launch_pass_b(lz_ctx *ctx, int64_t n, double *w, const double *u_cur, const double *alpha, const double *invb,
+                         int j, const LzFinal &fin)
+{
+    const bool vec = ((uintptr_t)w % 32 == 0) && ((uintptr_t)u_cur % 32 == 0);
+    const unsigned grid = stream_grid(ctx, n, VT * 8);
+    if (vec) k_pass_b<true><<<grid, VT, 0, ctx->stream>>>(n, w, u_cur, alpha, invb, j, ctx->partials, ctx->tickets + T_DOT, fin);
+    else k_pass_b<false><<<grid, VT, 0, ctx->stream>>>(n, w, u_cur, alpha, invb, j, ctx->partials, ctx->tickets + T_DOT, fin);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -330,9 +362,7 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
         LZ_TRY(lz_launch_spmv<LZ_EPI_LANCZOS>(ctx, A, u_cur, w, pa));          // :51,:54,:57
         LzFinal fin = {beta, invb, ctx->scalars + (reorth ? S_NRM2_BEFORE : S_NRM2), ctx->flags, j + 1, 1};
-        k_pass_b<<<stream_grid(ctx, n, VT * 4), VT, 0, ctx->stream>>>(n, w, u_cur, alpha, invb, j, ctx->partials,
-                                                                      ctx->tickets + T_DOT, fin);   // :60,:44
-        LZ_LAUNCH_CHECK(ctx);
+        LZ_TRY(launch_pass_b(ctx, n, w, u_cur, alpha, invb, j, fin));          // :60,:44
         if (reorth) {
             LzFinal f2 = {beta, invb, ctx->scalars + S_NRM2, ctx->flags, j + 1, 1};
             LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, reorth == LZ_REORTH_FULL_DGKS));

@@ -1,0 +1,53 @@
+"""Developer micro-benchmarks (CUDA events on the library's stream). Not the contract bench."""
+import os, sys, json, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gpu-implementation-of-signle-and-block-lanczos_b200"))
+import numpy as np
+import torch
+import lanczos_b200 as lz
+
+PEAK = 6435.1
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+def main():
+    which = sys.argv[1:] or ["spmv", "lanczos", "reorth"]
+    torch.cuda.set_device(0); torch.zeros(1, device="cuda")
+    ctx = lz.Context(0)
+    out = {}
+    for name, mk in (("lap2d_4096", lambda: lz.Matrix.laplacian2d(ctx, 4096, 4096)),
+                     ("lap3d_256", lambda: lz.Matrix.laplacian3d(ctx, 256, 256, 256))):
+        A = mk(); n, nnz = A.n_rows, A.nnz
+        x = torch.empty(n, dtype=torch.float64, device="cuda"); y = torch.empty_like(x)
+        lz.check(lz.lib().lz_gen_start_vector(ctx.h, n, 0x5EED, x.data_ptr()))
+        if "spmv" in which:
+            ms = timeit(lambda: lz.spmv(ctx, A, x, y))
+            byt = 12 * nnz + 20 * n + 4
+            out[name + "_spmv"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        if "lanczos" in which:
+            m = 50
+            al = torch.empty(m, dtype=torch.float64, device="cuda"); be = torch.empty_like(al)
+            ms = timeit(lambda: lz.vector_lanczos_async(ctx, A, x, m, al, be), reps=3, warm=1) / m
+            byt = 12 * nnz + 52 * n
+            out[name + "_step_noreorth"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        if "reorth" in which and name == "lap2d_4096":
+            for mode in (1, 2):
+                m = 100
+                al = torch.empty(m, dtype=torch.float64, device="cuda"); be = torch.empty_like(al)
+                ms = timeit(lambda: lz.vector_lanczos_async(ctx, A, x, m, al, be, reorth=mode), reps=2, warm=1)
+                reads = (4 if mode == 1 else 2) * 8 * n * (m * (m + 1) / 2)
+                out[name + "_reorth%d_m100" % mode] = dict(ms_total=ms, it_per_s=m / ms * 1e3, basis_gbs=reads / ms / 1e6)
+        A.close()
+    print(json.dumps(out, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "devbench.json"), "w"), indent=1)
+
+if __name__ == "__main__":
+    main()
