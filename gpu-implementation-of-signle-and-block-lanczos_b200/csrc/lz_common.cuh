@@ -69,10 +69,21 @@ struct lz_ctx {
     int64_t basis_ld;
     int basis_cols;
     lz_comm *comm;
+    // optional per-kernel-class timing (bench.py's roofline leg): CUDA events on ctx->stream
+    int prof_on;
+    int prof_used;
+    cudaEvent_t *prof_ev;   // 2 * LZ_PROF_CAP events
+    int *prof_cls;          // class id per pair
+    double *prof_bytes;     // algorithmic bytes per pair
     int spmv_variant;       // dev-time tuning knobs (env LZ_SPMV_VARIANT / LZ_SPMV_TILE)
     int spmv_tile;
 };
 
+#define LZ_PROF_CAP 16384
+// kernel classes for the profiler
+enum { LZ_K_SPMV = 0, LZ_K_PASSB = 1, LZ_K_PROJECT = 2, LZ_K_UPDATE = 3, LZ_K_SPMM = 4, LZ_K_GRAM = 5, LZ_K_PANEL = 6, LZ_K_SMALL = 7, LZ_K_COMM = 8, LZ_K_CLASSES = 9 };
+void lz_prof_begin(lz_ctx *ctx, int cls, double bytes);
+void lz_prof_end(lz_ctx *ctx);
 #define LZ_PARTIALS_CAP (1 << 20)
 #define LZ_TICKETS 64
 #define LZ_SCALARS 4096

@@ -69,6 +69,10 @@ int lz_ctx_destroy(lz_ctx *ctx)
     cudaFree(ctx->flags);
     cudaFree(ctx->work);
     cudaFree(ctx->basis);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < 2 * LZ_PROF_CAP; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+        delete[] ctx->prof_ev; delete[] ctx->prof_cls; delete[] ctx->prof_bytes;
+    }
     delete ctx;
     return LZ_OK;
 }
@@ -117,6 +121,56 @@ int lz_memset(lz_ctx *ctx, void *dptr, int value, size_t bytes)
 {
     LZ_CHECK(ctx, LZ_ERR_INVALID, "lz_memset: ctx is NULL");
     LZ_CUDA(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return LZ_OK;
+}
+
+}  // extern "C"
+
+void lz_prof_begin(lz_ctx *ctx, int cls, double bytes)
+{
+    if (!ctx->prof_on || ctx->prof_used >= LZ_PROF_CAP) return;
+    ctx->prof_cls[ctx->prof_used] = cls;
+    ctx->prof_bytes[ctx->prof_used] = bytes;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], ctx->stream);
+}
+
+void lz_prof_end(lz_ctx *ctx)
+{
+    if (!ctx->prof_on || ctx->prof_used >= LZ_PROF_CAP) return;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], ctx->stream);
+    ctx->prof_used++;
+}
+
+extern "C" {
+
+// enable (1) / disable (0) per-kernel-class event timing; enabling resets the log
+int lz_ctx_profile(lz_ctx *ctx, int enable)
+{
+    LZ_CHECK(ctx, LZ_ERR_INVALID, "lz_ctx_profile: ctx is NULL");
+    if (enable && !ctx->prof_ev) {
+        ctx->prof_ev = new cudaEvent_t[2 * LZ_PROF_CAP];
+        ctx->prof_cls = new int[LZ_PROF_CAP];
+        ctx->prof_bytes = new double[LZ_PROF_CAP];
+        for (int i = 0; i < 2 * LZ_PROF_CAP; ++i) LZ_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    ctx->prof_on = enable;
+    if (enable) ctx->prof_used = 0;
+    return LZ_OK;
+}
+
+// sums per class since the last enable: launches, milliseconds, algorithmic bytes (arrays of LZ_K_CLASSES = 9)
+int lz_ctx_profile_read(lz_ctx *ctx, int64_t *launches, double *ms, double *bytes)
+{
+    LZ_CHECK(ctx && launches && ms && bytes, LZ_ERR_INVALID, "lz_ctx_profile_read: NULL argument");
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < LZ_K_CLASSES; ++c) { launches[c] = 0; ms[c] = 0.0; bytes[c] = 0.0; }
+    for (int i = 0; i < ctx->prof_used; ++i) {
+        float t = 0.f;
+        LZ_CUDA(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        const int c = ctx->prof_cls[i];
+        launches[c]++; ms[c] += t; bytes[c] += ctx->prof_bytes[i];
+    }
+    ctx->prof_used = 0;
     return LZ_OK;
 }
 

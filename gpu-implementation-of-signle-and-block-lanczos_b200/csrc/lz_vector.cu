@@ -302,14 +302,18 @@ static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, c
                      int need_flag, int dgks_test)
 {
     const size_t smem_p = sizeof(double) * (VT / 32) * (size_t)K;
+    lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
     k_cgs_project<<<g.grid, VT, smem_p, ctx->stream>>>(n, K, g.V, g.ld, w, g.cpart, ctx->flags, need_flag);
     LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
     k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)g.grid, g.cpart, g.c, ctx->flags, need_flag);
     LZ_LAUNCH_CHECK(ctx);
+    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
     k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
         n, K, g.V, g.ld, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test,
         ctx->scalars + S_NRM2_BEFORE);
     LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
     return LZ_OK;
 }
 
@@ -360,9 +364,13 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         pa.qout = q ? q + j : nullptr;
         pa.lc = lc; pa.j = j; pa.first = (j == 0);
         pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
+        lz_prof_begin(ctx, LZ_K_SPMV, 12.0 * (double)A->nnz + 28.0 * (double)n + (reorth ? 8.0 * (double)n : 0.0));
         LZ_TRY(lz_launch_spmv<LZ_EPI_LANCZOS>(ctx, A, u_cur, w, pa));          // :51,:54,:57
+        lz_prof_end(ctx);
         LzFinal fin = {beta, invb, ctx->scalars + (reorth ? S_NRM2_BEFORE : S_NRM2), ctx->flags, j + 1, 1};
+        lz_prof_begin(ctx, LZ_K_PASSB, 24.0 * (double)n);
         LZ_TRY(launch_pass_b(ctx, n, w, u_cur, alpha, invb, j, fin));          // :60,:44
+        lz_prof_end(ctx);
         if (reorth) {
             LzFinal f2 = {beta, invb, ctx->scalars + S_NRM2, ctx->flags, j + 1, 1};
             LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, reorth == LZ_REORTH_FULL_DGKS));

@@ -42,6 +42,8 @@ def lib():
         "lz_ctx_sync": (i32, [vp]),
         "lz_ctx_device": (i32, [vp]),
         "lz_ctx_launch_count": (i64, [vp]),
+        "lz_ctx_profile": (i32, [vp, i32]),
+        "lz_ctx_profile_read": (i32, [vp, P(i64), P(dbl), P(dbl)]),
         "lz_malloc": (i32, [vp, sz, P(vp)]),
         "lz_free": (i32, [vp, vp]),
         "lz_memcpy": (i32, [vp, vp, vp, sz, i32]),
@@ -116,6 +118,17 @@ class Context:
     @property
     def launches(self):
         return int(lib().lz_ctx_launch_count(self.h))
+
+    def profile(self, enable=True):
+        check(lib().lz_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{class: (launches, ms, algorithmic_bytes)} accumulated since profiling was enabled."""
+        n = 9
+        la, ms, by = (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+        check(lib().lz_ctx_profile_read(self.h, la, ms, by))
+        names = ["spmv", "pass_b", "cgs_project", "cgs_update", "spmm", "gram", "panel", "small", "comm"]
+        return {names[i]: (int(la[i]), float(ms[i]), float(by[i])) for i in range(n)}
 
     def close(self):
         if self.h:
