@@ -63,6 +63,8 @@ struct lz_ctx {
     // generic workspace (grown on demand, outside timed regions after the first call)
     void *work;
     size_t work_bytes;
+    void *scratch;          // small second scratch (Gram partials) that never aliases `work`
+    size_t scratch_bytes;
     // Krylov basis slab kept by the full-reorth drivers
     double *basis;
     size_t basis_bytes;
@@ -86,11 +88,12 @@ void lz_prof_begin(lz_ctx *ctx, int cls, double bytes);
 void lz_prof_end(lz_ctx *ctx);
 #define LZ_PARTIALS_CAP (1 << 20)
 #define LZ_TICKETS 64
-#define LZ_SCALARS 4096
+#define LZ_SCALARS 8192
 #define LZ_FLAGS 64
 
 int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out);   // grow-only scratch
 int lz_ctx_basis(lz_ctx *ctx, int64_t ld, int cols, double **out);
+int lz_ctx_scratch(lz_ctx *ctx, size_t bytes, void **out);
 
 // ---- sparse operator -----------------------------------------------------------------
 enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };

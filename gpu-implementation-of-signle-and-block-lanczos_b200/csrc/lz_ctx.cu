@@ -68,6 +68,7 @@ int lz_ctx_destroy(lz_ctx *ctx)
     cudaFree(ctx->scalars);
     cudaFree(ctx->flags);
     cudaFree(ctx->work);
+    cudaFree(ctx->scratch);
     cudaFree(ctx->basis);
     if (ctx->prof_ev) {
         for (int i = 0; i < 2 * LZ_PROF_CAP; ++i) cudaEventDestroy(ctx->prof_ev[i]);
@@ -188,6 +189,21 @@ int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out)
         ctx->work_bytes = want;
     }
     *out = ctx->work;
+    return LZ_OK;
+}
+
+int lz_ctx_scratch(lz_ctx *ctx, size_t bytes, void **out)
+{
+    if (bytes > ctx->scratch_bytes) {
+        LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) LZ_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+        LZ_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
     return LZ_OK;
 }
 

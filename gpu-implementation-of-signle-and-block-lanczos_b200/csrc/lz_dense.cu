@@ -1,0 +1,265 @@
+// lz_dense.cu -- host launchers and C-ABI entry points of the tall-skinny dense products, the
+// b x b matrix square root, and the small helpers of the block path (row extraction, T assembly).
+#include <math.h>
+
+#include "lz_dense_host.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers (shared with lz_block.cu through lz_dense_host.cuh)
+// ---------------------------------------------------------------------------------------------
+static inline int dense_grid(const lz_ctx *ctx, int64_t n)
+{
+    int64_t slabs = (n + 31) / 32;
+    int64_t want = (slabs + LZ_DENSE_WARPS - 1) / LZ_DENSE_WARPS;
+    int64_t cap = (int64_t)ctx->sm_count * 4;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+template <bool RMX, bool RMY>
+static int gram_launch(lz_ctx *ctx, int64_t n, int bw, const double *X, int64_t ldx, const double *Y, int64_t ldy,
+                       double *G, int mode, double *gpart, int grid)
+{
+    lz_prof_begin(ctx, LZ_K_GRAM, 8.0 * (double)n * bw * (X == Y ? 1.0 : 2.0));
+    if (bw == 8) k_gram_dmma<8, RMX, RMY><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, gpart);
+    else if (bw == 16) k_gram_dmma<16, RMX, RMY><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, gpart);
+    else if (bw == 32) k_gram_dmma<32, RMX, RMY><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, gpart);
+    else k_gram_simt<RMX, RMY><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, bw, X, ldx, Y, ldy, gpart);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    k_gram_reduce<<<1, 256, 0, ctx->stream>>>(bw, grid, gpart, G, mode);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_gram(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *X, int64_t ldx, const double *Y, int64_t ldy,
+            double *G, int mode)
+{
+    const int grid = dense_grid(ctx, n);
+    void *w;
+    LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * bw * bw, &w));
+    if (rm) return gram_launch<true, true>(ctx, n, bw, X, ldx, Y, ldy, G, mode, (double *)w, grid);
+    return gram_launch<false, false>(ctx, n, bw, X, ldx, Y, ldy, G, mode, (double *)w, grid);
+}
+
+template <bool RM>
+static int panel_launch(lz_ctx *ctx, int64_t n, int bw, const double *T, int64_t ldt, const double *S, double beta,
+                        double alpha, double *R, int64_t ldr, double *G, double *gpart, int grid)
+{
+    const bool gram = G != nullptr;
+    lz_prof_begin(ctx, LZ_K_PANEL, 8.0 * (double)n * bw * (beta != 0.0 ? 3.0 : 2.0));
+#define LZ_PANEL_CASE(B)                                                                                            \
+    if (gram) k_panel_dmma<B, RM, RM, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, T, ldt, S, beta, alpha, R, ldr, gpart); \
+    else k_panel_dmma<B, RM, RM, false><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, T, ldt, S, beta, alpha, R, ldr, gpart)
+    if (bw == 8) { LZ_PANEL_CASE(8); }
+    else if (bw == 16) { LZ_PANEL_CASE(16); }
+    else if (bw == 32) { LZ_PANEL_CASE(32); }
+    else {
+        k_panel_simt<RM, RM><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, bw, T, ldt, S, beta, alpha, R, ldr);
+    }
+#undef LZ_PANEL_CASE
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    if (gram) {
+        if (bw == 8 || bw == 16 || bw == 32) {
+            k_gram_reduce<<<1, 256, 0, ctx->stream>>>(bw, grid, gpart, G, 0);
+            LZ_LAUNCH_CHECK(ctx);
+        } else {
+            return gram_launch<RM, RM>(ctx, n, bw, R, ldr, R, ldr, G, 0, gpart, grid);
+        }
+    }
+    return LZ_OK;
+}
+
+int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t ldt, const double *S, double beta,
+             double alpha, double *R, int64_t ldr, double *G_opt)
+{
+    const int grid = dense_grid(ctx, n);
+    void *w = nullptr;
+    if (G_opt) LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * bw * bw, &w));
+    if (rm) return panel_launch<true>(ctx, n, bw, T, ldt, S, beta, alpha, R, ldr, G_opt, (double *)w, grid);
+    return panel_launch<false>(ctx, n, bw, T, ldt, S, beta, alpha, R, ldr, G_opt, (double *)w, grid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// b x b symmetric eigen-decomposition + matrix square root, one CTA.
+// Parallel cyclic Jacobi (round-robin pairing: b/2 disjoint rotations per round, b-1 rounds per
+// sweep), then S = V sqrt|L| V^T, Sinv = V |L|^{-1/2} V^T  -- the semantics of
+// cusolverDnDsyevjBatched + custom_mult2 (utils/lib_utils.hpp:650-745) and of
+// sqrtm::My_sqrtm_cusolver (kernels/my_sqrtm_cusolver.hpp:174-361).  Reads the lower triangle.
+// ---------------------------------------------------------------------------------------------
+#define SQ_LD 33
+__global__ void __launch_bounds__(1024) k_sqrtm(int b, double *__restrict__ S, double *__restrict__ Sinv, int *flags)
+{
+    __shared__ double A[32 * SQ_LD], V[32 * SQ_LD], cs[32], sn[32], lam[32];
+    __shared__ int pp[32], qq[32];
+    __shared__ double off2, dia2;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int r = tid % b, c = tid / b;           // valid when tid < b*b
+    const bool act = tid < b * b;
+    if (act) {
+        A[r + c * SQ_LD] = (r >= c) ? S[r + c * b] : S[c + r * b];
+        V[r + c * SQ_LD] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int m = (b + 1) & ~1;                   // players in the round-robin tournament (pad odd b)
+    for (int sweep = 0; sweep < 30 && b > 1; ++sweep) {
+        // convergence test: off-diagonal mass negligible against the diagonal
+        if (tid == 0) { off2 = 0.0; dia2 = 0.0; }
+        __syncthreads();
+        {
+            const double v = act ? A[r + c * SQ_LD] : 0.0;
+            double o = (act && r != c) ? v * v : 0.0, d = (act && r == c) ? v * v : 0.0;
+            o = lz_warp_sum(o); d = lz_warp_sum(d);
+            if ((tid & 31) == 0) { atomicAdd(&off2, o); atomicAdd(&dia2, d); }
+        }
+        __syncthreads();
+        if (off2 <= 1e-34 * dia2) break;
+        for (int round = 0; round < m - 1; ++round) {
+            // pairing of round `round`: player 0 fixed, the others rotate
+            if (tid < m / 2) {
+                int a0 = (tid == 0) ? 0 : 1 + (tid - 1 + round) % (m - 1);
+                int a1 = 1 + (m - 1 - tid - 1 + round) % (m - 1);
+                int p = min(a0, a1), q = max(a0, a1);
+                double cc = 1.0, ss = 0.0;
+                if (q < b) {
+                    const double apq = A[p + q * SQ_LD];
+                    if (apq != 0.0) {
+                        const double tau = (A[q + q * SQ_LD] - A[p + p * SQ_LD]) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        cc = 1.0 / sqrt(1.0 + t * t);
+                        ss = t * cc;
+                    }
+                } else { p = q = -1; }
+                pp[tid] = p; qq[tid] = q; cs[tid] = cc; sn[tid] = ss;
+            }
+            __syncthreads();
+            // columns: A <- A J, V <- V J   (thread (pair, k) handles row k of the two columns)
+            for (int e = tid; e < (m / 2) * b; e += nthr) {
+                const int pr = e / b, k = e % b, p = pp[pr], q = qq[pr];
+                if (p >= 0) {
+                    const double cc = cs[pr], ss = sn[pr];
+                    const double akp = A[k + p * SQ_LD], akq = A[k + q * SQ_LD];
+                    A[k + p * SQ_LD] = cc * akp - ss * akq;
+                    A[k + q * SQ_LD] = ss * akp + cc * akq;
+                    const double vkp = V[k + p * SQ_LD], vkq = V[k + q * SQ_LD];
+                    V[k + p * SQ_LD] = cc * vkp - ss * vkq;
+                    V[k + q * SQ_LD] = ss * vkp + cc * vkq;
+                }
+            }
+            __syncthreads();
+            // rows: A <- J^T A
+            for (int e = tid; e < (m / 2) * b; e += nthr) {
+                const int pr = e / b, k = e % b, p = pp[pr], q = qq[pr];
+                if (p >= 0) {
+                    const double cc = cs[pr], ss = sn[pr];
+                    const double apk = A[p + k * SQ_LD], aqk = A[q + k * SQ_LD];
+                    A[p + k * SQ_LD] = cc * apk - ss * aqk;
+                    A[q + k * SQ_LD] = ss * apk + cc * aqk;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < b) {
+        lam[tid] = fabs(A[tid + tid * SQ_LD]);
+        if (!(lam[tid] > 0.0) || !isfinite(lam[tid])) atomicMin(flags, 0);     // singular / non-finite block
+    }
+    __syncthreads();
+    if (act) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < b; ++i) {
+            const double rt = sqrt(lam[i]);
+            s1 += V[r + i * SQ_LD] * rt * V[c + i * SQ_LD];
+            s2 += V[r + i * SQ_LD] * 1.0 / rt * V[c + i * SQ_LD];
+        }
+        S[r + c * b] = s1;
+        Sinv[r + c * b] = s2;
+    }
+}
+
+int lz_sqrtm_launch(lz_ctx *ctx, int b, double *S, double *Sinv, int *flag)
+{
+    lz_prof_begin(ctx, LZ_K_SMALL, 0.0);
+    int threads = ((b * b + 31) / 32) * 32;
+    k_sqrtm<<<1, threads, 0, ctx->stream>>>(b, S, Sinv, flag);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    return LZ_OK;
+}
+
+// q[off + c] = Q[lc, c]
+template <bool RM>
+__global__ void k_copy_row(int64_t lc, int b, const double *__restrict__ Q, int64_t ld, double *__restrict__ q, int64_t off)
+{
+    const LzLay<RM> l{ld, b};
+    if (threadIdx.x < b) q[off + threadIdx.x] = Q[l.at(lc, threadIdx.x)];
+}
+
+int lz_copy_row_launch(lz_ctx *ctx, int64_t lc, int b, bool rm, const double *Q, int64_t ld, double *q, int64_t off)
+{
+    if (rm) k_copy_row<true><<<1, 32, 0, ctx->stream>>>(lc, b, Q, ld, q, off);
+    else k_copy_row<false><<<1, 32, 0, ctx->stream>>>(lc, b, Q, ld, q, off);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+// dense block-tridiagonal T from alpha[0..m), beta[1..m)   (objects/tridiagonal_matrix.hpp:13-54,90-127)
+__global__ void k_assemble_T(int m, int b, const double *__restrict__ alpha, const double *__restrict__ beta, double *__restrict__ T)
+{
+    const int N = m * b;
+    const int64_t total = (int64_t)m * b * b;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int blk = (int)(e / (b * b)), i = (int)(e % (b * b)), r = i % b, c = i / b;
+        T[(blk * b + r) + (int64_t)(blk * b + c) * N] = alpha[e];
+        if (blk >= 1) {
+            const double v = beta[e];
+            T[((blk - 1) * b + r) + (int64_t)(blk * b + c) * N] = v;
+            T[(blk * b + c) + (int64_t)((blk - 1) * b + r) * N] = v;
+        }
+    }
+}
+
+extern "C" {
+
+int lz_mm_tt(lz_ctx *ctx, int64_t n, int b, const double *T, int64_t ld, double *R)
+{
+    LZ_CHECK(ctx && T && R && n > 0 && b >= 1 && b <= 32 && ld >= n, LZ_ERR_INVALID, "lz_mm_tt: bad arguments (b must be 1..32)");
+    return lz_gram(ctx, n, b, false, T, ld, T, ld, R, 0);
+}
+
+int lz_mm_tt2(lz_ctx *ctx, int64_t n, int b, const double *T1, int64_t ld1, const double *T2, int64_t ld2, double *R)
+{
+    LZ_CHECK(ctx && T1 && T2 && R && n > 0 && b >= 1 && b <= 32 && ld1 >= n && ld2 >= n, LZ_ERR_INVALID, "lz_mm_tt2: bad arguments");
+    return lz_gram(ctx, n, b, false, T1, ld1, T2, ld2, R, 1);
+}
+
+int lz_mm_ts(lz_ctx *ctx, int64_t n, int b, double beta, double alpha, const double *T, int64_t ldt, const double *S,
+             double *R, int64_t ldr)
+{
+    LZ_CHECK(ctx && T && S && R && n > 0 && b >= 1 && b <= 32 && ldt >= n && ldr >= n, LZ_ERR_INVALID, "lz_mm_ts: bad arguments");
+    return lz_panel(ctx, n, b, false, T, ldt, S, beta, alpha, R, ldr, nullptr);
+}
+
+int lz_sqrtm(lz_ctx *ctx, int b, double *S, double *Sinv)
+{
+    LZ_CHECK(ctx && S && Sinv && b >= 1 && b <= 32, LZ_ERR_INVALID, "lz_sqrtm: bad arguments (b must be 1..32)");
+    return lz_sqrtm_launch(ctx, b, S, Sinv, ctx->flags + 2);
+}
+
+int lz_copy_row(lz_ctx *ctx, int64_t lc, int b, const double *Q, int64_t ld, double *q, int64_t off)
+{
+    LZ_CHECK(ctx && Q && q && b >= 1 && b <= 32 && lc >= 0 && lc < ld, LZ_ERR_INVALID, "lz_copy_row: bad arguments");
+    return lz_copy_row_launch(ctx, lc, b, false, Q, ld, q, off);
+}
+
+int lz_assemble_T(lz_ctx *ctx, int m, int b, const double *alpha, const double *beta, double *T)
+{
+    LZ_CHECK(ctx && alpha && beta && T && m >= 1 && b >= 1, LZ_ERR_INVALID, "lz_assemble_T: bad arguments");
+    const size_t N = (size_t)m * b;
+    LZ_CUDA(cudaMemsetAsync(T, 0, sizeof(double) * N * N, ctx->stream));
+    k_assemble_T<<<64, 256, 0, ctx->stream>>>(m, b, alpha, beta, T);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+}  // extern "C"

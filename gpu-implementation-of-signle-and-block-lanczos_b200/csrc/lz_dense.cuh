@@ -1,0 +1,289 @@
+// lz_dense.cuh -- tall-skinny dense contractions of block Lanczos on the fp64 tensor pipe.
+//
+// Replaces the reference's mm_tt / mm_tt2 / mm_ts SIMT kernels (kernels/mm_tt.hpp, mm_tt2.hpp,
+// mm_ts.hpp -- float only, and mm_tt/mm_tt2 multiply .z*.x), their cuBLAS
+// stand-ins (utils/lib_utils.hpp:28-202) and the non-compiling wmma sketches under
+// tensor_core_unfinished_work/.  tcgen05.mma has no fp64 kind (ptxas rejects .kind::f64), so the
+// native fp64 tensor instruction on sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4); operands go
+// global -> registers directly in fragment order (every 32-byte sector is used once), accumulators
+// stay in registers, and partial results are combined in a fixed order (deterministic).
+//
+// Panels are n x BW.  Layout is a template parameter: row-major (BW contiguous, the drivers'
+// internal layout) or column-major with leading dimension ld (the reference's Dense_matrix layout,
+// objects/dense_matrix.hpp:9).  BW in {8,16,32} runs on DMMA; any 1 <= BW <= 32 has a SIMT path.
+#pragma once
+#include "lz_common.cuh"
+
+template <bool RM>
+struct LzLay {
+    int64_t ld;   // column-major leading dimension (ignored for row-major)
+    int bw;
+    __device__ __forceinline__ int64_t at(int64_t i, int c) const { return RM ? i * bw + c : (int64_t)c * ld + i; }
+};
+
+__device__ __forceinline__ void lz_dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+#define LZ_DENSE_THREADS 256
+#define LZ_DENSE_WARPS (LZ_DENSE_THREADS / 32)
+
+// ---------------------------------------------------------------------------------------------
+// G_partial[cta] = X^T Y over the CTA's rows  (BW x BW, column-major G[p + q*BW]).
+// Each warp walks 32-row slabs; per 4-row group it loads BW/8 A fragments (X^T) and BW/8 B
+// fragments (Y) -- one double per thread each -- and issues (BW/8)^2 DMMAs.
+// ---------------------------------------------------------------------------------------------
+template <int BW, bool RMX, bool RMY>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_gram_dmma(int64_t n, const double *__restrict__ X, int64_t ldx, const double *__restrict__ Y, int64_t ldy,
+            double *__restrict__ gpart)
+{
+    constexpr int T = BW / 8;
+    const LzLay<RMX> lx{ldx, BW};
+    const LzLay<RMY> ly{ldy, BW};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    double acc[T][T][2];
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int b = 0; b < T; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    const int64_t n_slabs = (n + 31) / 32;
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+        const int64_t base = slab * 32;
+        if (base + 32 <= n) {
+#pragma unroll 2
+            for (int g = 0; g < 8; ++g) {
+                const int64_t i = base + g * 4 + kk;
+                double xa[T], yb[T];
+#pragma unroll
+                for (int t = 0; t < T; ++t) { xa[t] = __ldg(X + lx.at(i, t * 8 + mm)); yb[t] = __ldg(Y + ly.at(i, t * 8 + mm)); }
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) lz_dmma(acc[a][b][0], acc[a][b][1], xa[a], yb[b]);
+            }
+        } else {
+            for (int g = 0; g < 8; ++g) {
+                const int64_t i = base + g * 4 + kk;
+                double xa[T], yb[T];
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    xa[t] = i < n ? X[lx.at(i, t * 8 + mm)] : 0.0;
+                    yb[t] = i < n ? Y[ly.at(i, t * 8 + mm)] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) lz_dmma(acc[a][b][0], acc[a][b][1], xa[a], yb[b]);
+            }
+        }
+    }
+    // combine the warps of the CTA in a fixed order (warp 0 first), then publish the CTA partial
+    __shared__ double sm[BW * BW];
+    for (int w = 0; w < LZ_DENSE_WARPS; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int a = 0; a < T; ++a)
+#pragma unroll
+                for (int b = 0; b < T; ++b) {
+                    const int p = a * 8 + mm, q = b * 8 + 2 * kk;
+                    if (w == 0) { sm[p + q * BW] = acc[a][b][0]; sm[p + (q + 1) * BW] = acc[a][b][1]; }
+                    else { sm[p + q * BW] += acc[a][b][0]; sm[p + (q + 1) * BW] += acc[a][b][1]; }
+                }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < BW * BW; e += LZ_DENSE_THREADS) gpart[(size_t)blockIdx.x * BW * BW + e] = sm[e];
+}
+
+// generic SIMT Gram for any 1 <= bw <= 32: thread e owns output (p,q) = (e % bw, e / bw);
+// rows are staged through shared memory 32 at a time.
+template <bool RMX, bool RMY>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_gram_simt(int64_t n, int bw, const double *__restrict__ X, int64_t ldx, const double *__restrict__ Y, int64_t ldy,
+            double *__restrict__ gpart)
+{
+    const LzLay<RMX> lx{ldx, bw};
+    const LzLay<RMY> ly{ldy, bw};
+    __shared__ double xs[32][33], ys[32][33];
+    double acc[4] = {0, 0, 0, 0};                       // outputs e = tid + k*256 (bw*bw <= 1024)
+    const int64_t n_slabs = (n + 31) / 32;
+    for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        const int64_t base = slab * 32;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * bw; e += LZ_DENSE_THREADS) {
+            const int r = RMX ? e / bw : e % 32, c = RMX ? e % bw : e / 32;
+            const int64_t i = base + r;
+            xs[r][c] = i < n ? X[lx.at(i, c)] : 0.0;
+            ys[r][c] = i < n ? Y[ly.at(i, c)] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = threadIdx.x + k * LZ_DENSE_THREADS;
+            if (e < bw * bw) {
+                const int p = e % bw, q = e / bw;
+                double s = acc[k];
+                for (int r = 0; r < 32; ++r) s = fma(xs[r][p], ys[r][q], s);
+                acc[k] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x + k * LZ_DENSE_THREADS;
+        if (e < bw * bw) gpart[(size_t)blockIdx.x * bw * bw + e] = acc[k];
+    }
+}
+
+// G = sum over CTA partials (fixed order).  mode 0: G as is; 1: 0.5*G + 0.5*G^T (mm_tt2, lib_utils.hpp:165-202)
+static __global__ void k_gram_reduce(int bw, int n_parts, const double *__restrict__ gpart, double *__restrict__ G, int mode)
+{
+    __shared__ double tmp[32 * 32];
+    for (int e = threadIdx.x; e < bw * bw; e += blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < n_parts; ++p) s += gpart[(size_t)p * bw * bw + e];
+        tmp[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < bw * bw; e += blockDim.x) {
+        const int p = e % bw, q = e / bw;
+        G[e] = mode == 0 ? tmp[e] : 0.5 * tmp[p + q * bw] + 0.5 * tmp[q + p * bw];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// R = beta * R + alpha * T S     (T, R: n x BW panels; S: BW x BW column-major, device).
+// Optionally (GRAM) also G_partial = R_new^T R_new, fused in the same pass through a per-warp
+// shared-memory transpose of the freshly written 8-row group.
+// R may alias T (rows are independent and every group reads T before it writes R).
+// ---------------------------------------------------------------------------------------------
+template <int BW, bool RMT, bool RMR, bool GRAM>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_panel_dmma(int64_t n, const double *T_, int64_t ldt, const double *__restrict__ S, double beta, double alpha,
+             double *R_, int64_t ldr, double *__restrict__ gpart)
+{
+    constexpr int NT = BW / 8, KT = BW / 4;
+    const LzLay<RMT> lt{ldt, BW};
+    const LzLay<RMR> lr{ldr, BW};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    // B fragments of alpha*S: B[k][nn] = S[kt*4 + kk, nt*8 + mm]
+    double sb[KT][NT];
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) sb[kt][nt] = alpha * S[(kt * 4 + kk) + (nt * 8 + mm) * BW];
+    double gacc[GRAM ? NT : 1][GRAM ? NT : 1][2];
+    if (GRAM) {
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int b = 0; b < NT; ++b) gacc[a][b][0] = gacc[a][b][1] = 0.0;
+    }
+    __shared__ double stage[GRAM ? LZ_DENSE_WARPS : 1][GRAM ? 8 * (BW + 1) : 1];
+
+    const int64_t n_slabs = (n + 31) / 32;
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+#pragma unroll 2
+        for (int g = 0; g < 4; ++g) {
+            const int64_t i = slab * 32 + g * 8 + mm;      // this thread's row in A / C fragments
+            const bool ok = i < n;
+            double ta[KT];
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) ta[kt] = ok ? T_[lt.at(i, kt * 4 + kk)] : 0.0;
+            double d[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                d[nt][0] = d[nt][1] = 0.0;
+                if (beta != 0.0 && ok) {
+                    d[nt][0] = beta * R_[lr.at(i, nt * 8 + 2 * kk)];
+                    d[nt][1] = beta * R_[lr.at(i, nt * 8 + 2 * kk + 1)];
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) lz_dmma(d[nt][0], d[nt][1], ta[kt], sb[kt][nt]);
+            if (ok) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    if (RMR) {
+                        *reinterpret_cast<double2 *>(R_ + lr.at(i, nt * 8 + 2 * kk)) = make_double2(d[nt][0], d[nt][1]);
+                    } else {
+                        R_[lr.at(i, nt * 8 + 2 * kk)] = d[nt][0];
+                        R_[lr.at(i, nt * 8 + 2 * kk + 1)] = d[nt][1];
+                    }
+                }
+            }
+            if (GRAM) {
+                // 8 new rows -> shared (row mm, cols) -> Gram fragments: two k-steps of 4 rows
+                double *st = stage[warp];
+                __syncwarp();
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    st[mm * (BW + 1) + nt * 8 + 2 * kk] = ok ? d[nt][0] : 0.0;
+                    st[mm * (BW + 1) + nt * 8 + 2 * kk + 1] = ok ? d[nt][1] : 0.0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double fr[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) fr[t] = st[(h * 4 + kk) * (BW + 1) + t * 8 + mm];
+#pragma unroll
+                    for (int a = 0; a < NT; ++a)
+#pragma unroll
+                        for (int b = 0; b < NT; ++b) lz_dmma(gacc[a][b][0], gacc[a][b][1], fr[a], fr[b]);
+                }
+            }
+        }
+    }
+    if (GRAM) {
+        __shared__ double sm[BW * BW];
+        for (int w = 0; w < LZ_DENSE_WARPS; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int b = 0; b < NT; ++b) {
+                        const int p = a * 8 + mm, q = b * 8 + 2 * kk;
+                        if (w == 0) { sm[p + q * BW] = gacc[a][b][0]; sm[p + (q + 1) * BW] = gacc[a][b][1]; }
+                        else { sm[p + q * BW] += gacc[a][b][0]; sm[p + (q + 1) * BW] += gacc[a][b][1]; }
+                    }
+            }
+            __syncthreads();
+        }
+        for (int e = threadIdx.x; e < BW * BW; e += LZ_DENSE_THREADS) gpart[(size_t)blockIdx.x * BW * BW + e] = sm[e];
+    }
+}
+
+// generic SIMT panel update for any bw: one thread per row, S in shared memory
+template <bool RMT, bool RMR>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_panel_simt(int64_t n, int bw, const double *T_, int64_t ldt, const double *__restrict__ S, double beta, double alpha,
+             double *R_, int64_t ldr)
+{
+    const LzLay<RMT> lt{ldt, bw};
+    const LzLay<RMR> lr{ldr, bw};
+    __shared__ double ss[32 * 32];
+    for (int e = threadIdx.x; e < bw * bw; e += LZ_DENSE_THREADS) ss[e] = S[e];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * LZ_DENSE_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * LZ_DENSE_THREADS + threadIdx.x; i < n; i += stride) {
+        double row[32];
+        for (int k = 0; k < bw; ++k) row[k] = T_[lt.at(i, k)];
+        for (int j = 0; j < bw; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < bw; ++k) s = fma(row[k], ss[k + j * bw], s);
+            const double r = beta != 0.0 ? beta * R_[lr.at(i, j)] : 0.0;
+            R_[lr.at(i, j)] = r + alpha * s;
+        }
+    }
+}

@@ -1,0 +1,12 @@
+// lz_dense_host.cuh -- host-side launchers of the dense block kernels shared by lz_dense.cu and lz_block.cu
+#pragma once
+#include "lz_dense.cuh"
+
+// G = X^T Y (mode 0) or 0.5 (X^T Y) + 0.5 (X^T Y)^T (mode 1); rm: panels row-major (ld ignored) or column-major
+int lz_gram(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *X, int64_t ldx, const double *Y, int64_t ldy,
+            double *G, int mode);
+// R = beta R + alpha T S ; G_opt (device bw*bw) additionally receives R_new^T R_new
+int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t ldt, const double *S, double beta,
+             double alpha, double *R, int64_t ldr, double *G_opt);
+int lz_sqrtm_launch(lz_ctx *ctx, int b, double *S, double *Sinv, int *flag);
+int lz_copy_row_launch(lz_ctx *ctx, int64_t lc, int b, bool rm, const double *Q, int64_t ld, double *q, int64_t off);
