@@ -178,7 +178,8 @@ def run_gpu(args, wl, rank, world):
     b = torch.empty(n_local, dtype=torch.float64, device="cuda")
     if world > 1:
         lo, hi = lz.C.c_int64(), lz.C.c_int64()
-        lz.check(lz.lib().lz_partition_rows(n_global, world, rank, lz.C.byref(lo), lz.C.byref(hi)))
+        granule = n_global // wl["dims"][-1]
+        lz.check(lz.lib().lz_partition_rows(n_global, granule, world, rank, lz.C.byref(lo), lz.C.byref(hi)))
         full = torch.empty(n_global, dtype=torch.float64, device="cuda")
         lz.check(lz.lib().lz_gen_start_vector(ctx.h, n_global, 0x5EED, full.data_ptr()))
         ctx.sync()

@@ -94,6 +94,12 @@ void lz_prof_end(lz_ctx *ctx);
 int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out);   // grow-only scratch
 int lz_ctx_basis(lz_ctx *ctx, int64_t ld, int cols, double **out);
 int lz_ctx_scratch(lz_ctx *ctx, size_t bytes, void **out);
+// communicator hooks (lz_multi.cu); all enqueue on ctx->stream
+int lz_comm_world(const lz_ctx *ctx);
+int lz_comm_rank(const lz_ctx *ctx);
+int lz_comm_allreduce_sum(lz_ctx *ctx, double *buf, size_t count);
+// u points at the local rows; hlo entries are received just below it, hhi entries just above u[n)
+int lz_comm_halo_exchange(lz_ctx *ctx, double *u, int64_t n, int64_t hlo, int64_t hhi);
 
 // ---- sparse operator -----------------------------------------------------------------
 enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };

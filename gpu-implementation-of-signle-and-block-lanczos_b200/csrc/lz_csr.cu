@@ -124,24 +124,31 @@ __global__ void k_ell4_interleave(int64_t n, const double *__restrict__ data, co
 // ---------------------------------------------------------------------------------------------
 // generators
 // ---------------------------------------------------------------------------------------------
-__global__ void k_lap2d(int64_t nx, int64_t ny, int32_t *__restrict__ rowptr, int32_t *__restrict__ colidx,
-                        double *__restrict__ vals)
+// rows [row0, row0 + n_local) of the nx*ny 5-point Laplacian, column ids shifted by col_shift
+__device__ __host__ inline int64_t lz_lap2d_before(int64_t i, int64_t nx, int64_t ny)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t n = nx * ny;
-    if (i > n) return;
-    int64_t y = i / nx, x = i - y * nx;
-    if (i == n) { y = ny; x = 0; }
     // entries before row i = 5 i - (#rows<i on each of the four boundaries)
-    int64_t before = 5 * i - min(i, nx) - max((int64_t)0, i - (ny - 1) * nx) - (y + (x > 0)) - y;
-    rowptr[i] = (int32_t)before;
-    if (i == n) return;
-    int64_t p = before;
-    if (y > 0)      { colidx[p] = (int32_t)(i - nx); vals[p++] = -1.0; }
-    if (x > 0)      { colidx[p] = (int32_t)(i - 1);  vals[p++] = -1.0; }
-    colidx[p] = (int32_t)i; vals[p++] = 4.0;
-    if (x < nx - 1) { colidx[p] = (int32_t)(i + 1);  vals[p++] = -1.0; }
-    if (y < ny - 1) { colidx[p] = (int32_t)(i + nx); vals[p++] = -1.0; }
+    int64_t y = i / nx, x = i - y * nx;
+    if (i >= nx * ny) { y = ny; x = 0; }
+    const int64_t b0 = i < nx ? i : nx, b1 = i - (ny - 1) * nx > 0 ? i - (ny - 1) * nx : 0;
+    return 5 * i - b0 - b1 - (y + (x > 0)) - y;
+}
+
+__global__ void k_lap2d(int64_t nx, int64_t ny, int64_t row0, int64_t n_local, int64_t col_shift,
+                        int32_t *__restrict__ rowptr, int32_t *__restrict__ colidx, double *__restrict__ vals)
+{
+    int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li > n_local) return;
+    const int64_t i = row0 + li;
+    int64_t p = lz_lap2d_before(i, nx, ny) - lz_lap2d_before(row0, nx, ny);
+    rowptr[li] = (int32_t)p;
+    if (li == n_local) return;
+    const int64_t y = i / nx, x = i - y * nx, c = i - col_shift;
+    if (y > 0)      { colidx[p] = (int32_t)(c - nx); vals[p++] = -1.0; }
+    if (x > 0)      { colidx[p] = (int32_t)(c - 1);  vals[p++] = -1.0; }
+    colidx[p] = (int32_t)c; vals[p++] = 4.0;
+    if (x < nx - 1) { colidx[p] = (int32_t)(c + 1);  vals[p++] = -1.0; }
+    if (y < ny - 1) { colidx[p] = (int32_t)(c + nx); vals[p++] = -1.0; }
 }
 
 // rows [row0, row0 + n_local) of the nx*ny*nz 7-point Laplacian.  Column ids are written as
@@ -230,6 +237,24 @@ int lz_gen_lap3d_rows(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int64_t r
     LZ_CUDA(cudaMalloc(&va, sizeof(double) * (nnz + 8)));
     A->rowptr = rp; A->colidx = ci; A->vals = va;
     k_lap3d<<<(unsigned)((n_local + 1 + 255) / 256), 256, 0, ctx->stream>>>(nx, ny, nz, row0, n_local, col_shift, rp, ci, va);
+    LZ_LAUNCH_CHECK(ctx);
+    return finish_csr(ctx, A, out);
+}
+
+int lz_gen_lap2d_rows(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t row0, int64_t n_local, int64_t col_shift,
+                      int64_t n_cols, lz_matrix **out)
+{
+    const int64_t nnz = lz_lap2d_before(row0 + n_local, nx, ny) - lz_lap2d_before(row0, nx, ny);
+    LZ_TRY(check_dims(n_local, n_cols, nnz));
+    lz_matrix *A = new_matrix(ctx, LZ_FMT_CSR, n_local, n_cols, nnz);
+    A->owns = 1;
+    int32_t *rp, *ci;
+    double *va;
+    LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n_local + 1)));
+    LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * (nnz + 8)));
+    LZ_CUDA(cudaMalloc(&va, sizeof(double) * (nnz + 8)));
+    A->rowptr = rp; A->colidx = ci; A->vals = va;
+    k_lap2d<<<(unsigned)((n_local + 1 + 255) / 256), 256, 0, ctx->stream>>>(nx, ny, row0, n_local, col_shift, rp, ci, va);
     LZ_LAUNCH_CHECK(ctx);
     return finish_csr(ctx, A, out);
 }
@@ -370,18 +395,7 @@ int lz_gen_laplacian2d(lz_ctx *ctx, int64_t nx, int64_t ny, lz_matrix **out)
 {
     LZ_CHECK(ctx && out && nx >= 2 && ny >= 2, LZ_ERR_INVALID, "lz_gen_laplacian2d: bad arguments");
     LZ_CUDA(cudaSetDevice(ctx->device));
-    const int64_t n = nx * ny, nnz = 5 * n - 2 * nx - 2 * ny;
-    LZ_TRY(check_dims(n, n, nnz));
-    lz_matrix *A = new_matrix(ctx, LZ_FMT_CSR, n, n, nnz);
-    A->owns = 1;
-    int32_t *rp, *ci; double *va;
-    LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n + 1)));
-    LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * (nnz + 8)));
-    LZ_CUDA(cudaMalloc(&va, sizeof(double) * (nnz + 8)));
-    A->rowptr = rp; A->colidx = ci; A->vals = va;
-    k_lap2d<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(nx, ny, rp, ci, va);
-    LZ_LAUNCH_CHECK(ctx);
-    return finish_csr(ctx, A, out);
+    return lz_gen_lap2d_rows(ctx, nx, ny, 0, nx * ny, 0, nx * ny, out);
 }
 
 int lz_gen_laplacian3d(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, lz_matrix **out)

@@ -299,7 +299,7 @@ struct LzCgs {
 
 // one CGS sweep of w against the first K basis columns; the update's epilogue finalises beta[jn]
 static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin,
-                     int need_flag, int dgks_test)
+                     int need_flag, int dgks_test, bool sharded)
 {
     const size_t smem_p = sizeof(double) * (VT / 32) * (size_t)K;
     lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
@@ -308,6 +308,7 @@ static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, c
     lz_prof_end(ctx);
     k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)g.grid, g.cpart, g.c, ctx->flags, need_flag);
     LZ_LAUNCH_CHECK(ctx);
+    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
     k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
         n, K, g.V, g.ld, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test,
@@ -319,28 +320,46 @@ static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, c
 
 __global__ void k_copy_scalar(const double *src, double *dst) { *dst = *src; }
 
+// sharded runs: the local partial has been all-reduced into *nrm2; finalise beta[jn] from it
+__global__ void k_finalize_beta(const double *nrm2, double *beta, double *invb, int *flags, int jn)
+{
+    const LzFinal f = {beta, invb, const_cast<double *>(nrm2), flags, jn, 1};
+    lz_finalize_beta(f, *nrm2);
+}
+
 // The single-vector driver.  Device arrays: alpha[m], beta[m+1], invb[m+1].
+// With a communicator attached to the context (lz_comm_init) the operator is this rank's row slab,
+// b holds the local rows, every gather source carries [lower halo | local | upper halo] and every
+// reduction is completed by an all-reduce before it is consumed; without one the same code runs the
+// single-GPU path with no collective at all.
 static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
                                double *alpha, double *beta, double *invb, double *q)
 {
     const int64_t n = A->n_rows;
-    LZ_CHECK(A->n_cols == n, LZ_ERR_INVALID, "lz_vector_lanczos: operator must be square (%lld x %lld)", (long long)n, (long long)A->n_cols);
-    LZ_CHECK(lc >= 0 && lc < n, LZ_ERR_INVALID, "lz_vector_lanczos: lc %lld out of range", (long long)lc);
+    const bool sharded = ctx->comm != nullptr && lz_comm_world(ctx) > 1;
+    const int64_t hlo = A->halo_lo, hhi = A->halo_hi;
+    LZ_CHECK(A->n_cols == n + hlo + hhi, LZ_ERR_INVALID, "lz_vector_lanczos: operator must be square (%lld x %lld)", (long long)n, (long long)A->n_cols);
+    LZ_CHECK(sharded || (hlo == 0 && hhi == 0), LZ_ERR_INVALID, "lz_vector_lanczos: a sharded operator needs lz_comm_init");
+    LZ_CHECK(lc >= -1 && lc < n, LZ_ERR_INVALID, "lz_vector_lanczos: lc %lld out of range", (long long)lc);
     LZ_CHECK(reorth >= LZ_REORTH_NONE && reorth <= LZ_REORTH_FULL_DGKS, LZ_ERR_INVALID, "lz_vector_lanczos: reorth mode %d", reorth);
+    LZ_CHECK(!(sharded && reorth == LZ_REORTH_FULL_DGKS), LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: DGKS reorthogonalisation is single-GPU only");
     const int64_t ld = round_up(n, 4);
-    // three rotating work vectors (the reference's q0, q1, w: test_lanczos.cu:57-59)
+    // three rotating work vectors (the reference's q0, q1, w: test_lanczos.cu:57-59), each laid out
+    // [pad | lower halo | local rows | upper halo] with the local part 32-byte aligned
+    const int64_t off = round_up(hlo, 4);
+    const int64_t stride = round_up(off + n + hhi, 4);
     LzCgs g = {nullptr, ld, nullptr, nullptr, 0};
     const unsigned cgs_grid = stream_grid(ctx, n, CGS_TILE) < (unsigned)(ctx->sm_count * 2)
                                   ? stream_grid(ctx, n, CGS_TILE) : (unsigned)(ctx->sm_count * 2);
-    size_t work_bytes = sizeof(double) * (size_t)ld * 3;
+    size_t work_bytes = sizeof(double) * (size_t)stride * 3;
     if (reorth) work_bytes += sizeof(double) * ((size_t)cgs_grid * m + m + 8);
     void *work;
     LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
-    double *u_prev = (double *)work, *u_cur = u_prev + ld, *w = u_cur + ld;
+    double *u_prev = (double *)work + off, *u_cur = u_prev + stride, *w = u_cur + stride;
     if (reorth) {
         LZ_CHECK(sizeof(double) * (VT / 32) * (size_t)m <= 200 * 1024, LZ_ERR_UNSUPPORTED,
                  "lz_vector_lanczos: m = %d too large for the projection kernel's shared memory", m);
-        g.cpart = w + ld;
+        g.cpart = (double *)work + 3 * stride;
         g.c = g.cpart + (size_t)cgs_grid * m;
         g.grid = cgs_grid;
         LZ_TRY(lz_ctx_basis(ctx, ld, m, &g.V));
@@ -350,35 +369,48 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
             attr_set = true;
         }
     }
+    double *sc = ctx->scalars;
     LZ_CUDA(cudaMemcpyAsync(u_cur, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     // beta[0] = ||b||  (vector_lanczos.hpp:21)
-    LZ_TRY(dot_async(ctx, n, b, b, ctx->scalars + S_NRM2));
-    k_finalize_first<<<1, 1, 0, ctx->stream>>>(ctx->scalars + S_NRM2, beta, invb, ctx->flags);
+    LZ_TRY(dot_async(ctx, n, b, b, sc + S_NRM2));
+    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_NRM2, 1));
+    k_finalize_first<<<1, 1, 0, ctx->stream>>>(sc + S_NRM2, beta, invb, ctx->flags);
     LZ_LAUNCH_CHECK(ctx);
 
     for (int j = 0; j < m; ++j) {
+        if (sharded) LZ_TRY(lz_comm_halo_exchange(ctx, u_cur, n, hlo, hhi));     // neighbours' boundary planes of q_j
         LzPassA pa;
         pa.x_own = u_cur; pa.u_prev = u_prev; pa.invb = invb; pa.beta = beta;
-        pa.alpha_out = alpha + j; pa.alpha_partial = ctx->scalars + S_ALPHA_LOCAL;
+        pa.alpha_out = sharded ? nullptr : alpha + j; pa.alpha_partial = sc + S_ALPHA_LOCAL;
         pa.vcol = reorth ? g.V + (size_t)j * ld : nullptr;
-        pa.qout = q ? q + j : nullptr;
+        pa.qout = (q && lc >= 0) ? q + j : nullptr;
         pa.lc = lc; pa.j = j; pa.first = (j == 0);
         pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
         lz_prof_begin(ctx, LZ_K_SPMV, 12.0 * (double)A->nnz + 28.0 * (double)n + (reorth ? 8.0 * (double)n : 0.0));
-        LZ_TRY(lz_launch_spmv<LZ_EPI_LANCZOS>(ctx, A, u_cur, w, pa));          // :51,:54,:57
+        LZ_TRY(lz_launch_spmv<LZ_EPI_LANCZOS>(ctx, A, u_cur - hlo, w, pa));    // :51,:54,:57
         lz_prof_end(ctx);
-        LzFinal fin = {beta, invb, ctx->scalars + (reorth ? S_NRM2_BEFORE : S_NRM2), ctx->flags, j + 1, 1};
+        if (sharded) {
+            LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_ALPHA_LOCAL, 1));
+            k_copy_scalar<<<1, 1, 0, ctx->stream>>>(sc + S_ALPHA_LOCAL, alpha + j);
+            LZ_LAUNCH_CHECK(ctx);
+        }
+        LzFinal fin = {beta, invb, sc + (reorth ? S_NRM2_BEFORE : S_NRM2), ctx->flags, j + 1, sharded ? 0 : 1};
         lz_prof_begin(ctx, LZ_K_PASSB, 24.0 * (double)n);
         LZ_TRY(launch_pass_b(ctx, n, w, u_cur, alpha, invb, j, fin));          // :60,:44
         lz_prof_end(ctx);
         if (reorth) {
-            LzFinal f2 = {beta, invb, ctx->scalars + S_NRM2, ctx->flags, j + 1, 1};
-            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, reorth == LZ_REORTH_FULL_DGKS));
-            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, reorth == LZ_REORTH_FULL_DGKS, 0));
+            LzFinal f2 = {beta, invb, sc + S_NRM2, ctx->flags, j + 1, sharded ? 0 : 1};
+            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, reorth == LZ_REORTH_FULL_DGKS, sharded));
+            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, reorth == LZ_REORTH_FULL_DGKS, 0, sharded));
+        }
+        if (sharded) {
+            LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_NRM2, 1));
+            k_finalize_beta<<<1, 1, 0, ctx->stream>>>(sc + S_NRM2, beta, invb, ctx->flags, j + 1);
+            LZ_LAUNCH_CHECK(ctx);
         }
         double *t = u_prev; u_prev = u_cur; u_cur = w; w = t;                  // :62 (pointer rotation, no copy)
     }
-    k_copy_scalar<<<1, 1, 0, ctx->stream>>>(beta + m, ctx->scalars + S_BETA_LAST);
+    k_copy_scalar<<<1, 1, 0, ctx->stream>>>(beta + m, sc + S_BETA_LAST);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
@@ -427,7 +459,7 @@ int lz_vector_lanczos_async(lz_ctx *ctx, const lz_matrix *A, const double *b, in
                             double *alpha_dev, double *beta_dev, double *q)
 {
     LZ_CHECK(ctx && A && b && alpha_dev && beta_dev && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos_async: bad arguments");
-    LZ_CHECK(2 * m + 2 + 16 <= LZ_SCALARS, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
+    LZ_CHECK(2 * m + 2 + 16 <= 4096, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
     LZ_CUDA(cudaSetDevice(ctx->device));
     // beta needs m+1 slots and invb m+1 slots: keep them in the context's scalar bank
     double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1);
@@ -440,7 +472,7 @@ int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, i
                       double *alpha_host, double *beta_host, double *q, int *steps_done)
 {
     LZ_CHECK(ctx && A && b && alpha_host && beta_host && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos: bad arguments");
-    LZ_CHECK(3 * m + 3 + 16 <= LZ_SCALARS, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
+    LZ_CHECK(3 * m + 3 + 16 <= 4096, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
     LZ_CUDA(cudaSetDevice(ctx->device));
     double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1), *alpha_i = invb + (m + 1);
     LZ_TRY(vector_lanczos_core(ctx, A, b, m, lc, reorth, alpha_i, beta_i, invb, q));
@@ -456,6 +488,19 @@ int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, i
         lz_set_error("lz_vector_lanczos: breakdown, beta[%d] is zero or not finite", done);
         return LZ_ERR_BREAKDOWN;
     }
+    return LZ_OK;
+}
+
+int lz_vector_lanczos_sharded(lz_ctx *ctx, const lz_matrix *A_local, const double *b_local, int m, int reorth,
+                              double *alpha_dev, double *beta_dev)
+{
+    LZ_CHECK(ctx && A_local && b_local && alpha_dev && beta_dev && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos_sharded: bad arguments");
+    LZ_CHECK(ctx->comm, LZ_ERR_COMM, "lz_vector_lanczos_sharded: call lz_comm_init first");
+    LZ_CHECK(2 * m + 2 + 16 <= 4096, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos_sharded: m = %d exceeds the scalar bank", m);
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1);
+    LZ_TRY(vector_lanczos_core(ctx, A_local, b_local, m, -1, reorth, alpha_dev, beta_i, invb, nullptr));
+    LZ_CUDA(cudaMemcpyAsync(beta_dev, beta_i, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
     return LZ_OK;
 }
 

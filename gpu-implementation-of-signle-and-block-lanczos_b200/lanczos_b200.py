@@ -78,7 +78,7 @@ def lib():
         "lz_comm_unique_id": (i32, [vp]),
         "lz_comm_init": (i32, [vp, i32, i32, vp]),
         "lz_comm_destroy": (i32, [vp]),
-        "lz_partition_rows": (i32, [i64, i32, i32, P(i64), P(i64)]),
+        "lz_partition_rows": (i32, [i64, i64, i32, i32, P(i64), P(i64)]),
         "lz_gen_laplacian3d_shard": (i32, [vp, i64, i64, i64, i32, i32, P(vp)]),
         "lz_gen_laplacian2d_shard": (i32, [vp, i64, i64, i32, i32, P(vp)]),
         "lz_vector_lanczos_sharded": (i32, [vp, vp, vp, i32, i32, vp, vp]),

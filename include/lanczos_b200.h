@@ -182,10 +182,12 @@ int lz_ritz(int m, int bw, const double *alpha_host, const double *beta_host,
 int lz_comm_unique_id(void *id128_host);
 int lz_comm_init(lz_ctx *ctx, int world_size, int rank, const void *id128_host);
 int lz_comm_destroy(lz_ctx *ctx);
-/* contiguous row-block partition: rows [begin,end) of rank r out of world_size (host logic) */
-int lz_partition_rows(int64_t n_rows, int world_size, int rank, int64_t *begin, int64_t *end);
-/* local slab of the 7-/5-point Laplacian: rows [begin,end) with columns remapped to
- * [local | lower halo | upper halo]; halo = one xy-plane (3-D) / one x-line (2-D) per side */
+/* contiguous row-block partition (host logic): rows are dealt in whole granules (a grid plane /
+ * line for the stencil operators, 1 for anything else); rank r owns rows [begin,end) */
+int lz_partition_rows(int64_t n_rows, int64_t granule, int world_size, int rank, int64_t *begin, int64_t *end);
+/* local slab of the 7-/5-point Laplacian: rows [begin,end) = lz_partition_rows(n, plane, ...) with
+ * column ids shifted to the index space [lower halo | local | upper halo]; halo = one xy-plane
+ * (3-D) / one x-line (2-D) per existing neighbour */
 int lz_gen_laplacian3d_shard(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int world_size,
                              int rank, lz_matrix **out);
 int lz_gen_laplacian2d_shard(lz_ctx *ctx, int64_t nx, int64_t ny, int world_size, int rank,

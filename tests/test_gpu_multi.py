@@ -1,0 +1,69 @@
+"""GPU suite, N > 1: the sharded single-vector driver (row slabs, NCCL halo exchange + all-reduce)
+against the single-GPU driver and the oracle.  Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+WORKER = r'''
+import os, sys, ctypes as C
+import numpy as np, torch, torch.distributed as dist
+ROOT = sys.argv[1]
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gpu-implementation-of-signle-and-block-lanczos_b200"))
+import lanczos_b200 as lz
+from oracle import orc
+lr = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(lr); torch.zeros(1, device="cuda")
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+rank, world = dist.get_rank(), dist.get_world_size()
+ctx = lz.Context(lr)
+ident = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    buf = (C.c_ubyte * 128)(); lz.check(lz.lib().lz_comm_unique_id(buf)); ident = torch.tensor(list(buf), dtype=torch.uint8)
+ident = ident.cuda(); dist.broadcast(ident, 0)
+lz.check(lz.lib().lz_comm_init(ctx.h, world, rank, bytes(ident.cpu().tolist())))
+orc.set_threads(4)
+for kind, dims, m in (("lap3d", (24, 20, 16), 40), ("lap2d", (64, 48), 40)):
+    n = int(np.prod(dims))
+    if kind == "lap3d":
+        A = lz.Matrix.laplacian3d_shard(ctx, *dims, world, rank); csr = orc.lap3d(*dims); gran = dims[0] * dims[1]
+    else:
+        A = lz.Matrix.laplacian2d_shard(ctx, *dims, world, rank); csr = orc.lap2d(*dims); gran = dims[0]
+    lo, hi = C.c_int64(), C.c_int64()
+    lz.check(lz.lib().lz_partition_rows(n, gran, world, rank, C.byref(lo), C.byref(hi)))
+    bfull = orc.start_vector(n)
+    b = torch.from_numpy(bfull[lo.value:hi.value].copy()).cuda()
+    for reorth in (0, 1):
+        al = torch.zeros(m, dtype=torch.float64, device="cuda"); be = torch.zeros(m, dtype=torch.float64, device="cuda")
+        lz.check(lz.lib().lz_vector_lanczos_sharded(ctx.h, A.h, b.data_ptr(), m, reorth, al.data_ptr(), be.data_ptr()))
+        ctx.sync()
+        ref = orc.vector_lanczos(csr, bfull, m, reorth=reorth)
+        a, bb = al.cpu().numpy(), be.cpu().numpy()
+        scale = np.maximum(np.abs(ref["alpha"]), np.mean(ref["beta"][1:]))
+        ea = np.max(np.abs(a - ref["alpha"]) / scale); eb = np.max(np.abs(bb - ref["beta"]) / ref["beta"])
+        assert ea < 1e-10 and eb < 1e-10, (kind, reorth, ea, eb)
+        # every rank holds the same coefficients bit for bit
+        t = al.clone(); dist.broadcast(t, 0); assert torch.equal(t, al)
+print("rank %d ok" % rank)
+ctx.close()
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_vector_lanczos_matches_oracle(tmp_path):
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29641", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("ok") == world
