@@ -261,7 +261,16 @@ def run_gpu(args, wl, rank, world):
         e2e = {"value": m / dt, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * m),
                "ms_per_step": dt * 1e3}
 
+    def teardown():
+        # identical order on every rank: library communicator first, then torch's
+        A.close()
+        ctx.close()
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+
     if rank != 0:
+        teardown()
         return
     # ---- roofline of the dominant kernel (live CUDA-event times from the timed region) -------
     dom = max(prof, key=lambda k: prof[k][1])
@@ -292,9 +301,8 @@ def run_gpu(args, wl, rank, world):
         line["cpu_baseline"] = {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port",
                                 "sample": "first %d of %d iterations of the same solve, oracle/lanczos_oracle.c with OpenMP (%.1f s)"
                                           % (min(CPU_SAMPLE_ITERS, m), m, dt)}
-    print(json.dumps(line))
-    if dist:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    teardown()
 
 
 def main():

@@ -1,0 +1,85 @@
+// utils/common.hpp -- shared macros and helpers of the C++ mirror.
+//
+// Mirrors the reference's utils/common.hpp (CEIL_DIV, WARP_SIZE, AssertCuda abort policy :105-112,
+// CUBLAS_CHECK/CUSOLVER_CHECK throw policy :83-103, steady_clock wrapper :46-66, print helper).
+// Host code is plain C++ (g++): every device operation goes through the C-ABI of
+// liblanczos_b200.so (include/lanczos_b200.h); there is no CUDA in these headers.
+#ifndef lzb_common_hpp
+#define lzb_common_hpp
+
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <iomanip>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "lanczos_b200.h"
+
+#define CEIL_DIV(M, N) (((M) + (N)-1) / (N))
+#define WARP_SIZE 32
+
+// Same policy as the reference's AssertCuda: report file/line and abort (common.hpp:105-112).
+#define AssertCuda(status_expr)                                                                      \
+    do {                                                                                             \
+        const int lz_status__ = (status_expr);                                                       \
+        if (lz_status__ != LZ_OK) {                                                                  \
+            std::cerr << "lanczos_b200 error " << lz_status__ << " at " << __FILE__ << ":" << __LINE__ \
+                      << ": " << lz_last_error() << std::endl;                                       \
+            std::abort();                                                                            \
+        }                                                                                            \
+    } while (0)
+
+// Same policy as CUBLAS_CHECK / CUSOLVER_CHECK: report and throw std::runtime_error (common.hpp:83-103).
+#define LZ_THROW_CHECK(status_expr)                                                                  \
+    do {                                                                                             \
+        const int lz_status__ = (status_expr);                                                       \
+        if (lz_status__ != LZ_OK) {                                                                  \
+            std::cerr << "lanczos_b200 error " << lz_status__ << " at " << __FILE__ << ":" << __LINE__ \
+                      << ": " << lz_last_error() << std::endl;                                       \
+            throw std::runtime_error(lz_last_error());                                               \
+        }                                                                                            \
+    } while (0)
+#define CUBLAS_CHECK(expr) LZ_THROW_CHECK(expr)
+#define CUSOLVER_CHECK(expr) LZ_THROW_CHECK(expr)
+
+// The reference runs on one device and the default stream; the mirror keeps one
+// process-wide context for device LZB_DEVICE (default 0), created on first use.
+inline lz_ctx *lanczos_context()
+{
+    static lz_ctx *ctx = nullptr;
+    if (!ctx) {
+        const char *dev = std::getenv("LZB_DEVICE");
+        AssertCuda(lz_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &ctx));
+    }
+    return ctx;
+}
+inline void cudaDeviceSynchronize_() { AssertCuda(lz_ctx_sync(lanczos_context())); }
+
+// wall-clock timer in the shape of the reference's steady_clock wrapper (common.hpp:46-66)
+class steady_clock {
+    std::chrono::time_point<std::chrono::steady_clock> t0_, t1_;
+
+public:
+    void start() { t0_ = std::chrono::steady_clock::now(); }
+    void end() { t1_ = std::chrono::steady_clock::now(); }
+    double duration() const { return std::chrono::duration<double>(t1_ - t0_).count(); }
+};
+
+template <typename T>
+void print(const T &v)
+{
+    std::cout << v << std::endl;
+}
+
+inline void CudaDeviceInfo()
+{
+    std::cout << "lanczos_b200 " << lz_version() << " on device " << lz_ctx_device(lanczos_context()) << std::endl;
+}
+
+#endif

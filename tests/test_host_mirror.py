@@ -1,0 +1,81 @@
+"""The C++ mirror of the reference surface (host/): the problem generator against the goldens minted
+by the reference's own builder (CPU, bit-exact), and the harness test_lanczos driving the library
+through the reference's driver signatures (GPU)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_gold
+
+HOST = os.path.join(ROOT, "gpu-implementation-of-signle-and-block-lanczos_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def host_built():
+    subprocess.run(["make", "-s", "-C", HOST, "all"], check=True)
+    return HOST
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 10])
+def test_matrix_a_bit_identical_to_reference_builder(host_built, orc, tmp_path, N):
+    out = str(tmp_path / "ma.bin")
+    subprocess.run([os.path.join(host_built, "dump_matrix_a"), str(N), out], check=True)
+    d, g = orc.read_dump(out), load_gold("maxwell_N%d_matrix.npz" % N)
+    assert d["n_rows"] == int(g["n_rows"]) == 3 * N * (N + 1) * (2 * N + 1)
+    assert d["width"] == 4
+    for key in ("D_data", "D_idx", "W_data", "W_idx", "ell_data", "ell_idx"):
+        assert np.array_equal(d[key], g[key]), key
+    if N == 10:
+        gv = load_gold("maxwell_N10_vector_m100.npz")
+        assert d["lc"] == int(gv["lc"]) and np.array_equal(d["b"], gv["b"])    # glibc rand() stream, harness order
+
+
+def run_harness(host, args, tmp_path, exe="test_lanczos"):
+    out = str(tmp_path / "run.bin")
+    r = subprocess.run([os.path.join(host, exe)] + args + ["--dump", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["ell", "csr"])
+def test_harness_vector_matches_golden(host_built, orc, tmp_path, fmt):
+    stdout, out = run_harness(host_built, ["-N", "10", "-m", "100", "--vector", "--format", fmt, "--k", "6"], tmp_path)
+    d, g = orc.read_dump(out), load_gold("maxwell_N10_vector_m100.npz")
+    assert np.array_equal(d["b"], g["b"]) and d["lc"] == int(g["lc"])
+    scale = np.maximum(np.abs(g["alpha"][:50]), np.mean(np.abs(g["beta"][1:50])))
+    assert np.max(np.abs(d["alpha"][:50] - g["alpha"][:50]) / scale) < 1e-10
+    assert np.max(np.abs(d["beta"][:50] - g["beta"][:50]) / np.abs(g["beta"][:50])) < 1e-10
+    assert np.max(np.abs(d["q"][:50] - g["q"][:50])) < 1e-10 * np.abs(g["q"]).max()
+    # Ritz values printed by the harness = eig(T) of the golden coefficients, to 1e-8 (north_star)
+    w = np.linalg.eigvalsh(orc.assemble_T(g["alpha"], g["beta"]))
+    assert np.max(np.abs(d["theta"] - np.r_[w[:3], w[-3:]])) < 1e-8 * np.abs(w).max()
+    assert "elapsed time" in stdout and "iterations/s" in stdout
+
+
+@pytest.mark.gpu
+def test_harness_block_matches_golden(host_built, orc, tmp_path):
+    stdout, out = run_harness(host_built, ["-N", "10", "-m", "25", "--block", "4"], tmp_path)
+    d, g = orc.read_dump(out), load_gold("maxwell_N10_block4_m25.npz")
+    assert np.array_equal(d["B"], g["B"])
+    nb = 10 * 16
+    assert np.max(np.abs(d["alpha"][:nb] - g["alpha"][:nb])) < 1e-10 * np.abs(g["alpha"]).max()
+    assert np.max(np.abs(d["beta"][:nb] - g["beta"][:nb])) < 1e-10 * np.abs(g["beta"][:nb]).max()
+    m, bw = 25, 4
+    T = d["T"].reshape(m * bw, m * bw).T
+    a = d["alpha"].reshape(m, bw, bw).transpose(0, 2, 1)
+    b = d["beta"].reshape(m + 1, bw, bw).transpose(0, 2, 1)
+    assert np.array_equal(T, orc.assemble_T(a, b))                 # Assemble_T through the mirror == oracle layout
+    w = np.linalg.eigvalsh(T)
+    assert np.max(np.abs(d["theta"] - np.r_[w[:2], w[-2:]])) < 1e-8 * np.abs(w).max()
+
+
+@pytest.mark.gpu
+def test_harness_laplacian_full_reorth(host_built, orc, tmp_path):
+    stdout, out = run_harness(host_built, ["--matrix", "lap2d", "-N", "200", "-m", "80", "--vector", "--reorth", "full"], tmp_path)
+    d = orc.read_dump(out)
+    ref = orc.vector_lanczos(orc.lap2d(200, 200), orc.start_vector(200 * 200), 80, reorth=1)
+    assert np.max(np.abs(d["alpha"][:50] - ref["alpha"][:50])) < 1e-10 * np.abs(ref["alpha"]).max()
+    assert np.max(np.abs(d["beta"][:50] - ref["beta"][:50]) / ref["beta"][:50]) < 1e-10
