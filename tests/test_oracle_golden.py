@@ -118,3 +118,19 @@ def test_ritz_oracle_on_laplacian(orc):
     lam = np.sort([4 - 2 * np.cos(i * np.pi / (nx + 1)) - 2 * np.cos(j * np.pi / (ny + 1))
                    for i in range(1, nx + 1) for j in range(1, ny + 1)])
     assert abs(theta[0] - lam[0]) < 1e-8 and abs(theta[-1] - lam[-1]) < 1e-8
+
+
+def test_oracle_matches_reference_cuda_run(orc, maxwell10):
+    """tests/golden/ref_cuda_*.npz: the reference's own CUDA drivers (sm_100 build, run on a B200 by
+    tools/run_ref_cuda.sh; cuBLAS reductions, cuSOLVER syevj square roots).  The oracle and the
+    Host-minted goldens agree with them to the north_star tolerance over the first 50 steps."""
+    r, g = load_gold("ref_cuda_vector_N10.npz"), load_gold("maxwell_N10_vector_m100.npz")
+    o = orc.vector_lanczos(maxwell10["csr"], g["b"], 100, lc=int(r["lc"]))
+    scale = np.maximum(np.abs(o["alpha"][:50]), np.mean(o["beta"][1:50]))
+    assert np.max(np.abs(r["alpha"][:50] - o["alpha"][:50]) / scale) < 1e-10
+    assert np.max(np.abs(r["beta"][:50] - o["beta"][:50]) / o["beta"][:50]) < 1e-10
+    for nc in (4, 8):
+        r, g = load_gold("ref_cuda_block%d_N10.npz" % nc), load_gold("maxwell_N10_block%d_m25.npz" % nc)
+        nb = 10 * nc * nc
+        assert np.max(np.abs(r["alpha"][:nb] - g["alpha"][:nb])) < 1e-10 * np.abs(g["alpha"]).max()
+        assert np.max(np.abs(r["beta"][:nb] - g["beta"][:nb])) < 1e-10 * np.abs(g["beta"][:nb]).max()
