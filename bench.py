@@ -234,7 +234,7 @@ def run_gpu(args, wl, rank, world):
 
     # ---- end-to-end through the C-ABI from pinned host buffers (single GPU path) --------------
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         rp, ci, va = A.csr_to_host()
         pin = lambda a: torch.from_numpy(a).pin_memory()
         rp_h, ci_h, va_h, b_h = pin(rp), pin(ci), pin(va), b.cpu().pin_memory()
@@ -273,7 +273,7 @@ def run_gpu(args, wl, rank, world):
         teardown()
         return
     # ---- roofline of the dominant kernel (live CUDA-event times from the timed region) -------
-    dom = max(prof, key=lambda k: prof[k][1])
+    dom = max((k for k in prof if k != "comm"), key=lambda k: prof[k][1])
     la, kms, kby = prof[dom]
     achieved = kby / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     traffic = None
@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

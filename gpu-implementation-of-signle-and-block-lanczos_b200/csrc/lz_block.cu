@@ -12,6 +12,8 @@
 #include "lz_dense_host.cuh"
 
 #define SPMM_THREADS 256
+#define SPMM_U 2            // independent rows per lane group in flight
+#define SPMM_SLAB 512     // rows per CTA slab of the row-major SpMM
 
 // ---------------------------------------------------------------------------------------------
 // Row-major SpMM, CSR:  W[i,:] = sum_k A[i,k] X[col_k,:]   (- Q0[i,:] B  when FUSE_SUB)
@@ -28,49 +30,125 @@ k_spmm_rm(int64_t n_rows, const int32_t *__restrict__ rowptr, const int32_t *__r
 {
     constexpr int LW = BW / 2;                       // lanes per row
     constexpr int RPW = 32 / LW;                     // rows per warp at a time
-    constexpr int BWP = BW + 1;                      // padded column stride: conflict-free across the group's lanes
-    __shared__ double bs[FUSE_SUB ? BW * BWP : 1];
+    constexpr int WARPS = SPMM_THREADS / 32;
+    // B of the fused subtraction, packed so that one conflict-free 128-bit shared load per lane
+    // brings the two rows (2p, 2p+1) of one of the lane's two columns: blo[p][l] = B[2p..2p+1, 2l],
+    // bhi[p][l] = B[2p..2p+1, 2l+1]
+    __shared__ double2 blo[FUSE_SUB ? LW * LW : 1], bhi[FUSE_SUB ? LW * LW : 1];
     if (FUSE_SUB) {
-        for (int e = threadIdx.x; e < BW * BW; e += SPMM_THREADS) bs[(e % BW) + (e / BW) * BWP] = Bm[e];
+        for (int e = threadIdx.x; e < LW * LW; e += SPMM_THREADS) {
+            const int p = e / LW, l = e % LW;
+            blo[e] = make_double2(Bm[(2 * p) + (2 * l) * BW], Bm[(2 * p + 1) + (2 * l) * BW]);
+            bhi[e] = make_double2(Bm[(2 * p) + (2 * l + 1) * BW], Bm[(2 * p + 1) + (2 * l + 1) * BW]);
+        }
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31, sub = lane / LW, l = lane % LW;
-    const int64_t warp = (int64_t)blockIdx.x * (SPMM_THREADS / 32) + (threadIdx.x >> 5);
-    const int64_t n_warps = (int64_t)gridDim.x * (SPMM_THREADS / 32);
-    for (int64_t r0 = warp * RPW; r0 < n_rows; r0 += n_warps * RPW) {
-        const int64_t r = r0 + sub;
-        const bool valid = r < n_rows;               // no early exit: the group shuffles below need every lane
-        const int s = valid ? rowptr[r] : 0, e = valid ? rowptr[r + 1] : 0;
-        double a0 = 0.0, a1 = 0.0;
-        int k = s;
-        for (; k + 4 <= e; k += 4) {                 // four gathers in flight per lane
-            int c[4]; double v[4]; double2 x[4];
+    const int lane = threadIdx.x & 31, sub = lane / LW, l = lane % LW, warp = threadIdx.x >> 5;
+    // A CTA owns contiguous slabs of SPMM_SLAB rows (slab index strided by the grid) and sweeps each
+    // slab front to back with all its warps, so the rows gathered for neighbouring matrix rows --
+    // the +-1 and +-nx neighbours of a stencil -- are still in this SM's L1 when they are needed
+    // again, and concurrently running CTAs stay within a narrow window of X (L2 reuse of +-nx*ny).
+    // Every warp keeps U independent rows per lane group in flight and fetches the row extents of
+    // its next trip while it works on the current one: the rowptr -> (col,val) -> X[col] chain is
+    // three dependent global loads, and this kernel lives or dies by how many of them overlap.
+    constexpr int U = SPMM_U;
+    constexpr int TRIPS = SPMM_SLAB / (WARPS * RPW * U);
+    const int64_t n_slabs = (n_rows + SPMM_SLAB - 1) / SPMM_SLAB;
+    auto row_of = [&](int64_t slab, int t, int u) -> int64_t {
+        return slab * SPMM_SLAB + (int64_t)((t * U + u) * WARPS + warp) * RPW + sub;
+    };
+    int ns[U], ne[U];
+    {
+        const int64_t slab = blockIdx.x;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { c[u] = colidx[k + u]; v[u] = vals[k + u]; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = __ldg(reinterpret_cast<const double2 *>(X + (int64_t)c[u] * BW) + l);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { a0 = fma(v[u], x[u].x, a0); a1 = fma(v[u], x[u].y, a1); }
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = row_of(slab, 0, u);
+            ns[u] = (slab < n_slabs && r < n_rows) ? rowptr[r] : 0;
+            ne[u] = (slab < n_slabs && r < n_rows) ? rowptr[r + 1] : 0;
         }
-        for (; k < e; ++k) {
-            const double v = vals[k];
-            const double2 x = __ldg(reinterpret_cast<const double2 *>(X + (int64_t)colidx[k] * BW) + l);
-            a0 = fma(v, x.x, a0); a1 = fma(v, x.y, a1);
-        }
-        if (FUSE_SUB) {
-            // W[i, 2l..2l+1] -= sum_p Q0[i,p] B[p, 2l..2l+1]; Q0 row broadcast through the group's lanes
-            const double2 q = valid ? __ldg(reinterpret_cast<const double2 *>(Q0 + r * BW) + l) : make_double2(0.0, 0.0);
+    }
+    for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        for (int t = 0; t < TRIPS; ++t) {
+            int64_t r[U]; int s[U], e[U]; bool valid[U];
 #pragma unroll
-            for (int p = 0; p < LW; ++p) {
-                const double q0 = __shfl_sync(0xffffffffu, q.x, sub * LW + p);
-                const double q1 = __shfl_sync(0xffffffffu, q.y, sub * LW + p);
-                a0 = fma(-q0, bs[(2 * p) + (2 * l) * BWP], a0);
-                a1 = fma(-q0, bs[(2 * p) + (2 * l + 1) * BWP], a1);
-                a0 = fma(-q1, bs[(2 * p + 1) + (2 * l) * BWP], a0);
-                a1 = fma(-q1, bs[(2 * p + 1) + (2 * l + 1) * BWP], a1);
+            for (int u = 0; u < U; ++u) { r[u] = row_of(slab, t, u); valid[u] = r[u] < n_rows; s[u] = ns[u]; e[u] = ne[u]; }
+            {   // extents of the next trip (possibly in the next slab of this CTA)
+                const int64_t nslab = (t + 1 < TRIPS) ? slab : slab + gridDim.x;
+                const int nt = (t + 1 < TRIPS) ? t + 1 : 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t rn = row_of(nslab, nt, u);
+                    const bool ok = nslab < n_slabs && rn < n_rows;
+                    ns[u] = ok ? rowptr[rn] : 0;
+                    ne[u] = ok ? rowptr[rn + 1] : 0;
+                }
             }
+            double2 q[U];
+            if (FUSE_SUB) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    q[u] = valid[u] ? __ldcs(reinterpret_cast<const double2 *>(Q0 + r[u] * BW) + l) : make_double2(0.0, 0.0);
+            }
+            // uniform trip count across the warp: the group shuffles below need every lane
+            int maxlen = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) maxlen = max(maxlen, e[u] - s[u]);
+#pragma unroll
+            for (int o = LW; o < 32; o <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+            double a0[U], a1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) a0[u] = a1[u] = 0.0;
+            for (int k0 = 0; k0 < maxlen; k0 += LW) {
+                // the group's lanes fetch LW consecutive (col, val) pairs of each row in one coalesced
+                // load, then hand them round with shuffles; streaming loads: read exactly once
+                int my_c[U]; double my_v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int k = s[u] + k0 + l;
+                    my_c[u] = (k < e[u]) ? __ldcs(colidx + k) : -1;
+                    my_v[u] = (k < e[u]) ? __ldcs(vals + k) : 0.0;
+                }
+                constexpr int G = LW < 4 ? LW : 4;   // U*G gathers in flight per lane
+#pragma unroll
+                for (int u0 = 0; u0 < LW; u0 += G) {
+                    int c[U][G]; double v[U][G]; double2 x[U][G];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            c[u][g] = __shfl_sync(0xffffffffu, my_c[u], sub * LW + u0 + g);
+                            v[u][g] = __shfl_sync(0xffffffffu, my_v[u], sub * LW + u0 + g);
+                        }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            x[u][g] = c[u][g] >= 0 ? __ldg(reinterpret_cast<const double2 *>(X + (int64_t)c[u][g] * BW) + l)
+                                                   : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int g = 0; g < G; ++g) { a0[u] = fma(v[u][g], x[u][g].x, a0[u]); a1[u] = fma(v[u][g], x[u][g].y, a1[u]); }
+                }
+            }
+            if (FUSE_SUB) {
+                // W[i, 2l..2l+1] -= sum_p Q0[i,p] B[p, 2l..2l+1]; Q0 row handed round the group's lanes
+#pragma unroll
+                for (int p = 0; p < LW; ++p) {
+                    const double2 b0 = blo[p * LW + l], b1 = bhi[p * LW + l];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const double q0 = __shfl_sync(0xffffffffu, q[u].x, sub * LW + p);
+                        const double q1 = __shfl_sync(0xffffffffu, q[u].y, sub * LW + p);
+                        a0[u] = fma(-q0, b0.x, a0[u]); a0[u] = fma(-q1, b0.y, a0[u]);
+                        a1[u] = fma(-q0, b1.x, a1[u]); a1[u] = fma(-q1, b1.y, a1[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (valid[u]) __stcs(reinterpret_cast<double2 *>(W + r[u] * BW) + l, make_double2(a0[u], a1[u]));
         }
-        if (valid) *(reinterpret_cast<double2 *>(W + r * BW) + l) = make_double2(a0, a1);
     }
 }
 
@@ -192,8 +270,8 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
         else { lz_set_error("block width %d is not supported on an ELL4 operator (use 1,2,4,8,16,32)", bw); return LZ_ERR_UNSUPPORTED; }
 #undef ELL_CASE
     } else {
-        int64_t want = (n + 63) / 64;
-        int64_t cap = (int64_t)ctx->sm_count * 16;
+        int64_t want = (n + SPMM_SLAB - 1) / SPMM_SLAB;
+        int64_t cap = (int64_t)ctx->sm_count * 8;
         const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
 #define CSR_CASE(B)                                                                                                     \
     if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, A->rowptr, A->colidx, A->vals, X, W, Q0, Bm); \

@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(1024) k_sqrtm(int b, double *__restrict__ S, d
     }
     __syncthreads();
     const int m = (b + 1) & ~1;                   // players in the round-robin tournament (pad odd b)
-    for (int sweep = 0; sweep < 30 && b > 1; ++sweep) {
-        // convergence test: off-diagonal mass negligible against the diagonal
+    bool last = false;                            // Jacobi converges quadratically: one sweep after off/diag < 1e-9 is at rounding level
+    for (int sweep = 0; sweep < 30 && b > 1 && !last; ++sweep) {
         if (tid == 0) { off2 = 0.0; dia2 = 0.0; }
         __syncthreads();
         {
@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(1024) k_sqrtm(int b, double *__restrict__ S, d
             if ((tid & 31) == 0) { atomicAdd(&off2, o); atomicAdd(&dia2, d); }
         }
         __syncthreads();
-        if (off2 <= 1e-34 * dia2) break;
+        if (off2 <= 1e-30 * dia2) break;
+        last = off2 <= 1e-18 * dia2;
         for (int round = 0; round < m - 1; ++round) {
             // pairing of round `round`: player 0 fixed, the others rotate
             if (tid < m / 2) {

@@ -45,6 +45,23 @@ def main():
                 reads = (4 if mode == 1 else 2) * 8 * n * (m * (m + 1) / 2)
                 out[name + "_reorth%d_m100" % mode] = dict(ms_total=ms, it_per_s=m / ms * 1e3, basis_gbs=reads / ms / 1e6)
         A.close()
+    if "block" in which:
+        for bw in [int(x) for x in os.environ.get("LZ_BLOCK_WIDTHS", "8,16,32").split(",")]:
+            A = lz.Matrix.laplacian3d(ctx, 256, 256, 256); n, nnz = A.n_rows, A.nnz
+            m = 8
+            B = torch.empty(n * bw, dtype=torch.float64, device="cuda")
+            lz.check(lz.lib().lz_gen_start_block(ctx.h, n, bw, n, 0x5EED, B.data_ptr()))
+            al = torch.zeros(m * bw * bw, dtype=torch.float64, device="cuda"); be = torch.zeros((m + 1) * bw * bw, dtype=torch.float64, device="cuda")
+            q = torch.zeros(m * bw, dtype=torch.float64, device="cuda")
+            run = lambda: lz.block_lanczos(ctx, A, B, n, bw, m, al, be, q)
+            run(); ctx.sync()
+            ctx.profile(True)
+            ms = timeit(run, reps=2, warm=0)
+            prof = ctx.profile_read(); ctx.profile(False)
+            byt = 12 * nnz + 4 * n + 8 * 8 * n * bw      # matrix + 8 panel passes
+            out["lap3d_256_block%d" % bw] = dict(ms_per_iter=ms / m, it_per_s=m / ms * 1e3, gbs=byt / (ms / m) / 1e6, frac=byt / (ms / m) / 1e6 / PEAK,
+                                                 classes={k: dict(n=v[0], ms=round(v[1] / 2 / m, 4), gbs=round(v[2] / max(v[1], 1e-9) / 1e6, 1)) for k, v in prof.items() if v[0]})
+            A.close(); del B
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "devbench.json"), "w"), indent=1)
