@@ -38,6 +38,7 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
 {
     A->tile = ctx->spmv_tile > 0 ? ctx->spmv_tile : LZ_SPMV_TILE;
     A->cap = A->tile <= 1536 ? 2048 : 4096;
+    if (ctx->spmv_variant == 1 || ctx->spmv_variant == 5 || ctx->spmv_variant == 6) { A->tile = 1536; A->cap = 1792; }     // dev-time sweep knobs
     int64_t nch = (A->nnz + A->tile - 1) / A->tile;
     if (nch < 1) nch = 1;
     LZ_CHECK(nch * 2 <= LZ_PARTIALS_CAP, LZ_ERR_UNSUPPORTED, "matrix too large for the reduction scratch (%lld chunks)", (long long)nch);
@@ -195,6 +196,22 @@ __global__ void k_start_block(int64_t n, int b, int64_t ld, uint64_t seed, doubl
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int c = 0; c < b; ++c) V[i + (int64_t)c * ld] = 2.0 * lz_u01(lz_splitmix64(seed ^ (uint64_t)(i * b + c))) - 1.0;
+}
+
+// R-MAT (a,b,c,d) = (0.57,0.19,0.19,0.05): one counter-based draw per (edge, level)   [SURVEY 8d, config 4]
+__global__ void k_rmat_edges(int scale, int64_t n_edges, uint64_t seed, int32_t *__restrict__ src, int32_t *__restrict__ dst)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    uint32_t r = 0, c = 0;
+    for (int l = 0; l < scale; ++l) {
+        const double u = lz_u01(lz_splitmix64(seed ^ ((uint64_t)e * 64ULL + (uint64_t)l)));
+        const int q = (u < 0.57) ? 0 : (u < 0.76) ? 1 : (u < 0.95) ? 2 : 3;
+        r = (r << 1) | (uint32_t)(q >> 1);
+        c = (c << 1) | (uint32_t)(q & 1);
+    }
+    src[e] = (int32_t)r;
+    dst[e] = (int32_t)c;
 }
 
 __global__ void k_fill(int64_t n, double value, double *__restrict__ x)
@@ -417,6 +434,14 @@ int lz_gen_start_block(lz_ctx *ctx, int64_t n, int b, int64_t ld, uint64_t seed,
 {
     LZ_CHECK(ctx && V && n > 0 && b > 0 && ld >= n, LZ_ERR_INVALID, "lz_gen_start_block: bad arguments");
     k_start_block<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, b, ld, seed, V);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_gen_rmat_edges(lz_ctx *ctx, int scale, int64_t n_edges, uint64_t seed, int32_t *src, int32_t *dst)
+{
+    LZ_CHECK(ctx && src && dst && scale >= 1 && scale <= 30 && n_edges > 0, LZ_ERR_INVALID, "lz_gen_rmat_edges: bad arguments");
+    k_rmat_edges<<<(unsigned)((n_edges + 255) / 256), 256, 0, ctx->stream>>>(scale, n_edges, seed, src, dst);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }

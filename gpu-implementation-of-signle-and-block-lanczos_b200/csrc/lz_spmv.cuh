@@ -601,12 +601,16 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
         k_ell4_spmv<MODE><<<grid, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->n_rows, A->ell_data, A->ell_idx, x, y, args);
     } else if (A->tma_ok) {
         // A->cap is fixed when the schedule is built (lz_csr.cu); variant = dev-time tuning knob
+        // kernel shape per schedule (A->cap is fixed when the schedule is built, lz_csr.cu)
         const int v = ctx->spmv_variant;
         if (A->cap == 2048) {
-            if (v == 1) LZ_TRY((lz_launch_ws_variant<MODE, 6, 5, 3, 2048>(ctx, A, x, y, args, 3)));
-            else if (v == 2) LZ_TRY((lz_launch_ws_variant<MODE, 4, 3, 2, 2048>(ctx, A, x, y, args, 4)));
-            else if (v == 3) LZ_TRY((lz_launch_tma_variant<MODE, 384, 2, 2048>(ctx, A, x, y, args, 4)));
-            else LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 3)));      // default
+            if (v == 3) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 3)));
+            else if (v == 4) LZ_TRY((lz_launch_ws_variant<MODE, 5, 10, 3, 2048>(ctx, A, x, y, args, 3)));
+            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 3)));      // default (profiles/r01_spmv_variants.md)
+        } else if (A->cap == 1792) {
+            if (v == 5) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 4, 1792>(ctx, A, x, y, args, 2)));
+            else if (v == 6) LZ_TRY((lz_launch_ws_variant<MODE, 10, 9, 5, 1792>(ctx, A, x, y, args, 2)));
+            else LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 5, 1792>(ctx, A, x, y, args, 2)));
         } else {
             LZ_TRY((lz_launch_tma_variant<MODE, 1024, 2, 4096>(ctx, A, x, y, args, 2)));
         }

@@ -57,6 +57,7 @@ def lib():
         "lz_matrix_csr_view": (i32, [vp, P(vp), P(vp), P(vp)]),
         "lz_gen_laplacian2d": (i32, [vp, i64, i64, P(vp)]),
         "lz_gen_laplacian3d": (i32, [vp, i64, i64, i64, P(vp)]),
+        "lz_gen_rmat_edges": (i32, [vp, i32, i64, u64, vp, vp]),
         "lz_gen_start_vector": (i32, [vp, i64, u64, vp]),
         "lz_gen_start_block": (i32, [vp, i64, i32, i64, u64, vp]),
         "lz_spmv": (i32, [vp, vp, vp, vp]),
@@ -185,6 +186,36 @@ class Matrix:
         h = C.c_void_p()
         check(lib().lz_gen_laplacian3d(ctx.h, nx, ny, nz, C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def rmat_laplacian(cls, ctx, scale, edge_factor=16, seed=0x5EED):
+        """Symmetrised, de-duplicated, loop-free R-MAT graph Laplacian L = D - A (config 4), built on the
+        device: edges from lz_gen_rmat_edges, sort/unique/CSR with torch (input generation, not the hot path)."""
+        import torch
+        n, ne = 1 << scale, (1 << scale) * edge_factor
+        src = torch.empty(ne, dtype=torch.int32, device="cuda")
+        dst = torch.empty(ne, dtype=torch.int32, device="cuda")
+        check(lib().lz_gen_rmat_edges(ctx.h, scale, ne, seed, src.data_ptr(), dst.data_ptr()))
+        ctx.sync()
+        s, d = src.long(), dst.long()
+        del src, dst
+        keep = s != d
+        s, d = s[keep], d[keep]
+        key = torch.unique(torch.cat([s * n + d, d * n + s]))
+        del s, d, keep
+        diag = torch.arange(n, device="cuda", dtype=torch.long) * (n + 1)
+        key = torch.sort(torch.cat([key, diag]))[0]                 # columns ascending inside each row, diagonal included
+        rows = key // n
+        cols = (key - rows * n).to(torch.int32)
+        del key
+        counts = torch.bincount(rows, minlength=n)
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+        rowptr[1:] = torch.cumsum(counts, 0)
+        vals = torch.full((cols.numel(),), -1.0, dtype=torch.float64, device="cuda")
+        is_diag = cols.long() == rows
+        vals[is_diag] = (counts - 1).to(torch.float64)              # degree (the diagonal entry itself is not an edge)
+        del rows, is_diag, counts
+        return cls.from_csr(ctx, rowptr.to(torch.int32), cols, vals)
 
     @classmethod
     def laplacian3d_shard(cls, ctx, nx, ny, nz, world_size, rank):

@@ -102,6 +102,9 @@ int lz_matrix_csr_view(const lz_matrix *A, const int32_t **rowptr, const int32_t
 /* synthetic operators generated on the device (BASELINE.json configs 2-5) */
 int lz_gen_laplacian2d(lz_ctx *ctx, int64_t nx, int64_t ny, lz_matrix **out);
 int lz_gen_laplacian3d(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, lz_matrix **out);
+/* directed R-MAT edge list, (a,b,c,d) = (0.57,0.19,0.19,0.05), counter-based RNG (config 4); the caller
+ * symmetrises / de-duplicates / adds the Laplacian diagonal (tools/rmat.py) and hands the CSR to lz_csr_create */
+int lz_gen_rmat_edges(lz_ctx *ctx, int scale, int64_t n_edges, uint64_t seed, int32_t *src, int32_t *dst);
 /* v[i] = 2*u(splitmix64(seed ^ i)) - 1 ; block: V[i + c*ld] = 2*u(splitmix64(seed ^ (i*b+c))) - 1 */
 int lz_gen_start_vector(lz_ctx *ctx, int64_t n, uint64_t seed, double *v);
 int lz_gen_start_block(lz_ctx *ctx, int64_t n, int b, int64_t ld, uint64_t seed, double *V);
