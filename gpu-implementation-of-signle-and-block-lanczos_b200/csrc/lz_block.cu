@@ -292,14 +292,9 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
 // basis block j (row-major) -> stored basis; block CGS sweep over the stored blocks
 __global__ void k_flag_init(int *flags) { flags[0] = 0x7fffffff; flags[2] = 0x7fffffff; }
 
-// C = V_j^T W for one stored block, then W -= V_j C   (classical block Gram-Schmidt, one block at a
-// time would be modified GS; we compute all projections first to stay classical)
 static int block_cgs_sweep(lz_ctx *ctx, int64_t n, int bw, int nblocks, const double *V, double *W, double *C)
 {
-    const size_t pan = (size_t)n * bw, bb = (size_t)bw * bw;
-    for (int j = 0; j < nblocks; ++j) LZ_TRY(lz_gram(ctx, n, bw, true, V + pan * j, 0, W, 0, C + bb * j, 0));
-    for (int j = 0; j < nblocks; ++j) LZ_TRY(lz_panel(ctx, n, bw, true, V + pan * j, 0, C + bb * j, 1.0, -1.0, W, 0, nullptr));
-    return LZ_OK;
+    return lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)n * bw, W, C);
 }
 
 extern "C" {

@@ -86,7 +86,7 @@ struct lz_ctx {
 enum { LZ_K_SPMV = 0, LZ_K_PASSB = 1, LZ_K_PROJECT = 2, LZ_K_UPDATE = 3, LZ_K_SPMM = 4, LZ_K_GRAM = 5, LZ_K_PANEL = 6, LZ_K_SMALL = 7, LZ_K_COMM = 8, LZ_K_CLASSES = 9 };
 void lz_prof_begin(lz_ctx *ctx, int cls, double bytes);
 void lz_prof_end(lz_ctx *ctx);
-#define LZ_PARTIALS_CAP (1 << 20)
+#define LZ_PARTIALS_CAP (1 << 22)
 #define LZ_TICKETS 64
 #define LZ_SCALARS 8192
 #define LZ_FLAGS 64

@@ -80,6 +80,44 @@ int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t l
     return panel_launch<false>(ctx, n, bw, T, ldt, S, beta, alpha, R, ldr, G_opt, (double *)w, grid);
 }
 
+// one classical block Gram-Schmidt sweep of W (row-major n x bw) against J stored row-major blocks
+template <int BW, int JB>
+static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int64_t pan, double *W, double *C)
+{
+    const int gx = ctx->sm_count * 2, batches = (J + JB - 1) / JB;
+    const size_t bb = (size_t)BW * BW;
+    void *w;
+    LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * ((size_t)batches * gx * JB * bb + (size_t)J * bb), &w));
+    double *gpart = (double *)w, *Cf = gpart + (size_t)batches * gx * JB * bb;
+    const int ugrid = ctx->sm_count * 4;
+    lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * BW * (J + batches));
+    if constexpr (BW >= 16) k_block_project_w<BW, JB><<<dim3(gx, batches), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, W, gpart);
+    else k_block_project<BW, JB><<<dim3(gx, batches), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, W, gpart);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    if constexpr (BW >= 16) k_block_project_reduce_w<BW, JB><<<J, 256, 0, ctx->stream>>>(J, gx, gpart, C, Cf);
+    else k_block_project_reduce<JB><<<J, 256, 0, ctx->stream>>>(BW, J, gx, gpart, C);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * BW * (J + 2));
+    if constexpr (BW >= 16) k_block_update_w<BW><<<ugrid < 1 ? 1 : ugrid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, Cf, W);
+    else k_block_update<BW><<<dense_grid(ctx, n), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, C, W);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    return LZ_OK;
+}
+
+int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C)
+{
+    if (bw == 8) return block_cgs_launch<8, 8>(ctx, n, J, V, pan, W, C);
+    if (bw == 16) return block_cgs_launch<16, 4>(ctx, n, J, V, pan, W, C);
+    if (bw == 32) return block_cgs_launch<32, 2>(ctx, n, J, V, pan, W, C);
+    // generic widths: block-by-block products (SIMT)
+    const size_t bb = (size_t)bw * bw;
+    for (int j = 0; j < J; ++j) LZ_TRY(lz_gram(ctx, n, bw, true, V + pan * j, 0, W, 0, C + bb * j, 0));
+    for (int j = 0; j < J; ++j) LZ_TRY(lz_panel(ctx, n, bw, true, V + pan * j, 0, C + bb * j, 1.0, -1.0, W, 0, nullptr));
+    return LZ_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // b x b symmetric eigen-decomposition + matrix square root, one CTA.
 // Parallel cyclic Jacobi (round-robin pairing: b/2 disjoint rotations per round, b-1 rounds per

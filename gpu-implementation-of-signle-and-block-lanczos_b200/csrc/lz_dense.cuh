@@ -287,3 +287,316 @@ k_panel_simt(int64_t n, int bw, const double *T_, int64_t ldt, const double *__r
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Block reorthogonalisation against J stored row-major blocks V_0..V_{J-1} (each n x BW, `pan`
+// doubles apart).  Two kernels per classical Gram-Schmidt sweep, each streaming the basis once:
+//   k_block_project : C_j = V_j^T W for a batch of JB stored blocks per CTA row (blockIdx.y); the W
+//                     fragments of a 4-row group are loaded once and reused for the JB blocks, so W
+//                     is re-read J/JB times instead of J times.
+//   k_block_update  : W -= sum_j V_j C_j ; the W tile IS the DMMA accumulator, so W is read and
+//                     written exactly once per sweep; the C_j fragments are reused over four 8-row groups.
+// flops 4 n (J BW) BW per sweep over 16 n J BW bytes: AI -> BW/4 flop/B.
+// ---------------------------------------------------------------------------------------------
+template <int BW, int JB>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_block_project(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ W,
+                double *__restrict__ gpart /* [gridDim.y][gridDim.x][JB][BW*BW] */)
+{
+    constexpr int T = BW / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    const int j0 = blockIdx.y * JB;
+    double acc[JB][T][T][2];
+#pragma unroll
+    for (int jb = 0; jb < JB; ++jb)
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) acc[jb][a][b][0] = acc[jb][a][b][1] = 0.0;
+    const int64_t n_slabs = (n + 31) / 32;
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+#pragma unroll 2
+        for (int g = 0; g < 8; ++g) {
+            const int64_t i = slab * 32 + g * 4 + kk;
+            const bool ok = i < n;
+            double yb[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) yb[t] = ok ? __ldg(W + i * BW + t * 8 + mm) : 0.0;
+#pragma unroll
+            for (int jb = 0; jb < JB; ++jb) {
+                if (j0 + jb < J) {
+                    const double *Vj = V + (int64_t)(j0 + jb) * pan;
+                    double xa[T];
+#pragma unroll
+                    for (int t = 0; t < T; ++t) xa[t] = ok ? __ldcs(Vj + i * BW + t * 8 + mm) : 0.0;
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) lz_dmma(acc[jb][a][b][0], acc[jb][a][b][1], xa[a], yb[b]);
+                }
+            }
+        }
+    }
+    __shared__ double sm[BW * BW];
+#pragma unroll
+    for (int jb = 0; jb < JB; ++jb) {
+        for (int w = 0; w < LZ_DENSE_WARPS; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int p = a * 8 + mm, q = b * 8 + 2 * kk;
+                        if (w == 0) { sm[p + q * BW] = acc[jb][a][b][0]; sm[p + (q + 1) * BW] = acc[jb][a][b][1]; }
+                        else { sm[p + q * BW] += acc[jb][a][b][0]; sm[p + (q + 1) * BW] += acc[jb][a][b][1]; }
+                    }
+            }
+            __syncthreads();
+        }
+        double *out = gpart + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * JB + jb) * BW * BW;
+        for (int e = threadIdx.x; e < BW * BW; e += LZ_DENSE_THREADS) out[e] = sm[e];
+        __syncthreads();
+    }
+}
+
+// C[j] = sum over CTAs of the partials of stored block j (fixed order)
+template <int JB>
+static __global__ void k_block_project_reduce(int bw, int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C)
+{
+    const int j = blockIdx.x, batch = j / JB, jb = j % JB;
+    for (int e = threadIdx.x; e < bw * bw; e += blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < n_parts; ++p) s += gpart[(((size_t)batch * n_parts + p) * JB + jb) * bw * bw + e];
+        C[(size_t)j * bw * bw + e] = s;
+    }
+}
+
+template <int BW>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_block_update(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ C, double *__restrict__ W)
+{
+    constexpr int NT = BW / 8, KT = BW / 4, G = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    const int64_t n_slabs = (n + 31) / 32;
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+        double d[G][NT][2];
+        int64_t row[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            row[g] = slab * 32 + g * 8 + mm;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double2 v = row[g] < n ? *reinterpret_cast<const double2 *>(W + row[g] * BW + nt * 8 + 2 * kk) : make_double2(0.0, 0.0);
+                d[g][nt][0] = v.x; d[g][nt][1] = v.y;
+            }
+        }
+        for (int j = 0; j < J; ++j) {
+            const double *Vj = V + (int64_t)j * pan, *Cj = C + (size_t)j * BW * BW;
+            double sb[KT][NT];
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) sb[kt][nt] = -__ldg(Cj + (kt * 4 + kk) + (nt * 8 + mm) * BW);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                double ta[KT];
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) ta[kt] = row[g] < n ? __ldcs(Vj + row[g] * BW + kt * 4 + kk) : 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int kt = 0; kt < KT; ++kt) lz_dmma(d[g][nt][0], d[g][nt][1], ta[kt], sb[kt][nt]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            if (row[g] < n) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    *reinterpret_cast<double2 *>(W + row[g] * BW + nt * 8 + 2 * kk) = make_double2(d[g][nt][0], d[g][nt][1]);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide-load versions for BW in {16, 32}: fragment-ordered 8-byte loads cost one L1 wavefront per 64
+// bytes (four half-lines per instruction), and the L1 data pipe -- not HBM -- bounds the kernel.
+// The MMA only needs a consistent labelling of rows/columns inside a tile, so the tiles are built
+// from PERMUTED columns and every load becomes a full-line vector load with no shuffle:
+//   project: lane (kk,mm) loads 16 bytes  X[i0+kk, 16v+2mm .. +1]  -> tile 2v+h owns columns 16v+2mm+h
+//   update : lane (kk,mm) loads 32 bytes  V[i0+mm, 16c+4kk .. +3]  -> k-tile 4c+e owns columns 16c+4kk+e
+// and the C_j operand of the update is pre-arranged in fragment order (Cf) by the reduce kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 lz_ld128_stream(const double *p)
+{
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+template <int BW, int JB>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_block_project_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ W,
+                  double *__restrict__ gpart /* [gridDim.y][gridDim.x][JB][BW*BW] */)
+{
+    constexpr int T = BW / 8, NV = BW / 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    const int j0 = blockIdx.y * JB;
+    double acc[JB][T][T][2];
+#pragma unroll
+    for (int jb = 0; jb < JB; ++jb)
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) acc[jb][a][b][0] = acc[jb][a][b][1] = 0.0;
+    const int64_t n_slabs = (n + 31) / 32;
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+#pragma unroll 2
+        for (int g = 0; g < 8; ++g) {
+            const int64_t i = slab * 32 + g * 4 + kk;
+            const bool ok = i < n;
+            double yb[T];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const double2 t = ok ? __ldg(reinterpret_cast<const double2 *>(W + i * BW + 16 * v + 2 * mm)) : make_double2(0.0, 0.0);
+                yb[2 * v] = t.x; yb[2 * v + 1] = t.y;
+            }
+            // all loads of the group first, then the MMAs: a warp waits once per group, not once per block
+            double xa[JB][T];
+#pragma unroll
+            for (int jb = 0; jb < JB; ++jb) {
+                const bool live = ok && (j0 + jb < J);
+                const double *Vj = V + (int64_t)(j0 + jb) * pan;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const double2 t = live ? lz_ld128_stream(Vj + i * BW + 16 * v + 2 * mm) : make_double2(0.0, 0.0);
+                    xa[jb][2 * v] = t.x; xa[jb][2 * v + 1] = t.y;
+                }
+            }
+#pragma unroll
+            for (int jb = 0; jb < JB; ++jb)
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) lz_dmma(acc[jb][a][b][0], acc[jb][a][b][1], xa[jb][a], yb[b]);
+        }
+    }
+    __shared__ double sm[BW * BW];
+#pragma unroll
+    for (int jb = 0; jb < JB; ++jb) {
+        for (int w = 0; w < LZ_DENSE_WARPS; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int p = 16 * (a / 2) + 2 * mm + (a % 2);
+                            const int q = 16 * (b / 2) + 2 * (2 * kk + e) + (b % 2);
+                            if (w == 0) sm[p + q * BW] = acc[jb][a][b][e];
+                            else sm[p + q * BW] += acc[jb][a][b][e];
+                        }
+            }
+            __syncthreads();
+        }
+        double *out = gpart + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * JB + jb) * BW * BW;
+        for (int e = threadIdx.x; e < BW * BW; e += LZ_DENSE_THREADS) out[e] = sm[e];
+        __syncthreads();
+    }
+}
+
+// C[j] = sum of partials (fixed order); Cf[j][kt][nt][lane] = -C_j[16c+4kk+e, 8nt+mm] with kt = 4c+e
+template <int BW, int JB>
+static __global__ void k_block_project_reduce_w(int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C,
+                                                double *__restrict__ Cf)
+{
+    constexpr int KT = BW / 4, NT = BW / 8;
+    __shared__ double cs[BW * BW];
+    const int j = blockIdx.x, batch = j / JB, jb = j % JB;
+    for (int e = threadIdx.x; e < BW * BW; e += blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < n_parts; ++p) s += gpart[(((size_t)batch * n_parts + p) * JB + jb) * BW * BW + e];
+        C[(size_t)j * BW * BW + e] = s;
+        cs[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KT * NT * 32; e += blockDim.x) {
+        const int lane = e % 32, nt = (e / 32) % NT, kt = e / (32 * NT);
+        const int kk = lane & 3, mm = lane >> 2, c = kt / 4, el = kt % 4;
+        Cf[(size_t)j * BW * BW + e] = -cs[(16 * c + 4 * kk + el) + (nt * 8 + mm) * BW];
+    }
+}
+
+template <int BW>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_block_update_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ Cf, double *__restrict__ W)
+{
+    constexpr int NT = BW / 8, KT = BW / 4, NC = BW / 16, G = BW == 16 ? 4 : 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    const int64_t n_slabs = (n + 8 * G - 1) / (8 * G);
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+        double d[G][NT][2];
+        int64_t row[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            row[g] = slab * (8 * G) + g * 8 + mm;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double2 v = row[g] < n ? *reinterpret_cast<const double2 *>(W + row[g] * BW + nt * 8 + 2 * kk) : make_double2(0.0, 0.0);
+                d[g][nt][0] = v.x; d[g][nt][1] = v.y;
+            }
+        }
+        // operands of stored block j: the V rows of the slab (one 256-bit load per 16 columns) and
+        // the fragment-ordered C_j; block j+1 is fetched while block j is multiplied
+        double ta[2][G][KT];
+        auto fetch = [&](int buf, int j) {
+            const double *Vj = V + (int64_t)j * pan;
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (row[g] < n) lz_ld256_stream(Vj + row[g] * BW + 16 * c + 4 * kk, ta[buf][g][4 * c], ta[buf][g][4 * c + 1], ta[buf][g][4 * c + 2], ta[buf][g][4 * c + 3]);
+                    else ta[buf][g][4 * c] = ta[buf][g][4 * c + 1] = ta[buf][g][4 * c + 2] = ta[buf][g][4 * c + 3] = 0.0;
+                }
+        };
+        auto multiply = [&](int buf, int j) {
+            const double *Cj = Cf + (size_t)j * BW * BW;      // a few KB per block, L1-resident across the CTA's warps
+            double sb[KT][NT];
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) sb[kt][nt] = __ldg(Cj + (kt * NT + nt) * 32 + lane);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) lz_dmma(d[g][nt][0], d[g][nt][1], ta[buf][g][kt], sb[kt][nt]);
+        };
+        fetch(0, 0);
+        int j = 0;
+        for (; j + 2 <= J; j += 2) {
+            fetch(1, j + 1);
+            multiply(0, j);
+            if (j + 2 < J) fetch(0, j + 2);
+            multiply(1, j + 1);
+        }
+        if (j < J) multiply(0, j);
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            if (row[g] < n) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    *reinterpret_cast<double2 *>(W + row[g] * BW + nt * 8 + 2 * kk) = make_double2(d[g][nt][0], d[g][nt][1]);
+            }
+    }
+}

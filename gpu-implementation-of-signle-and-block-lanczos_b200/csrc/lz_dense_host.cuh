@@ -10,3 +10,5 @@ int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t l
              double alpha, double *R, int64_t ldr, double *G_opt);
 int lz_sqrtm_launch(lz_ctx *ctx, int b, double *S, double *Sinv, int *flag);
 int lz_copy_row_launch(lz_ctx *ctx, int64_t lc, int b, bool rm, const double *Q, int64_t ld, double *q, int64_t off);
+// one classical block Gram-Schmidt sweep: C_j = V_j^T W (j < J), W -= sum_j V_j C_j; V_j row-major, `pan` apart
+int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C);

@@ -41,14 +41,20 @@ struct LzPassA {
 
 template <int MODE>
 struct LzRowEpi {
+    // the fields of LzPassA the epilogue needs, held by value: a reference to the kernel parameter
+    // would force the whole struct through local memory
     double sx, sprev, beta;
-    const LzPassA &a;
-    __device__ __forceinline__ LzRowEpi(const LzPassA &args) : a(args)
+    const double *x_own, *u_prev;
+    double *vcol, *qout;
+    int64_t lc;
+    bool first;
+    __device__ __forceinline__ LzRowEpi(const LzPassA &args)
     {
         sx = 1.0; sprev = 0.0; beta = 0.0;
+        x_own = args.x_own; u_prev = args.u_prev; vcol = args.vcol; qout = args.qout; lc = args.lc; first = args.first != 0;
         if (MODE == LZ_EPI_LANCZOS) {
-            sx = a.invb[a.j];
-            if (!a.first) { sprev = a.invb[a.j - 1]; beta = a.beta[a.j]; }
+            sx = args.invb[args.j];
+            if (!first) { sprev = args.invb[args.j - 1]; beta = args.beta[args.j]; }
         }
     }
     // scale applied to every gathered x value
@@ -58,8 +64,8 @@ struct LzRowEpi {
     {
         xo = 0.0; up = 0.0;
         if (MODE == LZ_EPI_LANCZOS) {
-            xo = a.x_own[i];
-            if (!a.first) up = a.u_prev[i];
+            xo = x_own[i];
+            if (!first) up = u_prev[i];
         }
     }
     // finish row i whose raw sum is t; returns the row's contribution to alpha
@@ -68,10 +74,10 @@ struct LzRowEpi {
         if (MODE == LZ_EPI_PLAIN) { y[i] = t; return 0.0; }
         const double qi = __dmul_rn(xo, sx);
         double w = t;
-        if (!a.first) w = __dadd_rn(t, __dmul_rn(-beta, __dmul_rn(up, sprev)));
+        if (!first) w = __dadd_rn(t, __dmul_rn(-beta, __dmul_rn(up, sprev)));
         y[i] = w;
-        if (a.vcol) a.vcol[i] = qi;
-        if (i == a.lc && a.qout) *a.qout = qi;
+        if (vcol) vcol[i] = qi;
+        if (i == lc && qout) *qout = qi;
         return __dmul_rn(w, qi);
     }
     __device__ __forceinline__ double finish(int64_t i, double t, double *__restrict__ y) const

@@ -32,14 +32,18 @@ def vector_case(ctx, A, name, m, out):
     out[name] = dict(ms_per_iter=ms / m, it_per_s=m / ms * 1e3, step_gbs=byt / (ms / m) / 1e6, step_frac=byt / (ms / m) / 1e6 / PEAK, classes=prof)
 
 
-def block_case(ctx, A, name, bw, m, out):
+def block_case(ctx, A, name, bw, m, out, reorth=0):
     n, nnz = A.n_rows, A.nnz
     B = torch.empty(n * bw, dtype=torch.float64, device="cuda")
     lz.check(lz.lib().lz_gen_start_block(ctx.h, n, bw, n, 0x5EED, B.data_ptr()))
     al = torch.zeros(m * bw * bw, dtype=torch.float64, device="cuda"); be = torch.zeros((m + 1) * bw * bw, dtype=torch.float64, device="cuda")
     q = torch.zeros(m * bw, dtype=torch.float64, device="cuda")
-    ms, prof = timed(ctx, lambda: lz.block_lanczos(ctx, A, B, n, bw, m, al, be, q), 2)
+    ms, prof = timed(ctx, lambda: lz.block_lanczos(ctx, A, B, n, bw, m, al, be, q, reorth=reorth), 2)
     assert torch.isfinite(al).all()
+    for k in ("cgs_project", "cgs_update"):       # reorth GEMMs: flops = 2 n (J b) b per launch = bytes/8 * 2b / ... report TFLOP/s
+        if k in prof:
+            # bytes recorded = 8 n b (J + extra): flops = 2 * (bytes/8) * b  (each basis element does b MACs)
+            prof[k]["tflops"] = 2.0 * (prof[k]["gbs"] * 1e9 / 8.0) * bw / 1e12
     byt = 12.0 * nnz + 4.0 * n + 10 * 8.0 * n * bw
     out[name] = dict(ms_per_iter=ms / m, it_per_s=m / ms * 1e3, step_gbs=byt / (ms / m) / 1e6, step_frac=byt / (ms / m) / 1e6 / PEAK, classes=prof)
 
@@ -51,10 +55,11 @@ def main():
     out = {}
     if "cfg2v" in which:
         A = lz.Matrix.laplacian2d(ctx, 4096, 4096); vector_case(ctx, A, "lap2d_4096_vector_noreorth", 100, out); A.close()
-    if "cfg3v" in which or "cfg3" in which:
+    if "cfg3v" in which or "cfg3" in which or "cfg3r" in which:
         A = lz.Matrix.laplacian3d(ctx, 256, 256, 256)
         if "cfg3v" in which: vector_case(ctx, A, "lap3d_256_vector_noreorth", 100, out)
         if "cfg3" in which: block_case(ctx, A, "lap3d_256_block16", 16, 12, out)
+        if "cfg3r" in which: block_case(ctx, A, "lap3d_256_block16_reorth", 16, 24, out, reorth=1)
         A.close()
     if "cfg4" in which:
         scale = int(os.environ.get("RMAT_SCALE", "24"))
