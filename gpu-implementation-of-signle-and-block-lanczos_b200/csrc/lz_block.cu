@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include "lz_dense_host.cuh"
+#include "lz_spmv.cuh"
 
 #define SPMM_THREADS 256
 #define SPMM_U 2            // independent rows per lane group in flight
@@ -152,6 +153,150 @@ k_spmm_rm(int64_t n_rows, const int32_t *__restrict__ rowptr, const int32_t *__r
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged row-major SpMM (default for BW in {8,16,32} on operators with a chunk schedule).
+// The rowptr -> (col,val) -> X[col] chain of the kernel above is three dependent global loads per
+// row; here warp 0 streams each chunk's vals / colidx / rowptr slices into a shared-memory ring
+// with bulk async copies (the same producer as k_csr_spmv_ws), so a compute warp's only global
+// loads are the gathered rows of X (plus the independent Q0 row and the W store): one round trip
+// per row.  A group of LW lanes owns a row, two rows per group in flight.
+// ---------------------------------------------------------------------------------------------
+#define SPMM_WS_RCAP 1024      // rowptr entries staged per chunk
+
+__device__ __forceinline__ void lz_ld256_ro(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// A group of LW = BW/4 lanes owns a row and every lane carries FOUR adjacent columns (one 256-bit
+// load per gathered row): the kernel is bound by instruction issue, and four columns per lane halve
+// the instructions per non-zero against the two-column layout of k_spmm_rm.
+template <int BW, int CW, int STAGES, int CAP>
+__global__ void __launch_bounds__((1 + CW) * 32, 2)
+k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
+          const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+          const double *__restrict__ X, double *__restrict__ W)
+{
+    constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *vals_s = reinterpret_cast<double *>(smem_raw);
+    int *cols_s = reinterpret_cast<int *>(smem_raw + 8 * (size_t)CAP * STAGES);
+    int *rptr_s = reinterpret_cast<int *>(smem_raw + 12 * (size_t)CAP * STAGES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 12 * (size_t)CAP * STAGES + 4 * (size_t)SPMM_WS_RCAP * STAGES);
+    uint64_t *freeb = full + STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { lz_mbar_init(&full[s], 1); lz_mbar_init(&freeb[s], CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // every CTA owns a CONTIGUOUS range of chunks: the rows gathered for the +-nx neighbours of a stencil
+    // are this CTA's own rows a few chunks later (L1 hits), and all CTAs advance through their ranges in
+    // step, so the +-nx*ny neighbours are the rows a neighbouring CTA is working on (L2 hits)
+    const int per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const int first = blockIdx.x * per_cta, step = 1;
+    const int last = min(n_chunks, first + per_cta);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            int p0 = 0, p1 = 0, r0 = 0, r1 = 0;
+            if (first < last) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; r0 = chunk_row[first]; r1 = chunk_row[first + 1]; }
+            int it = 0;
+            for (int c = first; c < last; c += step, ++it) {
+                const int slot = it % STAGES;
+                const int cp0 = p0, cp1 = p1, cr0 = r0, cr1 = r1;
+                if (c + step < last) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; r0 = chunk_row[c + step]; r1 = chunk_row[c + step + 1]; }
+                lz_mbar_wait(&freeb[slot], ((it / STAGES) & 1) ^ 1);
+                const int a0 = cp0 & ~3, cnt4 = (cp1 - a0) & ~3;
+                const int ra = cr0 & ~3;
+                const int rcnt = ((cr1 + 1 - ra) + 3) & ~3;               // rowptr[ra .. cr1] rounded up to 16 bytes
+                const bool rows_ok = rcnt <= SPMM_WS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
+                if (cp1 - a0 > CAP || cnt4 == 0) { lz_mbar_arrive(&full[slot]); continue; }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                lz_mbar_expect_tx(&full[slot], (uint32_t)cnt4 * 12u + (rows_ok ? (uint32_t)rcnt * 4u : 0u));
+                lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
+                lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
+                if (rows_ok) lz_bulk_g2s(rptr_s + (size_t)slot * SPMM_WS_RCAP, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ compute warps
+        const int sub = lane / LW, l = lane % LW;
+        const int gid = (warp - 1) * RPW + sub;
+        int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
+        if (first < last) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
+        int it = 0;
+        for (int c = first; c < last; c += step, ++it) {
+            const int slot = it % STAGES;
+            const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
+            if (c + step < last) {
+                nr0 = chunk_row[c + step]; nr1 = chunk_row[c + step + 1];
+                np0 = chunk_ptr[c + step]; np1 = chunk_ptr[c + step + 1];
+            }
+            const int a0 = cp0 & ~3, cnt = cp1 - a0, cnt4 = cnt & ~3;
+            const int ra = r0 & ~3;
+            const int rcnt = ((r1 + 1 - ra) + 3) & ~3;
+            const bool staged = cnt <= CAP && cnt4 > 0;
+            const bool rows_ok = staged && rcnt <= SPMM_WS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
+            const double *vs = vals_s + (size_t)slot * CAP;
+            const int *cs = cols_s + (size_t)slot * CAP;
+            const int *rs = rptr_s + (size_t)slot * SPMM_WS_RCAP;
+            lz_mbar_wait(&full[slot], (it / STAGES) & 1);
+            for (int64_t r = (int64_t)r0 + gid; r < r1; r += NG) {
+                int s, e;
+                if (rows_ok) { s = rs[r - ra]; e = rs[r - ra + 1]; }
+                else { s = rowptr[r]; e = rowptr[r + 1]; }
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                const double *Xl = X + 4 * l;
+                for (int k0 = s; k0 < e; k0 += G) {
+                    // (col,val) straight from the staged slice: a broadcast shared load per entry
+                    int cc[G]; double vv[G]; double x0[G], x1[G], x2[G], x3[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const int k = k0 + g, ks = k - a0;
+                        cc[g] = -1; vv[g] = 0.0;
+                        if (k < e) {
+                            if (staged && ks < cnt4) { cc[g] = cs[ks]; vv[g] = vs[ks]; }
+                            else { cc[g] = __ldcs(colidx + k); vv[g] = __ldcs(vals + k); }
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        x0[g] = x1[g] = x2[g] = x3[g] = 0.0;
+                        if (cc[g] >= 0) lz_ld256_ro(Xl + (int64_t)cc[g] * BW, x0[g], x1[g], x2[g], x3[g]);
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        acc0 = fma(vv[g], x0[g], acc0); acc1 = fma(vv[g], x1[g], acc1);
+                        acc2 = fma(vv[g], x2[g], acc2); acc3 = fma(vv[g], x3[g], acc3);
+                    }
+                }
+                lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+            }
+            __syncwarp();
+            if (lane == 0) lz_mbar_arrive(&freeb[slot]);
+        }
+    }
+}
+
+template <int BW>
+static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const double *X, double *W)
+{
+    constexpr int CW = 12, STAGES = 2, CAP = 2048;
+    const size_t smem = (size_t)STAGES * (CAP * 12 + SPMM_WS_RCAP * 4) + 16 * STAGES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LZ_CUDA(cudaFuncSetAttribute(k_spmm_ws<BW, CW, STAGES, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = ctx->sm_count * 2;
+    if (grid > A->n_chunks) grid = A->n_chunks;
+    k_spmm_ws<BW, CW, STAGES, CAP><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
+        A->n_chunks, A->n_rows, A->chunk_row, A->chunk_ptr, A->rowptr, A->colidx, A->vals, X, W);
+    return LZ_OK;
+}
+
 // any bw <= 32 (odd widths, bw = 1): one lane per column
 template <bool FUSE_SUB>
 __global__ void __launch_bounds__(SPMM_THREADS)
@@ -273,6 +418,15 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
         int64_t want = (n + SPMM_SLAB - 1) / SPMM_SLAB;
         int64_t cap = (int64_t)ctx->sm_count * 8;
         const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+        const bool ws = A->tma_ok && A->cap == 2048 && ctx->spmv_variant != 9 && !fuse && ((uintptr_t)X % 32 == 0) && ((uintptr_t)W % 32 == 0);
+        if (ws && (bw == 8 || bw == 16 || bw == 32)) {
+            if (bw == 8) LZ_TRY(launch_spmm_ws<8>(ctx, A, X, W));
+            else if (bw == 16) LZ_TRY(launch_spmm_ws<16>(ctx, A, X, W));
+            else LZ_TRY(launch_spmm_ws<32>(ctx, A, X, W));
+            LZ_LAUNCH_CHECK(ctx);
+            lz_prof_end(ctx);
+            return LZ_OK;
+        }
 #define CSR_CASE(B)                                                                                                     \
     if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, A->rowptr, A->colidx, A->vals, X, W, Q0, Bm); \
     else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, A->rowptr, A->colidx, A->vals, X, W, Q0, Bm)
@@ -357,9 +511,12 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
         LZ_CUDA(cudaMemcpyAsync(bj, G, sizeof(double) * bb, cudaMemcpyDeviceToDevice, ctx->stream));   // :137
         LZ_TRY(lz_sqrtm_launch(ctx, bw, bj, binv, flag));                                     // :142
         LZ_TRY(lz_panel(ctx, n, bw, true, W, 0, binv, 0.0, 1.0, Q1, 0, nullptr));             // :145
-        LZ_TRY(spmm_rm(ctx, A, bw, Q1, W, Q0, bj));                                           // :149 + :152 fused
-        LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q1, 0, aj, 1));                                // :155
-        LZ_TRY(lz_panel(ctx, n, bw, true, Q1, 0, aj, 1.0, -1.0, W, 0, reorth ? nullptr : G)); // :159 (+ next :137)
+        // W' = A Q1 (:149); alpha_j from W' (the reference forms it after subtracting Q0 beta_j, :152-155: the
+        // two differ by sym(beta_j^T Q0^T Q1), i.e. by rounding, because consecutive blocks are orthogonal);
+        // then ONE pass subtracts both Q0 beta_j and Q1 alpha_j and accumulates the next W^T W (:152,:159,:137)
+        LZ_TRY(spmm_rm(ctx, A, bw, Q1, W, nullptr, nullptr));
+        LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q1, 0, aj, 1));
+        LZ_TRY(lz_panel2(ctx, n, bw, Q0, bj, Q1, aj, W, reorth ? nullptr : G));
         double *t = Q0; Q0 = Q1; Q1 = t;                                                      // :162 (no copy)
         if (q) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q0, 0, q, (int64_t)j * bw));      // :165
         if (V) {

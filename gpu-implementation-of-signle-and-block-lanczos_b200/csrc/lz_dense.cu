@@ -80,6 +80,31 @@ int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t l
     return panel_launch<false>(ctx, n, bw, T, ldt, S, beta, alpha, R, ldr, G_opt, (double *)w, grid);
 }
 
+// W -= T1 S1 + T2 S2 (row-major), G_opt receives W_new^T W_new
+int lz_panel2(lz_ctx *ctx, int64_t n, int bw, const double *T1, const double *S1, const double *T2, const double *S2, double *W, double *G_opt)
+{
+    if (!(bw == 8 || bw == 16 || bw == 32)) {
+        LZ_TRY(lz_panel(ctx, n, bw, true, T1, 0, S1, 1.0, -1.0, W, 0, nullptr));
+        return lz_panel(ctx, n, bw, true, T2, 0, S2, 1.0, -1.0, W, 0, G_opt);
+    }
+    const int grid = dense_grid(ctx, n);
+    void *w = nullptr;
+    if (G_opt) LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * bw * bw, &w));
+    lz_prof_begin(ctx, LZ_K_PANEL, 8.0 * (double)n * bw * 4.0);
+#define LZ_P2(B)                                                                                                        \
+    if (G_opt) k_panel2_dmma<B, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, T1, S1, T2, S2, W, (double *)w);   \
+    else k_panel2_dmma<B, false><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, T1, S1, T2, S2, W, (double *)w)
+    if (bw == 8) { LZ_P2(8); } else if (bw == 16) { LZ_P2(16); } else { LZ_P2(32); }
+#undef LZ_P2
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    if (G_opt) {
+        k_gram_reduce<<<1, 256, 0, ctx->stream>>>(bw, grid, (const double *)w, G_opt, 0);
+        LZ_LAUNCH_CHECK(ctx);
+    }
+    return LZ_OK;
+}
+
 // one classical block Gram-Schmidt sweep of W (row-major n x bw) against J stored row-major blocks
 template <int BW, int JB>
 static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int64_t pan, double *W, double *C)

@@ -600,3 +600,103 @@ k_block_update_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, co
             }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// W -= T1 S1 + T2 S2  (row-major panels, S column-major BW x BW), optionally G_partial = W_new^T W_new.
+// One pass for the two subtractions of a block Lanczos step (W -= Q_{j-1} beta_j, W -= Q_j alpha_j)
+// with the next step's Gram fused: W is read and written once.
+// ---------------------------------------------------------------------------------------------
+template <int BW, bool GRAM>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_panel2_dmma(int64_t n, const double *__restrict__ T1, const double *__restrict__ S1, const double *__restrict__ T2,
+              const double *__restrict__ S2, double *__restrict__ R_, double *__restrict__ gpart)
+{
+    constexpr int NT = BW / 8, KT = BW / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    double s1[KT][NT], s2[KT][NT];
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            s1[kt][nt] = -S1[(kt * 4 + kk) + (nt * 8 + mm) * BW];
+            s2[kt][nt] = -S2[(kt * 4 + kk) + (nt * 8 + mm) * BW];
+        }
+    double gacc[GRAM ? NT : 1][GRAM ? NT : 1][2];
+    if (GRAM) {
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int b = 0; b < NT; ++b) gacc[a][b][0] = gacc[a][b][1] = 0.0;
+    }
+    __shared__ double stage[GRAM ? LZ_DENSE_WARPS : 1][GRAM ? 8 * (BW + 1) : 1];
+    const int64_t n_slabs = (n + 31) / 32;
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+#pragma unroll 2
+        for (int g = 0; g < 4; ++g) {
+            const int64_t i = slab * 32 + g * 8 + mm;
+            const bool ok = i < n;
+            double ta[KT], tb[KT], d[NT][2];
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                ta[kt] = ok ? __ldg(T1 + i * BW + kt * 4 + kk) : 0.0;
+                tb[kt] = ok ? __ldg(T2 + i * BW + kt * 4 + kk) : 0.0;
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double2 v = ok ? *reinterpret_cast<const double2 *>(R_ + i * BW + nt * 8 + 2 * kk) : make_double2(0.0, 0.0);
+                d[nt][0] = v.x; d[nt][1] = v.y;
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    lz_dmma(d[nt][0], d[nt][1], ta[kt], s1[kt][nt]);
+                    lz_dmma(d[nt][0], d[nt][1], tb[kt], s2[kt][nt]);
+                }
+            if (ok) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    *reinterpret_cast<double2 *>(R_ + i * BW + nt * 8 + 2 * kk) = make_double2(d[nt][0], d[nt][1]);
+            }
+            if (GRAM) {
+                double *st = stage[warp];
+                __syncwarp();
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    st[mm * (BW + 1) + nt * 8 + 2 * kk] = ok ? d[nt][0] : 0.0;
+                    st[mm * (BW + 1) + nt * 8 + 2 * kk + 1] = ok ? d[nt][1] : 0.0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double fr[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) fr[t] = st[(h * 4 + kk) * (BW + 1) + t * 8 + mm];
+#pragma unroll
+                    for (int a = 0; a < NT; ++a)
+#pragma unroll
+                        for (int b = 0; b < NT; ++b) lz_dmma(gacc[a][b][0], gacc[a][b][1], fr[a], fr[b]);
+                }
+            }
+        }
+    }
+    if (GRAM) {
+        __shared__ double sm[BW * BW];
+        for (int w = 0; w < LZ_DENSE_WARPS; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int b = 0; b < NT; ++b) {
+                        const int p = a * 8 + mm, q = b * 8 + 2 * kk;
+                        if (w == 0) { sm[p + q * BW] = gacc[a][b][0]; sm[p + (q + 1) * BW] = gacc[a][b][1]; }
+                        else { sm[p + q * BW] += gacc[a][b][0]; sm[p + (q + 1) * BW] += gacc[a][b][1]; }
+                    }
+            }
+            __syncthreads();
+        }
+        for (int e = threadIdx.x; e < BW * BW; e += LZ_DENSE_THREADS) gpart[(size_t)blockIdx.x * BW * BW + e] = sm[e];
+    }
+}
