@@ -281,7 +281,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
 }
 
 template <int BW>
-static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const double *X, double *W)
+static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W)
 {
     constexpr int CW = 12, STAGES = 2, CAP = 2048;
     const size_t smem = (size_t)STAGES * (CAP * 12 + SPMM_WS_RCAP * 4) + 16 * STAGES;
@@ -293,7 +293,7 @@ static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const double *X, doub
     int grid = ctx->sm_count * 2;
     if (grid > A->n_chunks) grid = A->n_chunks;
     k_spmm_ws<BW, CW, STAGES, CAP><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
-        A->n_chunks, A->n_rows, A->chunk_row, A->chunk_ptr, A->rowptr, A->colidx, A->vals, X, W);
+        A->n_chunks, n_rows, A->chunk_row, A->chunk_ptr, rowptr, A->colidx, A->vals, X, W);
     return LZ_OK;
 }
 
@@ -400,9 +400,9 @@ __global__ void __launch_bounds__(256) k_cm_to_rm(int64_t n, int bw, const doubl
     }
 }
 
-static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, double *W, const double *Q0, const double *Bm)
+static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n, int bw, const double *X, double *W,
+                       const double *Q0, const double *Bm)
 {
-    const int64_t n = A->n_rows;
     const bool fuse = Q0 != nullptr;
     lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 4.0 * (double)n + 16.0 * (double)n * bw + (fuse ? 8.0 * (double)n * bw : 0.0));
     if (A->format == LZ_FMT_ELL4) {
@@ -420,26 +420,54 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
         const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
         const bool ws = A->tma_ok && A->cap == 2048 && ctx->spmv_variant != 9 && !fuse && ((uintptr_t)X % 32 == 0) && ((uintptr_t)W % 32 == 0);
         if (ws && (bw == 8 || bw == 16 || bw == 32)) {
-            if (bw == 8) LZ_TRY(launch_spmm_ws<8>(ctx, A, X, W));
-            else if (bw == 16) LZ_TRY(launch_spmm_ws<16>(ctx, A, X, W));
-            else LZ_TRY(launch_spmm_ws<32>(ctx, A, X, W));
+            if (bw == 8) LZ_TRY(launch_spmm_ws<8>(ctx, A, rowptr, n, X, W));
+            else if (bw == 16) LZ_TRY(launch_spmm_ws<16>(ctx, A, rowptr, n, X, W));
+            else LZ_TRY(launch_spmm_ws<32>(ctx, A, rowptr, n, X, W));
             LZ_LAUNCH_CHECK(ctx);
             lz_prof_end(ctx);
             return LZ_OK;
         }
 #define CSR_CASE(B)                                                                                                     \
-    if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, A->rowptr, A->colidx, A->vals, X, W, Q0, Bm); \
-    else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, A->rowptr, A->colidx, A->vals, X, W, Q0, Bm)
+    if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->colidx, A->vals, X, W, Q0, Bm); \
+    else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->colidx, A->vals, X, W, Q0, Bm)
         if (bw == 4) { CSR_CASE(4); } else if (bw == 8) { CSR_CASE(8); } else if (bw == 16) { CSR_CASE(16); }
         else if (bw == 32) { CSR_CASE(32); }
         else {
-            if (fuse) k_spmm_rm_any<true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, A->rowptr, A->colidx, A->vals, X, W, Q0, Bm);
-            else k_spmm_rm_any<false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, A->rowptr, A->colidx, A->vals, X, W, Q0, Bm);
+            if (fuse) k_spmm_rm_any<true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->colidx, A->vals, X, W, Q0, Bm);
+            else k_spmm_rm_any<false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->colidx, A->vals, X, W, Q0, Bm);
         }
 #undef CSR_CASE
     }
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
+    return LZ_OK;
+}
+
+// W[r,:] = sum of the partial rows of r's virtual pieces (row-split operators)
+__global__ void __launch_bounds__(256)
+k_split_combine_rows(int64_t n_rows, int bw, const int32_t *__restrict__ vstart, const double *__restrict__ Wbar, double *__restrict__ W)
+{
+    const int64_t total = n_rows * bw, stride = (int64_t)gridDim.x * 256;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) {
+        const int64_t r = e / bw;
+        const int c = (int)(e - r * bw);
+        const int v0 = vstart[r], v1 = vstart[r + 1];
+        double t = Wbar[(int64_t)v0 * bw + c];
+        for (int v = v0 + 1; v < v1; ++v) t += Wbar[(int64_t)v * bw + c];
+        W[e] = t;
+    }
+}
+
+static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, double *W, const double *Q0, const double *Bm)
+{
+    if (!A->vrowptr) return spmm_rm_rows(ctx, A, A->rowptr, A->n_rows, bw, X, W, Q0, Bm);
+    // row-split operator: partial rows per virtual row, then an ordered combine
+    LZ_CHECK(Q0 == nullptr, LZ_ERR_UNSUPPORTED, "fused subtraction is not available on a row-split operator");
+    void *wbar;
+    LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)A->n_virtual * bw + 64, &wbar));
+    LZ_TRY(spmm_rm_rows(ctx, A, A->vrowptr, A->n_virtual, bw, X, (double *)wbar, nullptr, nullptr));
+    k_split_combine_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A->n_rows, bw, A->vstart, (const double *)wbar, W);
+    LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
 

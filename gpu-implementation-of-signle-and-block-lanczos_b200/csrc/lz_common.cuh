@@ -107,6 +107,7 @@ enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
 // row-aligned nnz chunks: chunk c covers rows [chunk_row[c], chunk_row[c+1])
 #define LZ_SPMV_THREADS 256
 #define LZ_SPMV_TILE 1536        // target nnz per chunk (default; see profiles/ for the sweep)
+#define LZ_SPLIT_L 256           // rows longer than this are split into virtual rows
 #define LZ_SPMV_CAP 4096         // shared-memory product slots per CTA (32 KB)
 
 struct lz_matrix {
@@ -125,6 +126,12 @@ struct lz_matrix {
     int tile, cap;           // nnz per chunk (target) and shared-memory product slots per CTA
     int tma_ok;              // vals / colidx 16-byte aligned: bulk-copy staged kernel usable
     int max_row_nnz;
+    // row-split view for operators with long rows (NULL otherwise): virtual row pointers over the same
+    // colidx/vals, first virtual row of every real row, and the per-virtual-row partial sums
+    int64_t n_virtual;
+    int32_t *vrowptr;        // n_virtual + 1
+    int32_t *vstart;         // n_rows + 1
+    double *ybar;            // n_virtual
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
     int64_t halo_lo, halo_hi;        // halo entries below / above the local range
     int64_t global_rows, row_begin;  // position in the global operator

@@ -3,6 +3,8 @@
 // SpMM kernels, and the on-device generators of BASELINE.json's synthetic operators.
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include "lz_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -34,11 +36,66 @@ __global__ void k_max_row(int64_t n_rows, const int32_t *__restrict__ rowptr, in
     if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
 }
 
+// pieces per row, then virtual row pointers (row r's k-th piece starts at rowptr[r] + k*LZ_SPLIT_L)
+__global__ void k_split_count(int64_t n_rows, const int32_t *__restrict__ rowptr, int32_t *__restrict__ pieces)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    if (r == n_rows) { pieces[r] = 0; return; }
+    const int len = rowptr[r + 1] - rowptr[r];
+    pieces[r] = len <= LZ_SPLIT_L ? 1 : (len + LZ_SPLIT_L - 1) / LZ_SPLIT_L;
+}
+__global__ void k_split_fill(int64_t n_rows, int64_t nnz, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ vstart,
+                             int32_t *__restrict__ vrowptr)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    if (r == n_rows) { vrowptr[vstart[n_rows]] = (int32_t)nnz; return; }
+    const int v0 = vstart[r], v1 = vstart[r + 1], s = rowptr[r];
+    for (int v = v0; v < v1; ++v) vrowptr[v] = s + (v - v0) * LZ_SPLIT_L;
+}
+
+static int build_split(lz_ctx *ctx, lz_matrix *A)
+{
+    const int64_t n = A->n_rows;
+    int32_t *pieces;
+    LZ_CUDA(cudaMalloc(&pieces, sizeof(int32_t) * (n + 1)));
+    LZ_CUDA(cudaMalloc(&A->vstart, sizeof(int32_t) * (n + 1)));
+    k_split_count<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->rowptr, pieces);
+    LZ_LAUNCH_CHECK(ctx);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pieces, A->vstart, (int)(n + 1), ctx->stream);
+    void *tmp;
+    LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pieces, A->vstart, (int)(n + 1), ctx->stream);
+    ctx->launches++;
+    int32_t nv = 0;
+    LZ_CUDA(cudaMemcpyAsync(&nv, A->vstart + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    LZ_CUDA(cudaFree(tmp));
+    LZ_CUDA(cudaFree(pieces));
+    A->n_virtual = nv;
+    LZ_CUDA(cudaMalloc(&A->vrowptr, sizeof(int32_t) * ((size_t)nv + 8)));
+    LZ_CUDA(cudaMalloc(&A->ybar, sizeof(double) * ((size_t)nv + 8)));
+    k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->nnz, A->rowptr, A->vstart, A->vrowptr);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
 static int build_schedule(lz_ctx *ctx, lz_matrix *A)
 {
     A->tile = ctx->spmv_tile > 0 ? ctx->spmv_tile : LZ_SPMV_TILE;
     A->cap = A->tile <= 1536 ? 2048 : 4096;
     if (ctx->spmv_variant == 1 || ctx->spmv_variant == 5 || ctx->spmv_variant == 6) { A->tile = 1536; A->cap = 1792; }     // dev-time sweep knobs
+    int *d_max = ctx->flags + 8;
+    LZ_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
+    k_max_row<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->rowptr, d_max);
+    LZ_LAUNCH_CHECK(ctx);
+    LZ_CUDA(cudaMemcpyAsync(&A->max_row_nnz, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (A->max_row_nnz > A->cap - A->tile && !getenv("LZ_NO_SPLIT")) LZ_TRY(build_split(ctx, A));   // a long row would push chunks off the streaming path
+    const int32_t *rp = A->vrowptr ? A->vrowptr : A->rowptr;
+    const int64_t rows = A->vrowptr ? A->n_virtual : A->n_rows;
     int64_t nch = (A->nnz + A->tile - 1) / A->tile;
     if (nch < 1) nch = 1;
     LZ_CHECK(nch * 2 <= LZ_PARTIALS_CAP, LZ_ERR_UNSUPPORTED, "matrix too large for the reduction scratch (%lld chunks)", (long long)nch);
@@ -46,13 +103,8 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     LZ_CUDA(cudaMalloc(&A->chunk_row, sizeof(int32_t) * (nch + 1)));
     LZ_CUDA(cudaMalloc(&A->chunk_ptr, sizeof(int32_t) * (nch + 1)));
     A->tma_ok = ((uintptr_t)A->vals % 16 == 0) && ((uintptr_t)A->colidx % 16 == 0);
-    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->nnz, A->rowptr, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
+    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, A->nnz, rp, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
-    int *d_max = ctx->flags + 8;
-    LZ_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
-    k_max_row<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->rowptr, d_max);
-    LZ_LAUNCH_CHECK(ctx);
-    LZ_CUDA(cudaMemcpyAsync(&A->max_row_nnz, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     return LZ_OK;
 }
@@ -386,6 +438,9 @@ int lz_matrix_destroy(lz_matrix *A)
     }
     cudaFree(A->chunk_row);
     cudaFree(A->chunk_ptr);
+    cudaFree(A->vrowptr);
+    cudaFree(A->vstart);
+    cudaFree(A->ybar);
     delete A;
     return LZ_OK;
 }

@@ -16,7 +16,7 @@
 #pragma once
 #include "lz_common.cuh"
 
-enum { LZ_EPI_PLAIN = 0, LZ_EPI_LANCZOS = 1 };
+enum { LZ_EPI_PLAIN = 0, LZ_EPI_LANCZOS = 1, LZ_EPI_SCALED = 2 };   // SCALED: gather scaling of LANCZOS, plain store
 
 // Arguments of the fused Lanczos epilogue (pass A of step j):
 //   q_j[i]  = x_own[i] * invb[j]                 (lazy normalisation: the same product the reference
@@ -52,13 +52,14 @@ struct LzRowEpi {
     {
         sx = 1.0; sprev = 0.0; beta = 0.0;
         x_own = args.x_own; u_prev = args.u_prev; vcol = args.vcol; qout = args.qout; lc = args.lc; first = args.first != 0;
+        if (MODE == LZ_EPI_SCALED) sx = args.invb[args.j];
         if (MODE == LZ_EPI_LANCZOS) {
             sx = args.invb[args.j];
             if (!first) { sprev = args.invb[args.j - 1]; beta = args.beta[args.j]; }
         }
     }
     // scale applied to every gathered x value
-    __device__ __forceinline__ double xs(double xv) const { return MODE == LZ_EPI_LANCZOS ? __dmul_rn(xv, sx) : xv; }
+    __device__ __forceinline__ double xs(double xv) const { return MODE != LZ_EPI_PLAIN ? __dmul_rn(xv, sx) : xv; }
     // epilogue operands of row i (fetched early by the pipelined kernels)
     __device__ __forceinline__ void load(int64_t i, double &xo, double &up) const
     {
@@ -71,7 +72,7 @@ struct LzRowEpi {
     // finish row i whose raw sum is t; returns the row's contribution to alpha
     __device__ __forceinline__ double finish(int64_t i, double t, double *__restrict__ y, double xo, double up) const
     {
-        if (MODE == LZ_EPI_PLAIN) { y[i] = t; return 0.0; }
+        if (MODE != LZ_EPI_LANCZOS) { y[i] = t; return 0.0; }
         const double qi = __dmul_rn(xo, sx);
         double w = t;
         if (!first) w = __dadd_rn(t, __dmul_rn(-beta, __dmul_rn(up, sprev)));
@@ -377,7 +378,7 @@ static inline int lz_launch_tma_variant(lz_ctx *ctx, const lz_matrix *A, const d
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > A->n_chunks) grid = A->n_chunks;
     k_csr_spmv_tma<MODE, THREADS, STAGES, CAP><<<grid, THREADS, smem, ctx->stream>>>(
-        A->n_chunks, A->chunk_row, A->chunk_ptr, A->rowptr, A->colidx, A->vals, x, y, args);
+        A->n_chunks, A->chunk_row, A->chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
     return LZ_OK;
 }
 
@@ -571,7 +572,7 @@ static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const do
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > A->n_chunks) grid = A->n_chunks;
     k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
-        A->n_chunks, A->chunk_row, A->chunk_ptr, A->rowptr, A->colidx, A->vals, x, y, args);
+        A->n_chunks, A->chunk_row, A->chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
     return LZ_OK;
 }
 
@@ -621,8 +622,55 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
             LZ_TRY((lz_launch_tma_variant<MODE, 1024, 2, 4096>(ctx, A, x, y, args, 2)));
         }
     } else {
-        k_csr_spmv<MODE><<<A->n_chunks, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->chunk_row, A->rowptr, A->colidx, A->vals, x, y, args);
+        k_csr_spmv<MODE><<<A->n_chunks, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->chunk_row, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
     }
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Row-split operators (power-law graphs): rows longer than LZ_SPLIT_L are cut into virtual rows of at
+// most LZ_SPLIT_L entries (same colidx/vals arrays, finer row pointers), so every chunk of the
+// schedule takes the streaming path and a 400k-entry hub row is spread over hundreds of CTAs.
+// The kernels above then produce one partial sum per virtual row; this kernel adds the pieces of each
+// real row in order (deterministic) and runs the epilogue.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_split_combine(int64_t n_rows, const int32_t *__restrict__ vstart, const double *__restrict__ ybar, double *__restrict__ y,
+                const LzPassA args)
+{
+    __shared__ double red[32];
+    const LzRowEpi<MODE> epi(args);
+    double acc = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n_rows; r += stride) {
+        const int v0 = vstart[r], v1 = vstart[r + 1];
+        double t = ybar[v0];
+        for (int v = v0 + 1; v < v1; ++v) t += ybar[v];
+        acc += epi.finish(r, t, y);
+    }
+    if (MODE == LZ_EPI_LANCZOS) {
+        acc = lz_block_sum<256>(acc, red);
+        double total;
+        if (lz_grid_sum<256, 1>(&acc, args.partials, args.ticket, red, &total)) {
+            if (threadIdx.x == 0) {
+                *args.alpha_partial = total;
+                if (args.alpha_out) *args.alpha_out = total;
+            }
+        }
+    }
+}
+
+template <int MODE>
+static inline int lz_spmv_any(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args)
+{
+    if (!A->vrowptr) return lz_launch_spmv<MODE>(ctx, A, x, y, args);
+    if (MODE == LZ_EPI_LANCZOS) LZ_TRY(lz_launch_spmv<LZ_EPI_SCALED>(ctx, A, x, A->ybar, args));
+    else LZ_TRY(lz_launch_spmv<LZ_EPI_PLAIN>(ctx, A, x, A->ybar, args));
+    int64_t want = (A->n_rows + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
+    k_split_combine<MODE><<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(A->n_rows, A->vstart, A->ybar, y, args);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }

@@ -387,7 +387,7 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         pa.lc = lc; pa.j = j; pa.first = (j == 0);
         pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
         lz_prof_begin(ctx, LZ_K_SPMV, 12.0 * (double)A->nnz + 28.0 * (double)n + (reorth ? 8.0 * (double)n : 0.0));
-        LZ_TRY(lz_launch_spmv<LZ_EPI_LANCZOS>(ctx, A, u_cur - hlo, w, pa));    // :51,:54,:57
+        LZ_TRY(lz_spmv_any<LZ_EPI_LANCZOS>(ctx, A, u_cur - hlo, w, pa));    // :51,:54,:57
         lz_prof_end(ctx);
         if (sharded) {
             LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_ALPHA_LOCAL, 1));
@@ -423,7 +423,7 @@ int lz_spmv(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y)
     LZ_CHECK(x != y, LZ_ERR_INVALID, "lz_spmv: x and y must not alias");
     LzPassA none;
     memset(&none, 0, sizeof(none));
-    return lz_launch_spmv<LZ_EPI_PLAIN>(ctx, A, x, y, none);
+    return lz_spmv_any<LZ_EPI_PLAIN>(ctx, A, x, y, none);
 }
 
 int lz_dot(lz_ctx *ctx, int64_t n, const double *x, const double *y, double *result_host)
