@@ -474,11 +474,6 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
 // basis block j (row-major) -> stored basis; block CGS sweep over the stored blocks
 __global__ void k_flag_init(int *flags) { flags[0] = 0x7fffffff; flags[2] = 0x7fffffff; }
 
-static int block_cgs_sweep(lz_ctx *ctx, int64_t n, int bw, int nblocks, const double *V, double *W, double *C)
-{
-    return lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)n * bw, W, C);
-}
-
 extern "C" {
 
 int lz_spmm(lz_ctx *ctx, const lz_matrix *A, int b, const double *X, int64_t ldx, double *Y, int64_t ldy)
@@ -501,39 +496,57 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
     LZ_CHECK(ctx && A && B && alpha && beta && m >= 1, LZ_ERR_INVALID, "lz_block_lanczos: bad arguments");
     LZ_CHECK(bw >= 1 && bw <= 32, LZ_ERR_INVALID, "lz_block_lanczos: block width %d outside 1..32", bw);
     const int64_t n = A->n_rows;
-    LZ_CHECK(A->n_cols == n && ldb >= n, LZ_ERR_INVALID, "lz_block_lanczos: operator must be square and ldb >= n");
-    LZ_CHECK(lc >= 0 && lc < n, LZ_ERR_INVALID, "lz_block_lanczos: lc out of range");
+    // with a communicator attached (lz_comm_init) A is this rank's row slab, B holds the local rows, the
+    // panels carry [lower halo | local | upper halo] rows and every Gram matrix is all-reduced
+    const bool sharded = ctx->comm != nullptr && lz_comm_world(ctx) > 1;
+    const int64_t hlo = A->halo_lo, hhi = A->halo_hi;
+    LZ_CHECK(A->n_cols == n + hlo + hhi && ldb >= n, LZ_ERR_INVALID, "lz_block_lanczos: operator must be square and ldb >= n");
+    LZ_CHECK(sharded || (hlo == 0 && hhi == 0), LZ_ERR_INVALID, "lz_block_lanczos: a sharded operator needs lz_comm_init");
+    LZ_CHECK(lc >= -1 && lc < n, LZ_ERR_INVALID, "lz_block_lanczos: lc out of range");
     LZ_CHECK(reorth == LZ_REORTH_NONE || reorth == LZ_REORTH_FULL, LZ_ERR_INVALID, "lz_block_lanczos: reorth mode %d", reorth);
     LZ_CUDA(cudaSetDevice(ctx->device));
     const size_t pan = (size_t)n * bw, bb = (size_t)bw * bw;
-    size_t work_bytes = sizeof(double) * (3 * pan + (reorth ? bb * m : 0) + 64);
+    const size_t pstride = (size_t)(hlo + n + hhi) * bw;                     // one panel incl. halo rows (multiple of bw doubles)
+    size_t work_bytes = sizeof(double) * (3 * pstride + (reorth ? 2 * bb * m : 0) + 64);
     void *work;
     LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
-    double *Q0 = (double *)work, *Q1 = Q0 + pan, *W = Q1 + pan, *C = W + pan;
+    double *Q0 = (double *)work + (size_t)hlo * bw, *Q1 = Q0 + pstride, *W = Q1 + pstride, *C = (double *)work + 3 * pstride;
     double *V = nullptr;
     if (reorth) LZ_TRY(lz_ctx_basis(ctx, (int64_t)pan, m, &V));     // block j at V + j*pan, row-major
     double *binv = beta + bb * m;                                         // beta[m]: scratch inverse (block_lanczos.hpp:111)
     int *flag = ctx->flags + 2;
     k_flag_init<<<1, 1, 0, ctx->stream>>>(ctx->flags);
     LZ_LAUNCH_CHECK(ctx);
+    auto reduce_small = [&](double *M) -> int { return sharded ? lz_comm_allreduce_sum(ctx, M, bb) : LZ_OK; };
+    auto halo = [&](double *Q) -> int {
+        return sharded ? lz_comm_halo_exchange(ctx, Q, (int64_t)pan, hlo * bw, hhi * bw) : LZ_OK;
+    };
+    auto cgs2 = [&](int nblocks) -> int {
+        for (int sweep = 0; sweep < 2; ++sweep) LZ_TRY(lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)pan, W, C, sharded));
+        return LZ_OK;
+    };
+    const bool qrow = q != nullptr && lc >= 0;
 
     // W <- B in row-major; beta[0] = (B^T B)^{1/2}; Q0 = B beta[0]^{-1}                     (:106-114)
     k_cm_to_rm<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, bw, B, ldb, W);
     LZ_LAUNCH_CHECK(ctx);
     LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, beta, 0));
+    LZ_TRY(reduce_small(beta));
     LZ_TRY(lz_sqrtm_launch(ctx, bw, beta, binv, flag));
     LZ_TRY(lz_panel(ctx, n, bw, true, W, 0, binv, 0.0, 1.0, Q0, 0, nullptr));
-    if (q) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q0, 0, q, 0));                        // :117
+    if (qrow) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q0, 0, q, 0));                     // :117
     if (V) LZ_CUDA(cudaMemcpyAsync(V, Q0, sizeof(double) * pan, cudaMemcpyDeviceToDevice, ctx->stream));
-    LZ_TRY(spmm_rm(ctx, A, bw, Q0, W, nullptr, nullptr));                                     // :121
+    LZ_TRY(halo(Q0));
+    LZ_TRY(spmm_rm(ctx, A, bw, Q0 - hlo * bw, W, nullptr, nullptr));                          // :121
     LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q0, 0, alpha, 1));                                 // :124
+    LZ_TRY(reduce_small(alpha));
     double *G = ctx->scalars + 4096;                                                          // W^T W of the updated W
     LZ_TRY(lz_panel(ctx, n, bw, true, Q0, 0, alpha, 1.0, -1.0, W, 0, reorth ? nullptr : G));  // :128 (+ :137 fused)
     if (reorth) {
-        LZ_TRY(block_cgs_sweep(ctx, n, bw, 1, V, W, C));
-        LZ_TRY(block_cgs_sweep(ctx, n, bw, 1, V, W, C));
+        LZ_TRY(cgs2(1));
         LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, G, 0));
     }
+    LZ_TRY(reduce_small(G));
     for (int j = 1; j < m; ++j) {                                                             // :132-166
         double *bj = beta + bb * j, *aj = alpha + bb * j;
         LZ_CUDA(cudaMemcpyAsync(bj, G, sizeof(double) * bb, cudaMemcpyDeviceToDevice, ctx->stream));   // :137
@@ -542,17 +555,19 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
         // W' = A Q1 (:149); alpha_j from W' (the reference forms it after subtracting Q0 beta_j, :152-155: the
         // two differ by sym(beta_j^T Q0^T Q1), i.e. by rounding, because consecutive blocks are orthogonal);
         // then ONE pass subtracts both Q0 beta_j and Q1 alpha_j and accumulates the next W^T W (:152,:159,:137)
-        LZ_TRY(spmm_rm(ctx, A, bw, Q1, W, nullptr, nullptr));
+        LZ_TRY(halo(Q1));
+        LZ_TRY(spmm_rm(ctx, A, bw, Q1 - hlo * bw, W, nullptr, nullptr));
         LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q1, 0, aj, 1));
+        LZ_TRY(reduce_small(aj));
         LZ_TRY(lz_panel2(ctx, n, bw, Q0, bj, Q1, aj, W, reorth ? nullptr : G));
         double *t = Q0; Q0 = Q1; Q1 = t;                                                      // :162 (no copy)
-        if (q) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q0, 0, q, (int64_t)j * bw));      // :165
+        if (qrow) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q0, 0, q, (int64_t)j * bw));   // :165
         if (V) {
             LZ_CUDA(cudaMemcpyAsync(V + pan * j, Q0, sizeof(double) * pan, cudaMemcpyDeviceToDevice, ctx->stream));
-            LZ_TRY(block_cgs_sweep(ctx, n, bw, j + 1, V, W, C));
-            LZ_TRY(block_cgs_sweep(ctx, n, bw, j + 1, V, W, C));
+            LZ_TRY(cgs2(j + 1));
             LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, G, 0));
         }
+        LZ_TRY(reduce_small(G));
     }
     return LZ_OK;
 }

@@ -107,7 +107,7 @@ int lz_panel2(lz_ctx *ctx, int64_t n, int bw, const double *T1, const double *S1
 
 // one classical block Gram-Schmidt sweep of W (row-major n x bw) against J stored row-major blocks
 template <int BW, int JB>
-static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int64_t pan, double *W, double *C)
+static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int64_t pan, double *W, double *C, bool sharded)
 {
     const int gx = ctx->sm_count * 2, batches = (J + JB - 1) / JB;
     const size_t bb = (size_t)BW * BW;
@@ -123,6 +123,10 @@ static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int6
     if constexpr (BW >= 16) k_block_project_reduce_w<BW, JB><<<J, 256, 0, ctx->stream>>>(J, gx, gpart, C, Cf);
     else k_block_project_reduce<JB><<<J, 256, 0, ctx->stream>>>(BW, J, gx, gpart, C);
     LZ_LAUNCH_CHECK(ctx);
+    if (sharded) {      // the coefficients of all ranks' row slabs add up (C and its fragment-ordered negative alike)
+        LZ_TRY(lz_comm_allreduce_sum(ctx, C, (size_t)J * bb));
+        if (BW >= 16) LZ_TRY(lz_comm_allreduce_sum(ctx, Cf, (size_t)J * bb));
+    }
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * BW * (J + 2));
     if constexpr (BW >= 16) k_block_update_w<BW><<<ugrid < 1 ? 1 : ugrid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, Cf, W);
     else k_block_update<BW><<<dense_grid(ctx, n), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, C, W);
@@ -131,14 +135,15 @@ static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int6
     return LZ_OK;
 }
 
-int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C)
+int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C, bool sharded)
 {
-    if (bw == 8) return block_cgs_launch<8, 8>(ctx, n, J, V, pan, W, C);
-    if (bw == 16) return block_cgs_launch<16, 4>(ctx, n, J, V, pan, W, C);
-    if (bw == 32) return block_cgs_launch<32, 2>(ctx, n, J, V, pan, W, C);
+    if (bw == 8) return block_cgs_launch<8, 8>(ctx, n, J, V, pan, W, C, sharded);
+    if (bw == 16) return block_cgs_launch<16, 4>(ctx, n, J, V, pan, W, C, sharded);
+    if (bw == 32) return block_cgs_launch<32, 2>(ctx, n, J, V, pan, W, C, sharded);
     // generic widths: block-by-block products (SIMT)
     const size_t bb = (size_t)bw * bw;
     for (int j = 0; j < J; ++j) LZ_TRY(lz_gram(ctx, n, bw, true, V + pan * j, 0, W, 0, C + bb * j, 0));
+    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, C, (size_t)J * bb));
     for (int j = 0; j < J; ++j) LZ_TRY(lz_panel(ctx, n, bw, true, V + pan * j, 0, C + bb * j, 1.0, -1.0, W, 0, nullptr));
     return LZ_OK;
 }

@@ -11,6 +11,6 @@ int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t l
 int lz_sqrtm_launch(lz_ctx *ctx, int b, double *S, double *Sinv, int *flag);
 int lz_copy_row_launch(lz_ctx *ctx, int64_t lc, int b, bool rm, const double *Q, int64_t ld, double *q, int64_t off);
 // one classical block Gram-Schmidt sweep: C_j = V_j^T W (j < J), W -= sum_j V_j C_j; V_j row-major, `pan` apart
-int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C);
+int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C, bool sharded = false);
 // W -= T1 S1 + T2 S2 (row-major panels), G_opt (device bw*bw) receives W_new^T W_new
 int lz_panel2(lz_ctx *ctx, int64_t n, int bw, const double *T1, const double *S1, const double *T2, const double *S2, double *W, double *G_opt);

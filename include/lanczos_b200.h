@@ -167,7 +167,9 @@ int lz_vector_basis(lz_ctx *ctx, const double **V, int64_t *ld, int *cols);
  *   beta   : device, (m+1) blocks; beta[0] = (B^T B)^{1/2}, beta[m] = last inverse square root
  *            (scratch slot exactly as the reference uses it, block_lanczos.hpp:111,142)
  *   q      : device, m*bw entries (row lc of every Q_j)
- * bw in {1..32}. */
+ * bw in {1..32}.  With a communicator attached (lz_comm_init) A is this rank's row slab, B its local rows
+ * (lc = -1, q = NULL): halo rows of the panels are exchanged before every SpMM and every b x b Gram matrix is
+ * all-reduced, so alpha/beta are identical on every rank. */
 int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t ldb, int bw, int m,
                      int64_t lc, int reorth, double *alpha, double *beta, double *q);
 

@@ -49,6 +49,24 @@ for kind, dims, m in (("lap3d", (24, 20, 16), 40), ("lap2d", (64, 48), 40)):
         assert ea < 1e-10 and eb < 1e-10, (kind, reorth, ea, eb)
         # every rank holds the same coefficients bit for bit
         t = al.clone(); dist.broadcast(t, 0); assert torch.equal(t, al)
+# block path, row-sharded: panels carry halo rows, every Gram matrix is all-reduced
+dims, bw, m = (24, 20, 16), 8, 10
+n = int(np.prod(dims)); gran = dims[0] * dims[1]
+A = lz.Matrix.laplacian3d_shard(ctx, *dims, world, rank); csr = orc.lap3d(*dims)
+lo, hi = C.c_int64(), C.c_int64()
+lz.check(lz.lib().lz_partition_rows(n, gran, world, rank, C.byref(lo), C.byref(hi)))
+Bfull = orc.start_block(n, bw)
+nl = hi.value - lo.value
+Bl = torch.from_numpy(np.ascontiguousarray(Bfull[lo.value:hi.value].T).reshape(-1)).cuda()      # local rows, column-major
+for reorth in (0, 1):
+    al = torch.zeros(m * bw * bw, dtype=torch.float64, device="cuda"); be = torch.zeros((m + 1) * bw * bw, dtype=torch.float64, device="cuda")
+    lz.check(lz.lib().lz_block_lanczos(ctx.h, A.h, Bl.data_ptr(), nl, bw, m, -1, reorth, al.data_ptr(), be.data_ptr(), None))
+    ctx.sync()
+    ref = orc.block_lanczos(csr, Bfull, m, reorth=reorth)
+    a = al.cpu().numpy().reshape(m, bw, bw).transpose(0, 2, 1); b = be.cpu().numpy().reshape(m + 1, bw, bw).transpose(0, 2, 1)
+    ea = max(np.max(np.abs(a[j] - ref["alpha"][j])) / np.max(np.abs(ref["alpha"][j])) for j in range(m))
+    eb = max(np.max(np.abs(b[j] - ref["beta"][j])) / np.max(np.abs(ref["beta"][j])) for j in range(m))
+    assert ea < 1e-10 and eb < 1e-10, ("block", reorth, ea, eb)
 print("rank %d ok" % rank)
 ctx.close()
 dist.destroy_process_group()
