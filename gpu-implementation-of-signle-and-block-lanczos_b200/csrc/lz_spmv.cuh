@@ -400,7 +400,7 @@ __global__ void __launch_bounds__((1 + GW + RW) * 32)
 k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
               const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-              const LzPassA args)
+              const LzPassA args, const int blocked)
 {
     constexpr int THREADS = (1 + GW + RW) * 32, GT = GW * 32, RT = RW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -418,18 +418,24 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int first = blockIdx.x, step = gridDim.x;
+    // chunk -> CTA map.  blocked: every CTA owns a contiguous range of chunks, so the x entries gathered for
+    // the +-1 / +-nx neighbours of a stencil row are this SM's own recent rows (L1 hits) and all CTAs move
+    // through their ranges in step (the +-nx*ny neighbours are a neighbouring CTA's rows: L2 hits).
+    // strided: chunk c, c + grid, ... (long rows are spread over the CTAs).
+    const int per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const int first = blocked ? blockIdx.x * per_cta : blockIdx.x, step = blocked ? 1 : gridDim.x;
+    const int last = blocked ? min(n_chunks, first + per_cta) : n_chunks;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             int p0 = 0, p1 = 0;
-            if (first < n_chunks) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
+            if (first < last) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
             int it = 0;
-            for (int c = first; c < n_chunks; c += step, ++it) {
+            for (int c = first; c < last; c += step, ++it) {
                 const int slot = it % STAGES;
                 const int cp0 = p0, cp1 = p1;
-                if (c + step < n_chunks) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
+                if (c + step < last) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
                 lz_mbar_wait(&freeb[slot], ((it / STAGES) & 1) ^ 1);
                 const int a0 = cp0 & ~3;
                 const int cnt4 = (cp1 - a0) & ~3;
@@ -444,12 +450,12 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
         // ------------------------------------------------------------------ gather warps
         const int gtid = tid - 32;
         int p0 = 0, p1 = 0;
-        if (first < n_chunks) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
+        if (first < last) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
         int it = 0;
-        for (int c = first; c < n_chunks; c += step, ++it) {
+        for (int c = first; c < last; c += step, ++it) {
             const int slot = it % STAGES;
             const int cp0 = p0, cp1 = p1;
-            if (c + step < n_chunks) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
+            if (c + step < last) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
             const int a0 = cp0 & ~3, cnt = cp1 - a0, cnt4 = cnt & ~3;
             double *vs = vals_s + (size_t)slot * CAP;
             const int *cs = cols_s + (size_t)slot * CAP;
@@ -481,12 +487,12 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
         // ------------------------------------------------------------------ row warps
         const int rtid = tid - 32 * (1 + GW), rwarp = rtid >> 5;
         int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
-        if (first < n_chunks) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
+        if (first < last) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
         int it = 0;
-        for (int c = first; c < n_chunks; c += step, ++it) {
+        for (int c = first; c < last; c += step, ++it) {
             const int slot = it % STAGES;
             const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
-            if (c + step < n_chunks) {
+            if (c + step < last) {
                 nr0 = chunk_row[c + step]; nr1 = chunk_row[c + step + 1];
                 np0 = chunk_ptr[c + step]; np1 = chunk_ptr[c + step + 1];
             }
@@ -561,7 +567,8 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
 }
 
 template <int MODE, int GW, int RW, int STAGES, int CAP>
-static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int ctas_per_sm)
+static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int ctas_per_sm,
+                                       int blocked = 0)
 {
     static bool attr_set = false;
     const size_t smem = (size_t)STAGES * CAP * 12 + 24 * STAGES;
@@ -572,7 +579,7 @@ static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const do
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > A->n_chunks) grid = A->n_chunks;
     k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
-        A->n_chunks, A->chunk_row, A->chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
+        A->n_chunks, A->chunk_row, A->chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked);
     return LZ_OK;
 }
 
@@ -610,10 +617,13 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
         // A->cap is fixed when the schedule is built (lz_csr.cu); variant = dev-time tuning knob
         // kernel shape per schedule (A->cap is fixed when the schedule is built, lz_csr.cu)
         const int v = ctx->spmv_variant;
+        const int blk = 0;                       // strided chunk map: blocked ranges measured slower (profiles/r01_spmv_variants.md)
         if (A->cap == 2048) {
-            if (v == 3) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 3)));
-            else if (v == 4) LZ_TRY((lz_launch_ws_variant<MODE, 5, 10, 3, 2048>(ctx, A, x, y, args, 3)));
-            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 3)));      // default (profiles/r01_spmv_variants.md)
+            if (v == 3) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 3, 0)));
+            else if (v == 4) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 2, 1)));
+            else if (v == 7) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 2, 1)));
+            else if (v == 8) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 3, 1)));
+            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 3, blk)));      // default (profiles/r01_spmv_variants.md)
         } else if (A->cap == 1792) {
             if (v == 5) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 4, 1792>(ctx, A, x, y, args, 2)));
             else if (v == 6) LZ_TRY((lz_launch_ws_variant<MODE, 10, 9, 5, 1792>(ctx, A, x, y, args, 2)));
