@@ -512,7 +512,7 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
     LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
     double *Q0 = (double *)work + (size_t)hlo * bw, *Q1 = Q0 + pstride, *W = Q1 + pstride, *C = (double *)work + 3 * pstride;
     double *V = nullptr;
-    if (reorth) LZ_TRY(lz_ctx_basis(ctx, (int64_t)pan, m, &V));     // block j at V + j*pan, row-major
+    if (reorth) LZ_TRY(lz_ctx_basis_blocks(ctx, (int64_t)pan, m, &V));     // block j at V + j*pan, row-major
     double *binv = beta + bb * m;                                         // beta[m]: scratch inverse (block_lanczos.hpp:111)
     int *flag = ctx->flags + 2;
     k_flag_init<<<1, 1, 0, ctx->stream>>>(ctx->flags);

@@ -68,7 +68,7 @@ struct lz_ctx {
     // Krylov basis slab kept by the full-reorth drivers
     double *basis;
     size_t basis_bytes;
-    int64_t basis_ld;
+    int64_t basis_ts, basis_cs, basis_rows;   // element (i,k) at basis[(i>>5)*ts + k*cs + (i&31)]
     int basis_cols;
     lz_comm *comm;
     // optional per-kernel-class timing (bench.py's roofline leg): CUDA events on ctx->stream
@@ -92,7 +92,8 @@ void lz_prof_end(lz_ctx *ctx);
 #define LZ_FLAGS 64
 
 int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out);   // grow-only scratch
-int lz_ctx_basis(lz_ctx *ctx, int64_t ld, int cols, double **out);
+int lz_ctx_basis(lz_ctx *ctx, int64_t rows, int cols, double **out);            // vector path: row-tiled slab
+int lz_ctx_basis_blocks(lz_ctx *ctx, int64_t pan, int blocks, double **out);  // block path: back-to-back panels
 int lz_ctx_scratch(lz_ctx *ctx, size_t bytes, void **out);
 // communicator hooks (lz_multi.cu); all enqueue on ctx->stream
 int lz_comm_world(const lz_ctx *ctx);

@@ -207,9 +207,9 @@ int lz_ctx_scratch(lz_ctx *ctx, size_t bytes, void **out)
     return LZ_OK;
 }
 
-int lz_ctx_basis(lz_ctx *ctx, int64_t ld, int cols, double **out)
+static int basis_alloc(lz_ctx *ctx, size_t bytes)
 {
-    size_t bytes = sizeof(double) * (size_t)ld * (size_t)cols;
+    bytes += 4096;
     if (bytes > ctx->basis_bytes) {
         LZ_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->basis) LZ_CUDA(cudaFree(ctx->basis));
@@ -218,8 +218,29 @@ int lz_ctx_basis(lz_ctx *ctx, int64_t ld, int cols, double **out)
         LZ_CUDA(cudaMalloc(&ctx->basis, bytes));
         ctx->basis_bytes = bytes;
     }
-    ctx->basis_ld = ld;
+    return LZ_OK;
+}
+
+// Krylov basis of the single-vector path, row-tiled: 32-row tiles, the `cols` columns of a tile back to
+// back, so element (i, k) sits at basis[(i >> 5) * ts + k * cs + (i & 31)] with cs = 32, ts = 32 * cols.
+// A tile's first K columns are one contiguous block (one bulk copy in the fused CGS kernel) and column
+// accesses of the streaming kernels stay 256-byte segments.
+int lz_ctx_basis(lz_ctx *ctx, int64_t rows, int cols, double **out)
+{
+    const int64_t tiles = (rows + 31) / 32;
+    LZ_TRY(basis_alloc(ctx, sizeof(double) * (size_t)tiles * 32 * (size_t)cols));
+    ctx->basis_cs = 32;
+    ctx->basis_ts = 32 * (int64_t)cols;
+    ctx->basis_rows = rows;
     ctx->basis_cols = cols;
+    *out = ctx->basis;
+    return LZ_OK;
+}
+
+int lz_ctx_basis_blocks(lz_ctx *ctx, int64_t pan, int blocks, double **out)
+{
+    LZ_TRY(basis_alloc(ctx, sizeof(double) * (size_t)pan * (size_t)blocks));
+    ctx->basis_cs = 0; ctx->basis_ts = 0; ctx->basis_rows = 0; ctx->basis_cols = 0;
     *out = ctx->basis;
     return LZ_OK;
 }

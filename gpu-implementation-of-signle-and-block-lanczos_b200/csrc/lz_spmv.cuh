@@ -30,7 +30,8 @@ struct LzPassA {
     const double *beta;     // beta[j]
     double *alpha_out;      // &alpha[j] (written by the last CTA) or NULL when the caller all-reduces
     double *alpha_partial;  // where the last CTA leaves the local sum (always)
-    double *vcol;           // basis column j to fill with q_j, or NULL
+    double *vcol;           // basis column j to fill with q_j (element i at vcol[(i >> 5) * vts + (i & 31)]), or NULL
+    int64_t vts;
     double *qout;           // &q[j]: receives q_j[lc] (copy_vector_element, copy_functions.hpp:116-133)
     int64_t lc;
     int j;
@@ -46,12 +47,12 @@ struct LzRowEpi {
     double sx, sprev, beta;
     const double *x_own, *u_prev;
     double *vcol, *qout;
-    int64_t lc;
+    int64_t lc, vts;
     bool first;
     __device__ __forceinline__ LzRowEpi(const LzPassA &args)
     {
         sx = 1.0; sprev = 0.0; beta = 0.0;
-        x_own = args.x_own; u_prev = args.u_prev; vcol = args.vcol; qout = args.qout; lc = args.lc; first = args.first != 0;
+        x_own = args.x_own; u_prev = args.u_prev; vcol = args.vcol; vts = args.vts; qout = args.qout; lc = args.lc; first = args.first != 0;
         if (MODE == LZ_EPI_SCALED) sx = args.invb[args.j];
         if (MODE == LZ_EPI_LANCZOS) {
             sx = args.invb[args.j];
@@ -77,7 +78,7 @@ struct LzRowEpi {
         double w = t;
         if (!first) w = __dadd_rn(t, __dmul_rn(-beta, __dmul_rn(up, sprev)));
         y[i] = w;
-        if (vcol) vcol[i] = qi;
+        if (vcol) vcol[(i >> 5) * vts + (i & 31)] = qi;
         if (i == lc && qout) *qout = qi;
         return __dmul_rn(w, qi);
     }

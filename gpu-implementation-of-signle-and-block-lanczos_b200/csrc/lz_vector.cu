@@ -6,6 +6,7 @@
 // methods/vector_lanczos.hpp:8-67.  Everything here keeps its scalars on the device: no
 // cudaMalloc, no D2H copy and no host synchronisation inside the iteration loop.
 #include <math.h>
+#include <stdlib.h>
 
 #include "lz_spmv.cuh"
 
@@ -139,7 +140,7 @@ static int launch_pass_b(lz_ctx *ctx, int64_t n, double *w, const double *u_cur,
 #define CGS_UNROLL 4
 
 __global__ void __launch_bounds__(VT)
-k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ld, const double *__restrict__ w,
+k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t cs, const double *__restrict__ w,
               double *__restrict__ cpart /* gridDim.x * K */, const int *__restrict__ flags, int need_flag)
 {
     extern __shared__ double csm[];           // [VT/32][K] per-warp partial coefficients
@@ -153,6 +154,8 @@ k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ld, const 
         const int64_t base = tile * CGS_TILE + (int64_t)warp * (32 * V_ROWS_PER_THREAD) + lane * 4;
         // rows base..base+3 and base+128..base+131 of this warp's 256-row slice
         const int64_t ra = base, rb = base + 128;
+        // element (i, k) of the basis lives at V[(i >> 5) * ts + k * cs + (i & 31)]  (see lz_ctx_basis)
+        const double *pa = V + (ra >> 5) * ts + (ra & 31), *pb = V + (rb >> 5) * ts + (rb & 31);
         double wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
         const bool fa = ra + 3 < n, fb = rb + 3 < n;
         if (fa) lz_ld256(w + ra, wa[0], wa[1], wa[2], wa[3]);
@@ -165,9 +168,9 @@ k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ld, const 
                 double va[CGS_UNROLL][4], vb[CGS_UNROLL][4];
 #pragma unroll
                 for (int u = 0; u < CGS_UNROLL; ++u) {
-                    const double *col = V + (int64_t)(k + u) * ld;
-                    lz_ld256_stream(col + ra, va[u][0], va[u][1], va[u][2], va[u][3]);
-                    lz_ld256_stream(col + rb, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
+                    const int64_t ko = (int64_t)(k + u) * cs;
+                    lz_ld256_stream(pa + ko, va[u][0], va[u][1], va[u][2], va[u][3]);
+                    lz_ld256_stream(pb + ko, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
                 }
 #pragma unroll
                 for (int u = 0; u < CGS_UNROLL; ++u) {
@@ -181,11 +184,11 @@ k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ld, const 
             }
         }
         for (; k < K; ++k) {
-            const double *col = V + (int64_t)k * ld;
+            const int64_t ko = (int64_t)k * cs;
             double s = 0.0;
             for (int t = 0; t < 4; ++t) {
-                if (ra + t < n) s = fma(col[ra + t], wa[t], s);
-                if (rb + t < n) s = fma(col[rb + t], wb[t], s);
+                if (ra + t < n) s = fma(pa[ko + t], wa[t], s);
+                if (rb + t < n) s = fma(pb[ko + t], wb[t], s);
             }
             s = lz_warp_sum(s);
             if (lane == 0) mine[k] += s;
@@ -198,6 +201,104 @@ k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ld, const 
         for (int wv = 0; wv < VT / 32; ++wv) s += csm[(size_t)wv * K + k];
         cpart[(size_t)blockIdx.x * K + k] = s;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused sweep-1 update + sweep-2 projection of CGS2:  w' = w - V c1 ;  c2_partial = V^T w'.
+// The two separate kernels stream the basis twice; here a CTA takes 32-row tiles -- one tile of the
+// row-tiled basis is K*256 contiguous bytes, i.e. ONE bulk async copy -- into a double-buffered
+// shared-memory tile (the next tile lands while this one is used), finishes w' for the tile's rows
+// and immediately accumulates the second projection from the same buffer.  CGS2 then reads the basis
+// three times per step instead of four.
+// Phase 1: thread = (row, column group); phase 2: thread = column with a lane-skewed row order (32
+// lanes on 32 banks although their columns are 32 doubles apart), register accumulators over all tiles.
+// (A chunked ring with a producer warp and a deeper tile ring were measured slower: profiles/.)
+// ---------------------------------------------------------------------------------------------
+#define CF_R 32                 // rows per tile (= the basis layout's tile height)
+#define CF_THREADS 256
+#define CF_MAXC 2               // columns per thread: K <= CF_MAXC * CF_THREADS
+
+__global__ void __launch_bounds__(CF_THREADS)
+k_cgs_update_project(int64_t n, int K, const double *__restrict__ V, int64_t ts, double *__restrict__ w,
+                     const double *__restrict__ c1, double *__restrict__ cpart2 /* gridDim.x * K */)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *vt = reinterpret_cast<double *>(smem_raw);                          // [2][K][CF_R]
+    double *wt = vt + 2 * (size_t)K * CF_R;                                     // [2][CF_R]
+    double *red = wt + 2 * CF_R;                                                // [CF_THREADS/CF_R][CF_R]
+    double *c1s = red + CF_THREADS;                                             // [K]
+    uint64_t *full = reinterpret_cast<uint64_t *>(c1s + ((K + 1) & ~1));        // [2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < K; k += CF_THREADS) c1s[k] = c1[k];
+    if (tid == 0) {
+        lz_mbar_init(&full[0], 1); lz_mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t n_tiles = (n + CF_R - 1) / CF_R;
+    auto issue = [&](int64_t tile, int buf) {        // lane 0 of warp 0: the tile's K columns are one contiguous block
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            lz_mbar_expect_tx(&full[buf], (uint32_t)((K + 1) * CF_R * 8));
+            lz_bulk_g2s(vt + (size_t)buf * K * CF_R, V + tile * ts, (uint32_t)K * CF_R * 8, &full[buf]);
+            lz_bulk_g2s(wt + buf * CF_R, w + tile * CF_R, CF_R * 8, &full[buf]);
+        }
+    };
+    double acc[CF_MAXC];
+#pragma unroll
+    for (int u = 0; u < CF_MAXC; ++u) acc[u] = 0.0;
+    const int r = tid % CF_R, g = tid / CF_R;          // phase-1 role: row r, column group g of CF_THREADS/CF_R
+    if (warp == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (warp == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);
+        lz_mbar_wait(&full[buf], (it >> 1) & 1);
+        const double *tv = vt + (size_t)buf * K * CF_R;
+        double *tw = wt + buf * CF_R;
+        const int rows_valid = (int)min((int64_t)CF_R, n - tile * CF_R);
+        // phase 1: partial V c1 over this group's columns, then the row's new value
+        double s = 0.0;
+        for (int k = g; k < K; k += CF_THREADS / CF_R) s = fma(c1s[k], tv[(size_t)k * CF_R + r], s);
+        red[g * CF_R + r] = s;
+        __syncthreads();
+        if (tid < CF_R) {
+            double t = tw[tid];
+#pragma unroll
+            for (int gg = 0; gg < CF_THREADS / CF_R; ++gg) t -= red[gg * CF_R + tid];
+            if (tid >= rows_valid) t = 0.0;            // rows past n: whatever the copy brought in is ignored
+            tw[tid] = t;
+            if (tid < rows_valid) w[tile * CF_R + tid] = t;
+        }
+        __syncthreads();
+        // phase 2: this thread's columns dotted with the new rows; lane-skewed row order keeps the
+        // 32 lanes of a warp on 32 different banks although their columns are CF_R doubles apart
+#pragma unroll
+        for (int u = 0; u < CF_MAXC; ++u) {
+            const int k = tid + u * CF_THREADS;
+            if (k < K) {
+                const double *col = tv + (size_t)k * CF_R;
+                double a = acc[u];
+#pragma unroll 8
+                for (int i = 0; i < CF_R; ++i) {
+                    const int rr = (i + lane) & (CF_R - 1);
+                    if (rr < rows_valid) a = fma(col[rr], tw[rr], a);
+                }
+                acc[u] = a;
+            }
+        }
+        __syncthreads();                               // the buffer may be refilled from here on
+    }
+#pragma unroll
+    for (int u = 0; u < CF_MAXC; ++u) {
+        const int k = tid + u * CF_THREADS;
+        if (k < K) cpart2[(size_t)blockIdx.x * K + k] = acc[u];
+    }
+}
+
+static inline size_t cgs_fused_smem(int K)
+{
+    return sizeof(double) * (2 * (size_t)K * CF_R + 2 * CF_R + CF_THREADS + ((K + 1) & ~1)) + 16;
 }
 
 // c[k] = sum over CTAs of cpart[cta][k]  (fixed order); optionally all K in one small launch
@@ -215,7 +316,7 @@ k_cgs_reduce(int K, int n_parts, const double *__restrict__ cpart, double *__res
 }
 
 __global__ void __launch_bounds__(VT)
-k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ld, double *__restrict__ w,
+k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t cs, double *__restrict__ w,
              const double *__restrict__ c, double *partials, unsigned int *ticket, const LzFinal fin,
              int *flags, int need_flag, int dgks_test, const double *nrm2_before)
 {
@@ -230,6 +331,8 @@ k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ld, double 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * CGS_TILE + (int64_t)warp * (32 * V_ROWS_PER_THREAD) + lane * 4;
         const int64_t ra = base, rb = base + 128;
+        // element (i, k) of the basis lives at V[(i >> 5) * ts + k * cs + (i & 31)]  (see lz_ctx_basis)
+        const double *pa = V + (ra >> 5) * ts + (ra & 31), *pb = V + (rb >> 5) * ts + (rb & 31);
         double wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
         const bool fa = ra + 3 < n, fb = rb + 3 < n;
         if (fa) lz_ld256(w + ra, wa[0], wa[1], wa[2], wa[3]);
@@ -242,9 +345,9 @@ k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ld, double 
                 double va[CGS_UNROLL][4], vb[CGS_UNROLL][4];
 #pragma unroll
                 for (int u = 0; u < CGS_UNROLL; ++u) {
-                    const double *col = V + (int64_t)(k + u) * ld;
-                    lz_ld256_stream(col + ra, va[u][0], va[u][1], va[u][2], va[u][3]);
-                    lz_ld256_stream(col + rb, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
+                    const int64_t ko = (int64_t)(k + u) * cs;
+                    lz_ld256_stream(pa + ko, va[u][0], va[u][1], va[u][2], va[u][3]);
+                    lz_ld256_stream(pb + ko, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
                 }
 #pragma unroll
                 for (int u = 0; u < CGS_UNROLL; ++u) {
@@ -255,11 +358,11 @@ k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ld, double 
             }
         }
         for (; k < K; ++k) {
-            const double *col = V + (int64_t)k * ld;
+            const int64_t ko = (int64_t)k * cs;
             const double ck = -csm[k];
             for (int t = 0; t < 4; ++t) {
-                if (ra + t < n) wa[t] = fma(ck, col[ra + t], wa[t]);
-                if (rb + t < n) wb[t] = fma(ck, col[rb + t], wb[t]);
+                if (ra + t < n) wa[t] = fma(ck, pa[ko + t], wa[t]);
+                if (rb + t < n) wb[t] = fma(ck, pb[ko + t], wb[t]);
             }
         }
         if (fa) lz_st256(w + ra, wa[0], wa[1], wa[2], wa[3]);
@@ -294,7 +397,7 @@ __global__ void k_finalize_first(const double *nrm2, double *beta, double *invb,
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct LzCgs {
-    double *V; int64_t ld; double *cpart; double *c; unsigned grid;
+    double *V; int64_t ts, cs; double *cpart; double *c; unsigned grid;      // basis element (i,k): V[(i>>5)*ts + k*cs + (i&31)]
 };
 
 // one CGS sweep of w against the first K basis columns; the update's epilogue finalises beta[jn]
@@ -303,7 +406,7 @@ static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, c
 {
     const size_t smem_p = sizeof(double) * (VT / 32) * (size_t)K;
     lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
-    k_cgs_project<<<g.grid, VT, smem_p, ctx->stream>>>(n, K, g.V, g.ld, w, g.cpart, ctx->flags, need_flag);
+    k_cgs_project<<<g.grid, VT, smem_p, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, need_flag);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)g.grid, g.cpart, g.c, ctx->flags, need_flag);
@@ -311,8 +414,50 @@ static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, c
     if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
     k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
-        n, K, g.V, g.ld, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test,
+        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test,
         ctx->scalars + S_NRM2_BEFORE);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    return LZ_OK;
+}
+
+// CGS2 with the middle two basis streams fused: project, [update + project], update.
+// Falls back to two plain sweeps when the tile does not fit in shared memory (large K) or the
+// operands are not 16-byte aligned for the bulk copies.
+static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, bool sharded)
+{
+    const size_t smem = cgs_fused_smem(K);
+    const bool ok = smem <= 220 * 1024 && K <= CF_MAXC * CF_THREADS && g.cs == CF_R && ((uintptr_t)w % 16 == 0) && !getenv("LZ_NO_CGS_FUSE");
+    if (!ok) {
+        LZ_TRY(cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded));
+        return cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        LZ_CUDA(cudaFuncSetAttribute(k_cgs_update_project, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    // sweep 1 projection
+    lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
+    k_cgs_project<<<g.grid, VT, sizeof(double) * (VT / 32) * (size_t)K, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, 0);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)g.grid, g.cpart, g.c, ctx->flags, 0);
+    LZ_LAUNCH_CHECK(ctx);
+    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
+    // sweep 1 update + sweep 2 projection, one basis stream
+    const unsigned fgrid = (unsigned)ctx->sm_count;
+    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
+    k_cgs_update_project<<<fgrid, CF_THREADS, smem, ctx->stream>>>(n, K, g.V, g.ts, w, g.c, g.cpart);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)fgrid, g.cpart, g.c, ctx->flags, 0);
+    LZ_LAUNCH_CHECK(ctx);
+    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
+    // sweep 2 update (+ ||w||^2, beta finalisation)
+    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
+    k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD,
+                                                                          fin, ctx->flags, 0, 0, ctx->scalars + S_NRM2_BEFORE);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     return LZ_OK;
@@ -348,7 +493,7 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
     // [pad | lower halo | local rows | upper halo] with the local part 32-byte aligned
     const int64_t off = round_up(hlo, 4);
     const int64_t stride = round_up(off + n + hhi, 4);
-    LzCgs g = {nullptr, ld, nullptr, nullptr, 0};
+    LzCgs g = {nullptr, 0, 0, nullptr, nullptr, 0};
     const unsigned cgs_grid = stream_grid(ctx, n, CGS_TILE) < (unsigned)(ctx->sm_count * 2)
                                   ? stream_grid(ctx, n, CGS_TILE) : (unsigned)(ctx->sm_count * 2);
     size_t work_bytes = sizeof(double) * (size_t)stride * 3;
@@ -362,7 +507,8 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         g.cpart = (double *)work + 3 * stride;
         g.c = g.cpart + (size_t)cgs_grid * m;
         g.grid = cgs_grid;
-        LZ_TRY(lz_ctx_basis(ctx, ld, m, &g.V));
+        LZ_TRY(lz_ctx_basis(ctx, n, m, &g.V));
+        g.ts = ctx->basis_ts; g.cs = ctx->basis_cs;
         static bool attr_set = false;
         if (!attr_set) {
             LZ_CUDA(cudaFuncSetAttribute(k_cgs_project, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -382,7 +528,8 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         LzPassA pa;
         pa.x_own = u_cur; pa.u_prev = u_prev; pa.invb = invb; pa.beta = beta;
         pa.alpha_out = sharded ? nullptr : alpha + j; pa.alpha_partial = sc + S_ALPHA_LOCAL;
-        pa.vcol = reorth ? g.V + (size_t)j * ld : nullptr;
+        pa.vcol = reorth ? g.V + (size_t)j * g.cs : nullptr;
+        pa.vts = g.ts;
         pa.qout = (q && lc >= 0) ? q + j : nullptr;
         pa.lc = lc; pa.j = j; pa.first = (j == 0);
         pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
@@ -400,8 +547,12 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         lz_prof_end(ctx);
         if (reorth) {
             LzFinal f2 = {beta, invb, sc + S_NRM2, ctx->flags, j + 1, sharded ? 0 : 1};
-            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, reorth == LZ_REORTH_FULL_DGKS, sharded));
-            LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, reorth == LZ_REORTH_FULL_DGKS, 0, sharded));
+            if (reorth == LZ_REORTH_FULL) {
+                LZ_TRY(cgs2_fused(ctx, g, n, j + 1, w, f2, sharded));
+            } else {
+                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, 1, sharded));
+                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 1, 0, sharded));
+            }
         }
         if (sharded) {
             LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_NRM2, 1));
@@ -413,6 +564,16 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
     k_copy_scalar<<<1, 1, 0, ctx->stream>>>(beta + m, sc + S_BETA_LAST);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
+}
+
+// columns j0 .. j0+ncols-1 of the stored basis -> column-major dst (leading dimension ldd)
+__global__ void k_basis_copy(int64_t n, int j0, int ncols, const double *__restrict__ V, int64_t ts, int64_t cs, double *__restrict__ dst, int64_t ldd)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * ncols) return;
+    const int64_t i = e % n;
+    const int c = (int)(e / n);
+    dst[i + (int64_t)c * ldd] = V[(i >> 5) * ts + (int64_t)(j0 + c) * cs + (i & 31)];
 }
 
 extern "C" {
@@ -504,11 +665,20 @@ int lz_vector_lanczos_sharded(lz_ctx *ctx, const lz_matrix *A_local, const doubl
     return LZ_OK;
 }
 
-int lz_vector_basis(lz_ctx *ctx, const double **V, int64_t *ld, int *cols)
+int lz_vector_basis_copy(lz_ctx *ctx, int j0, int ncols, double *dst, int64_t ldd)
 {
-    LZ_CHECK(ctx && ctx->basis, LZ_ERR_INVALID, "lz_vector_basis: no basis has been built on this context");
-    if (V) *V = ctx->basis;
-    if (ld) *ld = ctx->basis_ld;
+    LZ_CHECK(ctx && ctx->basis && dst, LZ_ERR_INVALID, "lz_vector_basis_copy: no basis has been built on this context");
+    LZ_CHECK(j0 >= 0 && ncols >= 1 && j0 + ncols <= ctx->basis_cols && ldd >= ctx->basis_rows, LZ_ERR_INVALID, "lz_vector_basis_copy: bad range");
+    const int64_t total = ctx->basis_rows * ncols;
+    k_basis_copy<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->basis_rows, j0, ncols, ctx->basis, ctx->basis_ts, ctx->basis_cs, dst, ldd);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_vector_basis_info(lz_ctx *ctx, int64_t *rows, int *cols)
+{
+    LZ_CHECK(ctx && ctx->basis, LZ_ERR_INVALID, "lz_vector_basis_info: no basis has been built on this context");
+    if (rows) *rows = ctx->basis_rows;
     if (cols) *cols = ctx->basis_cols;
     return LZ_OK;
 }

@@ -73,7 +73,8 @@ def lib():
         "lz_assemble_T": (i32, [vp, i32, i32, vp, vp, vp]),
         "lz_vector_lanczos": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp, P(i32)]),
         "lz_vector_lanczos_async": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp]),
-        "lz_vector_basis": (i32, [vp, P(vp), P(i64), P(i32)]),
+        "lz_vector_basis_info": (i32, [vp, P(i64), P(i32)]),
+        "lz_vector_basis_copy": (i32, [vp, i32, i32, vp, i64]),
         "lz_block_lanczos": (i32, [vp, vp, vp, i64, i32, i32, i64, i32, vp, vp, vp]),
         "lz_ritz": (i32, [i32, i32, vp, vp, vp, i32, vp, vp]),
         "lz_comm_unique_id": (i32, [vp]),

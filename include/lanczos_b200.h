@@ -158,8 +158,10 @@ int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, i
 /* same, but coefficients stay in DEVICE arrays and nothing synchronises (bench / graph use) */
 int lz_vector_lanczos_async(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc,
                             int reorth, double *alpha_dev, double *beta_dev, double *q);
-/* basis kept by the last full-reorth run: column j at V + j*ld (device, borrowed from ctx) */
-int lz_vector_basis(lz_ctx *ctx, const double **V, int64_t *ld, int *cols);
+/* Krylov basis kept by the last full-reorth run (stored row-tiled inside the context):
+ * copy columns j0 .. j0+ncols-1 into dst (device, column-major, leading dimension ldd >= rows) */
+int lz_vector_basis_info(lz_ctx *ctx, int64_t *rows, int *cols);
+int lz_vector_basis_copy(lz_ctx *ctx, int j0, int ncols, double *dst, int64_t ldd);
 
 /* block_lanczos_blas<double>  methods/block_lanczos.hpp:88-167 (and block_lanczos :13-80).
  *   B      : n x bw start block, column-major, leading dimension ldb (device), not modified

@@ -155,11 +155,13 @@ def test_vector_lanczos_full_reorth_vs_oracle(lz, ctx, orc, maxwell10, mode):
     assert ea < 1e-10 and eb < 1e-10, (ea, eb)
     # the stored basis is orthonormal to working precision
     import ctypes as C
-    V, ld, cols = C.c_void_p(), C.c_int64(), C.c_int()
-    lz.check(lz.lib().lz_vector_basis(ctx.h, C.byref(V), C.byref(ld), C.byref(cols)))
-    host = np.empty(ld.value * cols.value)
-    lz.check(lz.lib().lz_memcpy(ctx.h, host.ctypes.data, V, host.nbytes, lz.D2H))
-    Vh = host.reshape(cols.value, ld.value)[:, :maxwell10["n"]]
+    rows, cols = C.c_int64(), C.c_int()
+    lz.check(lz.lib().lz_vector_basis_info(ctx.h, C.byref(rows), C.byref(cols)))
+    assert rows.value == maxwell10["n"] and cols.value == 100
+    Vd = torch.empty(rows.value * cols.value, dtype=torch.float64, device="cuda")
+    lz.check(lz.lib().lz_vector_basis_copy(ctx.h, 0, cols.value, Vd.data_ptr(), rows.value))
+    ctx.sync()
+    Vh = Vd.cpu().numpy().reshape(cols.value, rows.value)
     assert np.max(np.abs(Vh @ Vh.T - np.eye(100))) < 1e-12
 
 
