@@ -396,6 +396,9 @@ __global__ void k_finalize_first(const double *nrm2, double *beta, double *invb,
 // ---------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+struct LzCgs;
+static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, int need_flag, int dgks_test);
+
 struct LzCgs {
     double *V; int64_t ts, cs; double *cpart; double *c; unsigned grid;      // basis element (i,k): V[(i>>5)*ts + k*cs + (i&31)]
 };
@@ -413,11 +416,18 @@ static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, c
     LZ_LAUNCH_CHECK(ctx);
     if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
-    k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
-        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test,
-        ctx->scalars + S_NRM2_BEFORE);
-    LZ_LAUNCH_CHECK(ctx);
+    LZ_TRY(launch_cgs_update(ctx, g, n, K, w, fin, need_flag, dgks_test));
     lz_prof_end(ctx);
+    return LZ_OK;
+}
+
+static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, int need_flag, int dgks_test)
+{
+    // (a variant that gave each warp one tile and four adjacent columns per load -- fully contiguous 1 KB
+    // reads of the tiled slab -- measured 4 % slower than this generic kernel: profiles/r01_cgs_fusion.md)
+    k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
+        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE);
+    LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
 
@@ -456,9 +466,7 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
     if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
     // sweep 2 update (+ ||w||^2, beta finalisation)
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
-    k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD,
-                                                                          fin, ctx->flags, 0, 0, ctx->scalars + S_NRM2_BEFORE);
-    LZ_LAUNCH_CHECK(ctx);
+    LZ_TRY(launch_cgs_update(ctx, g, n, K, w, fin, 0, 0));
     lz_prof_end(ctx);
     return LZ_OK;
 }
