@@ -291,9 +291,9 @@ static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr
         attr_set = true;
     }
     int grid = ctx->sm_count * 2;
-    if (grid > A->n_chunks) grid = A->n_chunks;
+    if (grid > A->mm_n_chunks) grid = A->mm_n_chunks;
     k_spmm_ws<BW, CW, STAGES, CAP><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
-        A->n_chunks, n_rows, A->chunk_row, A->chunk_ptr, rowptr, A->colidx, A->vals, X, W);
+        A->mm_n_chunks, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W);
     return LZ_OK;
 }
 
@@ -418,7 +418,7 @@ static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, 
         int64_t want = (n + SPMM_SLAB - 1) / SPMM_SLAB;
         int64_t cap = (int64_t)ctx->sm_count * 8;
         const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
-        const bool ws = A->tma_ok && A->cap == 2048 && ctx->spmv_variant != 9 && !fuse && ((uintptr_t)X % 32 == 0) && ((uintptr_t)W % 32 == 0);
+        const bool ws = A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 && !fuse && ((uintptr_t)X % 32 == 0) && ((uintptr_t)W % 32 == 0);
         if (ws && (bw == 8 || bw == 16 || bw == 32)) {
             if (bw == 8) LZ_TRY(launch_spmm_ws<8>(ctx, A, rowptr, n, X, W));
             else if (bw == 16) LZ_TRY(launch_spmm_ws<16>(ctx, A, rowptr, n, X, W));

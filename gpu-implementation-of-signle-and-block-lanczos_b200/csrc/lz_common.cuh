@@ -83,7 +83,8 @@ struct lz_ctx {
 
 #define LZ_PROF_CAP 16384
 // kernel classes for the profiler
-enum { LZ_K_SPMV = 0, LZ_K_PASSB = 1, LZ_K_PROJECT = 2, LZ_K_UPDATE = 3, LZ_K_SPMM = 4, LZ_K_GRAM = 5, LZ_K_PANEL = 6, LZ_K_SMALL = 7, LZ_K_COMM = 8, LZ_K_CLASSES = 9 };
+enum { LZ_K_SPMV = 0, LZ_K_PASSB = 1, LZ_K_PROJECT = 2, LZ_K_UPDATE = 3, LZ_K_SPMM = 4, LZ_K_GRAM = 5, LZ_K_PANEL = 6, LZ_K_SMALL = 7, LZ_K_COMM = 8, LZ_K_UPDPROJ = 9, LZ_K_CLASSES = 10 };
+static_assert(LZ_K_CLASSES == LZ_PROFILE_CLASSES, "profiler class count is part of the C-ABI");
 void lz_prof_begin(lz_ctx *ctx, int cls, double bytes);
 void lz_prof_end(lz_ctx *ctx);
 #define LZ_PARTIALS_CAP (1 << 22)
@@ -107,7 +108,8 @@ enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
 
 // row-aligned nnz chunks: chunk c covers rows [chunk_row[c], chunk_row[c+1])
 #define LZ_SPMV_THREADS 256
-#define LZ_SPMV_TILE 1536        // target nnz per chunk (default; see profiles/ for the sweep)
+#define LZ_SPMV_TILE 768         // target nnz per SpMV chunk (profiles/r01_spmv_variants.md)
+#define LZ_SPMM_TILE 1536        // target nnz per SpMM chunk (k_spmm_ws stages 2048 entries per slot)
 #define LZ_SPLIT_L 256           // rows longer than this are split into virtual rows
 #define LZ_SPMV_CAP 4096         // shared-memory product slots per CTA (32 KB)
 
@@ -125,6 +127,8 @@ struct lz_matrix {
     int32_t *chunk_row;      // n_chunks + 1
     int32_t *chunk_ptr;      // rowptr[chunk_row[c]], n_chunks + 1
     int tile, cap;           // nnz per chunk (target) and shared-memory product slots per CTA
+    int mm_n_chunks;         // second schedule with LZ_SPMM_TILE-sized chunks for the SpMM kernel
+    int32_t *mm_chunk_row, *mm_chunk_ptr;
     int tma_ok;              // vals / colidx 16-byte aligned: bulk-copy staged kernel usable
     int max_row_nnz;
     // row-split view for operators with long rows (NULL otherwise): virtual row pointers over the same

@@ -85,8 +85,13 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
 static int build_schedule(lz_ctx *ctx, lz_matrix *A)
 {
     A->tile = ctx->spmv_tile > 0 ? ctx->spmv_tile : LZ_SPMV_TILE;
-    A->cap = A->tile <= 1536 ? 2048 : 4096;
-    if (ctx->spmv_variant == 1 || ctx->spmv_variant == 5 || ctx->spmv_variant == 6) { A->tile = 1536; A->cap = 1792; }     // dev-time sweep knobs
+    A->cap = A->tile <= 768 ? 1024 : A->tile <= 1536 ? 2048 : 4096;
+    {   // dev-time sweep knobs (profiles/r01_spmv_variants.md)
+        const int v = ctx->spmv_variant;
+        if (v == 3 || v == 7 || v == 8) { A->tile = 1536; A->cap = 2048; }
+        if (v == 11 || v == 19) { A->tile = 1280; A->cap = 1536; }
+        if (v == 1 || v == 5 || v == 6) { A->tile = 1536; A->cap = 1792; }
+    }
     int *d_max = ctx->flags + 8;
     LZ_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
     k_max_row<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->rowptr, d_max);
@@ -104,6 +109,14 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     LZ_CUDA(cudaMalloc(&A->chunk_ptr, sizeof(int32_t) * (nch + 1)));
     A->tma_ok = ((uintptr_t)A->vals % 16 == 0) && ((uintptr_t)A->colidx % 16 == 0);
     k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, A->nnz, rp, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
+    LZ_LAUNCH_CHECK(ctx);
+    // the SpMM kernel amortises its per-chunk cost over wider rows: its own, coarser schedule
+    int64_t mch = (A->nnz + LZ_SPMM_TILE - 1) / LZ_SPMM_TILE;
+    if (mch < 1) mch = 1;
+    A->mm_n_chunks = (int)mch;
+    LZ_CUDA(cudaMalloc(&A->mm_chunk_row, sizeof(int32_t) * (mch + 1)));
+    LZ_CUDA(cudaMalloc(&A->mm_chunk_ptr, sizeof(int32_t) * (mch + 1)));
+    k_chunk_rows<<<(unsigned)((mch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, A->nnz, rp, (int)mch, LZ_SPMM_TILE, A->mm_chunk_row, A->mm_chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     return LZ_OK;
@@ -438,6 +451,8 @@ int lz_matrix_destroy(lz_matrix *A)
     }
     cudaFree(A->chunk_row);
     cudaFree(A->chunk_ptr);
+    cudaFree(A->mm_chunk_row);
+    cudaFree(A->mm_chunk_ptr);
     cudaFree(A->vrowptr);
     cudaFree(A->vstart);
     cudaFree(A->ybar);

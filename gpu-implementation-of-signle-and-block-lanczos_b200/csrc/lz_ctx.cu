@@ -159,7 +159,7 @@ int lz_ctx_profile(lz_ctx *ctx, int enable)
     return LZ_OK;
 }
 
-// sums per class since the last enable: launches, milliseconds, algorithmic bytes (arrays of LZ_K_CLASSES = 9)
+// sums per class since the last enable: launches, milliseconds, algorithmic bytes (arrays of LZ_K_CLASSES = LZ_PROFILE_CLASSES)
 int lz_ctx_profile_read(lz_ctx *ctx, int64_t *launches, double *ms, double *bytes)
 {
     LZ_CHECK(ctx && launches && ms && bytes, LZ_ERR_INVALID, "lz_ctx_profile_read: NULL argument");

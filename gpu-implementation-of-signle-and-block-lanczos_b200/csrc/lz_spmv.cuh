@@ -396,8 +396,8 @@ __device__ __forceinline__ void lz_mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lz_smem_u32(bar)) : "memory");
 }
 
-template <int MODE, int GW, int RW, int STAGES, int CAP>
-__global__ void __launch_bounds__((1 + GW + RW) * 32)
+template <int MODE, int GW, int RW, int STAGES, int CAP, int MINB = 1>
+__global__ void __launch_bounds__((1 + GW + RW) * 32, MINB)
 k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
               const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
@@ -567,20 +567,23 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
     }
 }
 
-template <int MODE, int GW, int RW, int STAGES, int CAP>
+template <int MODE, int GW, int RW, int STAGES, int CAP, int MINB = 1>
 static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int ctas_per_sm,
-                                       int blocked = 0)
+                                       int blocked = 0, bool coarse = false)
 {
+    // coarse: the LZ_SPMM_TILE schedule (plain SpMV prefers the larger chunks, profiles/r01_spmv_variants.md)
+    const int n_chunks = coarse ? A->mm_n_chunks : A->n_chunks;
+    const int32_t *chunk_row = coarse ? A->mm_chunk_row : A->chunk_row, *chunk_ptr = coarse ? A->mm_chunk_ptr : A->chunk_ptr;
     static bool attr_set = false;
     const size_t smem = (size_t)STAGES * CAP * 12 + 24 * STAGES;
     if (!attr_set) {
-        LZ_CUDA(cudaFuncSetAttribute(k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LZ_CUDA(cudaFuncSetAttribute(k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int grid = ctx->sm_count * ctas_per_sm;
-    if (grid > A->n_chunks) grid = A->n_chunks;
-    k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
-        A->n_chunks, A->chunk_row, A->chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked);
+    if (grid > n_chunks) grid = n_chunks;
+    k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
+        n_chunks, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked);
     return LZ_OK;
 }
 
@@ -619,12 +622,18 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
         // kernel shape per schedule (A->cap is fixed when the schedule is built, lz_csr.cu)
         const int v = ctx->spmv_variant;
         const int blk = 0;                       // strided chunk map: blocked ranges measured slower (profiles/r01_spmv_variants.md)
-        if (A->cap == 2048) {
-            if (v == 3) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 3, 0)));
-            else if (v == 4) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 2, 1)));
-            else if (v == 7) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 2, 1)));
-            else if (v == 8) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048>(ctx, A, x, y, args, 3, 1)));
-            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048>(ctx, A, x, y, args, 3, blk)));      // default (profiles/r01_spmv_variants.md)
+        if (A->cap == 1024) {
+            // default: 1 producer + 3 gather + 5 row warps, 3-slot ring of 1024 entries, 5 CTAs per SM.
+            // A stand-alone SpMV (x not L2-resident from a preceding pass B) runs faster on the coarse schedule.
+            if (MODE == LZ_EPI_PLAIN && A->mm_chunk_row && v != 20) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, blk, true)));
+            else LZ_TRY((lz_launch_ws_variant<MODE, 3, 5, 3, 1024, 5>(ctx, A, x, y, args, 5, blk)));
+        } else if (A->cap == 2048) {
+            if (v == 7) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048, 2>(ctx, A, x, y, args, 2, 1)));
+            else if (v == 8) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048, 3>(ctx, A, x, y, args, 3, 1)));
+            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, blk)));
+        } else if (A->cap == 1536) {
+            if (v == 19) LZ_TRY((lz_launch_ws_variant<MODE, 5, 8, 4, 1536, 3>(ctx, A, x, y, args, 3)));
+            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 4, 1536, 3>(ctx, A, x, y, args, 3)));
         } else if (A->cap == 1792) {
             if (v == 5) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 4, 1792>(ctx, A, x, y, args, 2)));
             else if (v == 6) LZ_TRY((lz_launch_ws_variant<MODE, 10, 9, 5, 1792>(ctx, A, x, y, args, 2)));

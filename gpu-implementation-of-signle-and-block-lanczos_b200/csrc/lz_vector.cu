@@ -457,7 +457,7 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
     if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
     // sweep 1 update + sweep 2 projection, one basis stream
     const unsigned fgrid = (unsigned)ctx->sm_count;
-    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
+    lz_prof_begin(ctx, LZ_K_UPDPROJ, 8.0 * (double)n * (K + 2));
     k_cgs_update_project<<<fgrid, CF_THREADS, smem, ctx->stream>>>(n, K, g.V, g.ts, w, g.c, g.cpart);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);

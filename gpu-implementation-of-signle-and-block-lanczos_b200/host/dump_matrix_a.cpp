@@ -1,5 +1,5 @@
 // dump_matrix_a.cpp -- writes Matrix_A<double>(N,N,N) (D, W and A = D*W) in the record container of
-// oracle/ref_host_dump so the CPU test suite can compare the mirror's builder with the golden
+// tests' reference-side dump tool so the CPU test suite can compare the mirror's builder with the golden
 // arrays minted by the reference's own builder.  Host-only: needs no GPU.
 #include <cstring>
 

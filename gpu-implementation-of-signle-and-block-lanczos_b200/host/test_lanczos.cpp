@@ -5,7 +5,7 @@
 // and the new options are real run-time flags:
 //   -N <grid points per dim>   -m <iterations>            (reference flags, :338-345)
 //   --matrix maxwell|lap2d|lap3d   --block <b>|--vector   --reorth none|full|dgks   --k <ritz pairs>
-//   --format ell|csr   --dump <file>  (alpha/beta/q in the oracle's record format, for the parity tests)
+//   --format ell|csr   --dump <file>  (alpha/beta/q in the parity tests' record format, for the parity tests)
 #ifndef N_COL
 #define N_COL 4
 #endif

@@ -126,10 +126,10 @@ class Context:
 
     def profile_read(self):
         """{class: (launches, ms, algorithmic_bytes)} accumulated since profiling was enabled."""
-        n = 9
+        n = 10
         la, ms, by = (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
         check(lib().lz_ctx_profile_read(self.h, la, ms, by))
-        names = ["spmv", "pass_b", "cgs_project", "cgs_update", "spmm", "gram", "panel", "small", "comm"]
+        names = ["spmv", "pass_b", "cgs_project", "cgs_update", "spmm", "gram", "panel", "small", "comm", "cgs_update_project"]
         return {names[i]: (int(la[i]), float(ms[i]), float(by[i])) for i in range(n)}
 
     def close(self):

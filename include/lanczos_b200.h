@@ -64,8 +64,9 @@ int lz_ctx_device(const lz_ctx *ctx);
 int64_t lz_ctx_launch_count(const lz_ctx *ctx);
 
 /* per-kernel-class timing with CUDA events on the context's stream (measurement only; bench.py).
- * classes: 0 spmv(+fused), 1 pass B, 2 CGS project, 3 CGS update, 4 spmm, 5 gram, 6 panel, 7 small, 8 comm */
-#define LZ_PROFILE_CLASSES 9
+ * classes: 0 spmv(+fused), 1 pass B, 2 CGS project, 3 CGS update, 4 spmm, 5 gram, 6 panel, 7 small, 8 comm,
+ * 9 fused CGS update+project; the three output arrays have LZ_PROFILE_CLASSES entries */
+#define LZ_PROFILE_CLASSES 10
 int lz_ctx_profile(lz_ctx *ctx, int enable);
 int lz_ctx_profile_read(lz_ctx *ctx, int64_t *launches, double *ms, double *bytes);
 
