@@ -171,11 +171,11 @@ __device__ __forceinline__ void lz_ld256_ro(const double *p, double &a, double &
 // A group of LW = BW/4 lanes owns a row and every lane carries FOUR adjacent columns (one 256-bit
 // load per gathered row): the kernel is bound by instruction issue, and four columns per lane halve
 // the instructions per non-zero against the two-column layout of k_spmm_rm.
-template <int BW, int CW, int STAGES, int CAP>
-__global__ void __launch_bounds__((1 + CW) * 32, 2)
+template <int BW, int CW, int STAGES, int CAP, int MINB>
+__global__ void __launch_bounds__((1 + CW) * 32, MINB)
 k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
           const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
-          const double *__restrict__ X, double *__restrict__ W)
+          const double *__restrict__ X, double *__restrict__ W, const int run, const int hint)
 {
     constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -190,23 +190,24 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // every CTA owns a CONTIGUOUS range of chunks: the rows gathered for the +-nx neighbours of a stencil
-    // are this CTA's own rows a few chunks later (L1 hits), and all CTAs advance through their ranges in
-    // step, so the +-nx*ny neighbours are the rows a neighbouring CTA is working on (L2 hits)
-    const int per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
-    const int first = blockIdx.x * per_cta, step = 1;
-    const int last = min(n_chunks, first + per_cta);
+    // chunk -> CTA map: runs of `run` consecutive chunks dealt round-robin to the CTAs.  Inside a run the rows
+    // gathered for the near neighbours of a stencil row are this CTA's own recent rows (L1 hits); all CTAs
+    // together sweep a window of grid*run chunks, so the far (+-nx*ny) neighbours were touched one window
+    // earlier and are still in L2 (with one contiguous range per CTA they were DRAM misses: ncu, L2 hit 15 %).
+    auto chunk_of = [&](int it) { return ((it / run) * (int)gridDim.x + (int)blockIdx.x) * run + (it % run); };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             int p0 = 0, p1 = 0, r0 = 0, r1 = 0;
-            if (first < last) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; r0 = chunk_row[first]; r1 = chunk_row[first + 1]; }
-            int it = 0;
-            for (int c = first; c < last; c += step, ++it) {
+            int c = chunk_of(0);
+            if (c < n_chunks) { p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1]; }
+            const uint64_t pol = lz_policy_evict_first();
+            for (int it = 0; c < n_chunks; ++it) {
                 const int slot = it % STAGES;
                 const int cp0 = p0, cp1 = p1, cr0 = r0, cr1 = r1;
-                if (c + step < last) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; r0 = chunk_row[c + step]; r1 = chunk_row[c + step + 1]; }
+                c = chunk_of(it + 1);
+                if (c < n_chunks) { p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1]; }
                 lz_mbar_wait(&freeb[slot], ((it / STAGES) & 1) ^ 1);
                 const int a0 = cp0 & ~3, cnt4 = (cp1 - a0) & ~3;
                 const int ra = cr0 & ~3;
@@ -215,9 +216,15 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                 if (cp1 - a0 > CAP || cnt4 == 0) { lz_mbar_arrive(&full[slot]); continue; }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 lz_mbar_expect_tx(&full[slot], (uint32_t)cnt4 * 12u + (rows_ok ? (uint32_t)rcnt * 4u : 0u));
-                lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
-                lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
-                if (rows_ok) lz_bulk_g2s(rptr_s + (size_t)slot * SPMM_WS_RCAP, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot]);
+                if (hint) {
+                    lz_bulk_g2s_hint(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot], pol);
+                    lz_bulk_g2s_hint(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot], pol);
+                    if (rows_ok) lz_bulk_g2s_hint(rptr_s + (size_t)slot * SPMM_WS_RCAP, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot], pol);
+                } else {
+                    lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
+                    lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
+                    if (rows_ok) lz_bulk_g2s(rptr_s + (size_t)slot * SPMM_WS_RCAP, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot]);
+                }
             }
         }
     } else {
@@ -225,14 +232,15 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
         const int sub = lane / LW, l = lane % LW;
         const int gid = (warp - 1) * RPW + sub;
         int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
-        if (first < last) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
-        int it = 0;
-        for (int c = first; c < last; c += step, ++it) {
+        int c = chunk_of(0);
+        if (c < n_chunks) { nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
+        for (int it = 0; c < n_chunks; ++it) {
             const int slot = it % STAGES;
             const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
-            if (c + step < last) {
-                nr0 = chunk_row[c + step]; nr1 = chunk_row[c + step + 1];
-                np0 = chunk_ptr[c + step]; np1 = chunk_ptr[c + step + 1];
+            c = chunk_of(it + 1);
+            if (c < n_chunks) {
+                nr0 = chunk_row[c]; nr1 = chunk_row[c + 1];
+                np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1];
             }
             const int a0 = cp0 & ~3, cnt = cp1 - a0, cnt4 = cnt & ~3;
             const int ra = r0 & ~3;
@@ -272,7 +280,8 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                         acc2 = fma(vv[g], x2[g], acc2); acc3 = fma(vv[g], x3[g], acc3);
                     }
                 }
-                lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                if (hint) lz_st256_stream(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                else lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
             }
             __syncwarp();
             if (lane == 0) lz_mbar_arrive(&freeb[slot]);
@@ -280,21 +289,40 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     }
 }
 
-template <int BW>
-static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W)
+template <int BW, int CW, int STAGES, int MINB>
+static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W, int run)
 {
-    constexpr int CW = 12, STAGES = 2, CAP = 2048;
+    constexpr int CAP = 2048;
     const size_t smem = (size_t)STAGES * (CAP * 12 + SPMM_WS_RCAP * 4) + 16 * STAGES;
     static bool attr_set = false;
     if (!attr_set) {
-        LZ_CUDA(cudaFuncSetAttribute(k_spmm_ws<BW, CW, STAGES, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LZ_CUDA(cudaFuncSetAttribute(k_spmm_ws<BW, CW, STAGES, CAP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    int grid = ctx->sm_count * 2;
+    int grid = ctx->sm_count * MINB;
     if (grid > A->mm_n_chunks) grid = A->mm_n_chunks;
-    k_spmm_ws<BW, CW, STAGES, CAP><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
-        A->mm_n_chunks, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W);
+    const int per_cta = (A->mm_n_chunks + grid - 1) / grid;
+    k_spmm_ws<BW, CW, STAGES, CAP, MINB><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
+        A->mm_n_chunks, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W, run > 0 ? run : per_cta,
+        getenv("LZ_SPMM_NOHINT") ? 0 : 1);
     return LZ_OK;
+}
+
+template <int BW>
+static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W)
+{
+    // dev-time knobs: LZ_SPMM_RUN = chunks per run of the chunk map (0: one contiguous range per CTA), LZ_SPMM_SHAPE
+    static int run = -1, shape = 0;
+    if (run < 0) {
+        const char *e = getenv("LZ_SPMM_RUN"); run = e ? atoi(e) : 1;
+        e = getenv("LZ_SPMM_SHAPE"); shape = e ? atoi(e) : 0;
+    }
+    if (shape == 1) return launch_spmm_ws_shape<BW, 8, 2, 3>(ctx, A, rowptr, n_rows, X, W, run);
+    if (shape == 2) return launch_spmm_ws_shape<BW, 12, 3, 2>(ctx, A, rowptr, n_rows, X, W, run);
+    if (shape == 3) return launch_spmm_ws_shape<BW, 14, 2, 2>(ctx, A, rowptr, n_rows, X, W, run);
+    if (shape == 4) return launch_spmm_ws_shape<BW, 10, 2, 3>(ctx, A, rowptr, n_rows, X, W, run);
+    if (shape == 5) return launch_spmm_ws_shape<BW, 16, 3, 1>(ctx, A, rowptr, n_rows, X, W, run);
+    return launch_spmm_ws_shape<BW, 12, 2, 2>(ctx, A, rowptr, n_rows, X, W, run);
 }
 
 // any bw <= 32 (odd widths, bw = 1): one lane per column

@@ -223,4 +223,10 @@ __device__ __forceinline__ void lz_st256(double *p, double a, double b, double c
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
+// streaming store (written once, not re-read before it would be evicted anyway)
+__device__ __forceinline__ void lz_st256_stream(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 #endif  // __CUDACC__

@@ -203,6 +203,20 @@ __device__ __forceinline__ void lz_bulk_g2s(void *dst_smem, const void *src, uin
                  ::"r"(lz_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(lz_smem_u32(bar)) : "memory");
 }
 
+// same copy with an L2 evict-first policy: the matrix streams are read once per product and must not
+// push the gathered operand (x / the X panel) out of L2
+__device__ __forceinline__ uint64_t lz_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void lz_bulk_g2s_hint(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(lz_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(lz_smem_u32(bar)), "l"(pol) : "memory");
+}
+
 #define LZ_TMA_ROWS_PER_THREAD 4
 
 template <int MODE, int THREADS, int STAGES, int CAP>
