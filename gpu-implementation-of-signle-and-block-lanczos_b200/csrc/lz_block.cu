@@ -304,7 +304,7 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
     const int per_cta = (A->mm_n_chunks + grid - 1) / grid;
     k_spmm_ws<BW, CW, STAGES, CAP, MINB><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
         A->mm_n_chunks, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W, run > 0 ? run : per_cta,
-        getenv("LZ_SPMM_NOHINT") ? 0 : 1);
+        getenv("LZ_SPMM_HINT") ? 1 : 0);      // evict-first streams: +5 % when the far neighbours miss L2, -3 % when they hit: off
     return LZ_OK;
 }
 

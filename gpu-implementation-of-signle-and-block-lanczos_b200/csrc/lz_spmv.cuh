@@ -415,7 +415,7 @@ __global__ void __launch_bounds__((1 + GW + RW) * 32, MINB)
 k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
               const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-              const LzPassA args, const int blocked)
+              const LzPassA args, const int blocked, const int hint)
 {
     constexpr int THREADS = (1 + GW + RW) * 32, GT = GW * 32, RT = RW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -447,6 +447,7 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
             int p0 = 0, p1 = 0;
             if (first < last) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
             int it = 0;
+            const uint64_t pol = lz_policy_evict_first();
             for (int c = first; c < last; c += step, ++it) {
                 const int slot = it % STAGES;
                 const int cp0 = p0, cp1 = p1;
@@ -457,8 +458,13 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
                 if (cp1 - a0 > CAP || cnt4 == 0) { lz_mbar_arrive(&full[slot]); continue; }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 lz_mbar_expect_tx(&full[slot], (uint32_t)cnt4 * 12u);
-                lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
-                lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
+                if (hint) {     // the matrix is read once per product: keep L2 for x / w (re-read by pass B and the next pass A)
+                    lz_bulk_g2s_hint(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot], pol);
+                    lz_bulk_g2s_hint(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot], pol);
+                } else {
+                    lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
+                    lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
+                }
             }
         }
     } else if (warp <= GW) {
@@ -597,7 +603,8 @@ static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const do
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > n_chunks) grid = n_chunks;
     k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
-        n_chunks, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked);
+        n_chunks, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked,
+        getenv("LZ_SPMV_HINT") ? 1 : 0);      // evict-first on the matrix streams measured 4-5 % slower: off
     return LZ_OK;
 }
 
