@@ -1,0 +1,96 @@
+"""Turns the ncu output of tools/profile_round.sh (gpurun_out/<round>_*) into the tracked evidence under
+profiles/: launch-list shares, raw metric pages of the full captures, DRAM traffic per algorithmic byte
+(profiles/roofline_traffic.json, read by bench.py) and SASS excerpts.  Runs in the dev container (no GPU)."""
+import csv, json, os, re, shutil, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+N = 4096 * 4096
+NNZ = 5 * N - 4 * 4096
+
+def launches():
+    src = os.path.join(GO, R + "_bench_launches.csv")
+    if not os.path.exists(src):
+        return None
+    rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if len(r) > 5]
+    hdr = rows[0]; ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    data = [(re.sub(r"[<(].*", "", r[ik]), float(r[iv].replace(",", ""))) for r in rows[1:] if r[iv]]
+    half = data[len(data) // 2:]                     # the timed solve (second of two identical solves)
+    tot = sum(v for _, v in half); by = {}
+    for k, v in half:
+        by.setdefault(k, [0, 0.0]); by[k][0] += 1; by[k][1] += v
+    shutil.copy(src, os.path.join(PR, R + "_bench_launches.csv"))
+    return {k: dict(launches=c, ms=v / 1e6, share=v / tot) for k, (c, v) in sorted(by.items(), key=lambda kv: -kv[1][1])}, len(data)
+
+def full(kernel):
+    rep = os.path.join(GO, "%s_full_%s.ncu-rep" % (R, kernel))
+    if not os.path.exists(rep):
+        return None
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    open(os.path.join(PR, "%s_full_%s.raw.csv" % (R, kernel)), "w").write(out)
+    rows = list(csv.reader(out.splitlines())); hdr, units, val = rows[0], rows[1], rows[2]
+    def get(name):
+        i = hdr.index(name); v = float(val[i].replace(",", "")); u = units[i].split("/")[0]
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1e-3, "us": 1e-6, "ns": 1e-9}.get(u, 1)
+    smem = get("launch__shared_mem_per_block_dynamic")
+    d = dict(dram_bytes=get("dram__bytes_read.sum") + get("dram__bytes_write.sum"), seconds=get("gpu__time_duration.sum"),
+             dyn_smem=smem,
+             regs=get("launch__registers_per_thread"), grid=get("launch__grid_size"), block=get("launch__block_size"))
+    if kernel == "k_cgs_update":
+        K = int(round(smem / 8)); alg = 8.0 * N * (K + 2)
+    elif kernel == "k_cgs_project":
+        K = int(round(smem / 64)); alg = 8.0 * N * (K + 1)
+    elif kernel == "k_cgs_update_project":
+        def fsmem(k, D, th): return 8 * (D * k * 32 + D * 32 + th + ((k + 1) & ~1)) + 8 * D + 8      # cgs_fused_smem (lz_vector.cu)
+        def ring(k, th):
+            D = 2
+            while D < 8 and fsmem(k, D + 1, th) <= 215 * 1024: D += 1
+            return D
+        th = int(d["block"])
+        K = next(k for k in range(1, 1024) if fsmem(k, ring(k, th), th) == int(smem)); alg = 8.0 * N * (K + 2)
+    else:
+        K = None; alg = 12.0 * NNZ + 36.0 * N
+    d.update(captured_K=K, algorithmic_bytes=alg, dram_bytes_per_algorithmic_byte=d["dram_bytes"] / alg,
+             dram_gbs_under_ncu=d["dram_bytes"] / d["seconds"] / 1e9)
+    return d
+
+def sass(kernel_regex, name):
+    lib = os.path.join(ROOT, "gpu-implementation-of-signle-and-block-lanczos_b200", "liblanczos_b200.so")
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    blocks = out.split("Function : ")
+    for b in blocks[1:]:
+        if re.match(kernel_regex, b):
+            ops = {}
+            for m in re.finditer(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", b, re.M):
+                ops[m.group(1)] = ops.get(m.group(1), 0) + 1
+            keep = {k: v for k, v in ops.items() if re.match(r"UBLKCP|SYNCS|DMMA|LDG\.E\.(ENL2\.)?(128|256|64)|LDG.*256|STG.*(128|256)|LDS|DFMA|UTMA", k)}
+            open(os.path.join(PR, "%s_sass_%s.txt" % (R, name)), "w").write(
+                "Function : " + b.split("\n")[0] + "\nopcode histogram (selected): " + json.dumps(keep, sort_keys=True) + "\n\n" + "\n".join(b.split("\n")[:400]))
+            return keep
+    return None
+
+def main():
+    res = {}
+    l = launches()
+    if l:
+        res["launch_shares"], res["launch_rows"] = l
+    traffic = {}
+    for kern, cls in (("k_cgs_update_project", "cgs_update_project"), ("k_cgs_update", "cgs_update"), ("k_cgs_project", "cgs_project"), ("k_csr_spmv_ws", "spmv")):
+        f = full(kern)
+        if f:
+            traffic[cls] = f
+    if traffic:
+        traffic["_source"] = "ncu --set full captures profiles/%s_full_*.raw.csv (dram__bytes_read.sum + dram__bytes_write.sum), bench.py cfg2, launch 250 of each kernel" % R
+        json.dump(traffic, open(os.path.join(PR, "roofline_traffic.json"), "w"), indent=1)
+    res["traffic"] = traffic
+    res["sass"] = {n: sass(rx, n) for rx, n in ((r"_Z20k_cgs_update_project", "k_cgs_update_project"), (r"_Z12k_cgs_update", "k_cgs_update"),
+                                               (r"_Z13k_cgs_project", "k_cgs_project"), (r"_Z13k_csr_spmv_wsILi1ELi3ELi5", "k_csr_spmv_ws"),
+                                               (r"_Z9k_spmm_wsILi16ELi12", "k_spmm_ws16"), (r"_Z11k_gram_dmmaILi16", "k_gram_dmma16"),
+                                               (r"_Z14k_block_updateILi16", "k_block_update16"))}
+    for f in (R + "_bench_plain.log",):
+        if os.path.exists(os.path.join(GO, f)):
+            shutil.copy(os.path.join(GO, f), os.path.join(PR, f))
+    print(json.dumps(res, indent=1))
+
+if __name__ == "__main__":
+    main()
