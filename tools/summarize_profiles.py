@@ -41,13 +41,8 @@ def full(kernel):
     elif kernel == "k_cgs_project":
         K = int(round(smem / 64)); alg = 8.0 * N * (K + 1)
     elif kernel == "k_cgs_update_project":
-        def fsmem(k, D, th): return 8 * (D * k * 32 + D * 32 + th + ((k + 1) & ~1)) + 8 * D + 8      # cgs_fused_smem (lz_vector.cu)
-        def ring(k, th):
-            D = 2
-            while D < 8 and fsmem(k, D + 1, th) <= 215 * 1024: D += 1
-            return D
-        th = int(d["block"])
-        K = next(k for k in range(1, 1024) if fsmem(k, ring(k, th), th) == int(smem)); alg = 8.0 * N * (K + 2)
+        # cgs_fused_smem (lz_vector.cu): two K x 32 tiles, two w slices, 256 partials, K coefficients, barriers
+        K = next(k for k in range(1, 1024) if 8 * (2 * k * 32 + 2 * 32 + 256 + ((k + 1) & ~1)) + 16 == int(smem)); alg = 8.0 * N * (K + 2)
     else:
         K = None; alg = 12.0 * NNZ + 36.0 * N
     d.update(captured_K=K, algorithmic_bytes=alg, dram_bytes_per_algorithmic_byte=d["dram_bytes"] / alg,
