@@ -218,9 +218,12 @@ k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_
 #define CF_THREADS 256
 #define CF_MAXC 2               // columns per thread: K <= CF_MAXC * CF_THREADS
 
+// threads sharing one column in phase 2 (each takes CF_R / S rows); S * K <= CF_THREADS
+__host__ __device__ __forceinline__ int cgs_fused_slices(int K) { return K <= 32 ? 8 : K <= 64 ? 4 : K <= 128 ? 2 : 1; }
+
 __global__ void __launch_bounds__(CF_THREADS)
 k_cgs_update_project(int64_t n, int K, const double *__restrict__ V, int64_t ts, double *__restrict__ w,
-                     const double *__restrict__ c1, double *__restrict__ cpart2 /* gridDim.x * K */)
+                     const double *__restrict__ c1, double *__restrict__ cpart2 /* gridDim.x * S * K */, const int S)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *vt = reinterpret_cast<double *>(smem_raw);                          // [2][K][CF_R]
@@ -248,6 +251,11 @@ k_cgs_update_project(int64_t n, int K, const double *__restrict__ V, int64_t ts,
 #pragma unroll
     for (int u = 0; u < CF_MAXC; ++u) acc[u] = 0.0;
     const int r = tid % CF_R, g = tid / CF_R;          // phase-1 role: row r, column group g of CF_THREADS/CF_R
+    // phase-2 role: column k0, row slice `part` of S.  With few columns one warp would carry all of phase 2
+    // while seven wait at the barrier (ncu at K = 21: 60 % barrier stalls, 0.8 us per tile whatever K), so for
+    // K <= 128 the 32 rows of a column are shared by S = 2, 4, 8 threads in different warps.
+    const int Kp = CF_THREADS / S, RP = CF_R / S;
+    const int part = tid / Kp, k0 = tid - part * Kp, i0 = part * RP;
     if (warp == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -273,26 +281,37 @@ k_cgs_update_project(int64_t n, int K, const double *__restrict__ V, int64_t ts,
         __syncthreads();
         // phase 2: this thread's columns dotted with the new rows; lane-skewed row order keeps the
         // 32 lanes of a warp on 32 different banks although their columns are CF_R doubles apart
+        if (S == 1) {
 #pragma unroll
-        for (int u = 0; u < CF_MAXC; ++u) {
-            const int k = tid + u * CF_THREADS;
-            if (k < K) {
-                const double *col = tv + (size_t)k * CF_R;
-                double a = acc[u];
+            for (int u = 0; u < CF_MAXC; ++u) {
+                const int k = tid + u * CF_THREADS;
+                if (k < K) {
+                    const double *col = tv + (size_t)k * CF_R;
+                    double a = acc[u];
 #pragma unroll 8
-                for (int i = 0; i < CF_R; ++i) {
-                    const int rr = (i + lane) & (CF_R - 1);
-                    if (rr < rows_valid) a = fma(col[rr], tw[rr], a);
+                    for (int i = 0; i < CF_R; ++i) {
+                        const int rr = (i + lane) & (CF_R - 1);
+                        if (rr < rows_valid) a = fma(col[rr], tw[rr], a);
+                    }
+                    acc[u] = a;
                 }
-                acc[u] = a;
             }
+        } else if (k0 < K) {
+            const double *col = tv + (size_t)k0 * CF_R;
+            double a = acc[0];
+#pragma unroll 4
+            for (int i = i0; i < i0 + RP; ++i) {
+                const int rr = (i + lane) & (CF_R - 1);
+                if (rr < rows_valid) a = fma(col[rr], tw[rr], a);
+            }
+            acc[0] = a;
         }
         __syncthreads();                               // the buffer may be refilled from here on
     }
 #pragma unroll
     for (int u = 0; u < CF_MAXC; ++u) {
-        const int k = tid + u * CF_THREADS;
-        if (k < K) cpart2[(size_t)blockIdx.x * K + k] = acc[u];
+        const int k = k0 + u * CF_THREADS;
+        if (k < K && (u == 0 || S == 1)) cpart2[((size_t)blockIdx.x * S + part) * K + k] = acc[u];
     }
 }
 
@@ -458,10 +477,13 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
     // sweep 1 update + sweep 2 projection, one basis stream
     const unsigned fgrid = (unsigned)ctx->sm_count;
     lz_prof_begin(ctx, LZ_K_UPDPROJ, 8.0 * (double)n * (K + 2));
-    k_cgs_update_project<<<fgrid, CF_THREADS, smem, ctx->stream>>>(n, K, g.V, g.ts, w, g.c, g.cpart);
+    static int no_slices = -1;
+    if (no_slices < 0) no_slices = getenv("LZ_CGS_NO_SLICES") ? 1 : 0;
+    const int S = no_slices ? 1 : cgs_fused_slices(K);
+    k_cgs_update_project<<<fgrid, CF_THREADS, smem, ctx->stream>>>(n, K, g.V, g.ts, w, g.c, g.cpart, S);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)fgrid, g.cpart, g.c, ctx->flags, 0);
+    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)fgrid * S, g.cpart, g.c, ctx->flags, 0);
     LZ_LAUNCH_CHECK(ctx);
     if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
     // sweep 2 update (+ ||w||^2, beta finalisation)
@@ -505,7 +527,9 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
     const unsigned cgs_grid = stream_grid(ctx, n, CGS_TILE) < (unsigned)(ctx->sm_count * 2)
                                   ? stream_grid(ctx, n, CGS_TILE) : (unsigned)(ctx->sm_count * 2);
     size_t work_bytes = sizeof(double) * (size_t)stride * 3;
-    if (reorth) work_bytes += sizeof(double) * ((size_t)cgs_grid * m + m + 8);
+    // projection partials: one row of m per CTA; the fused kernel writes S * K <= CF_THREADS entries per CTA
+    const size_t cpart_len = std::max((size_t)cgs_grid * m, (size_t)ctx->sm_count * CF_THREADS);
+    if (reorth) work_bytes += sizeof(double) * (cpart_len + m + 8);
     void *work;
     LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
     double *u_prev = (double *)work + off, *u_cur = u_prev + stride, *w = u_cur + stride;
@@ -513,7 +537,7 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         LZ_CHECK(sizeof(double) * (VT / 32) * (size_t)m <= 200 * 1024, LZ_ERR_UNSUPPORTED,
                  "lz_vector_lanczos: m = %d too large for the projection kernel's shared memory", m);
         g.cpart = (double *)work + 3 * stride;
-        g.c = g.cpart + (size_t)cgs_grid * m;
+        g.c = g.cpart + cpart_len;
         g.grid = cgs_grid;
         LZ_TRY(lz_ctx_basis(ctx, n, m, &g.V));
         g.ts = ctx->basis_ts; g.cs = ctx->basis_cs;
