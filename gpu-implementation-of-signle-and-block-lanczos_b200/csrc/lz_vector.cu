@@ -223,12 +223,15 @@ __host__ __device__ __forceinline__ int cgs_fused_slices(int K) { return K <= 32
 
 __global__ void __launch_bounds__(CF_THREADS)
 k_cgs_update_project(int64_t n, int K, const double *__restrict__ V, int64_t ts, double *__restrict__ w,
-                     const double *__restrict__ c1, double *__restrict__ cpart2 /* gridDim.x * S * K */, const int S)
+                     const double *__restrict__ c1, double *__restrict__ cpart2 /* gridDim.x * S * K */, const int S, const int NB)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *vt = reinterpret_cast<double *>(smem_raw);                          // [2][K][CF_R]
-    double *wt = vt + 2 * (size_t)K * CF_R;                                     // [2][CF_R]
-    double *red = wt + 2 * CF_R;                                                // [CF_THREADS/CF_R][CF_R]
+    // NB = 2: double-buffered tiles, one CTA per SM.  NB = 1: one tile per CTA and several CTAs per SM, so the
+    // copy of one CTA overlaps the phases of another and the barriers / serial section of one CTA no longer
+    // idle the SM (host picks: cgs_fused_shape)
+    double *vt = reinterpret_cast<double *>(smem_raw);                          // [NB][K][CF_R]
+    double *wt = vt + (size_t)NB * K * CF_R;                                    // [NB][CF_R]
+    double *red = wt + NB * CF_R;                                                // [CF_THREADS/CF_R][CF_R]
     double *c1s = red + CF_THREADS;                                             // [K]
     uint64_t *full = reinterpret_cast<uint64_t *>(c1s + ((K + 1) & ~1));        // [2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -256,12 +259,15 @@ k_cgs_update_project(int64_t n, int K, const double *__restrict__ V, int64_t ts,
     // K <= 128 the 32 rows of a column are shared by S = 2, 4, 8 threads in different warps.
     const int Kp = CF_THREADS / S, RP = CF_R / S;
     const int part = tid / Kp, k0 = tid - part * Kp, i0 = part * RP;
-    if (warp == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    if (NB == 2 && warp == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (warp == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);
-        lz_mbar_wait(&full[buf], (it >> 1) & 1);
+        const int buf = NB == 2 ? (it & 1) : 0;
+        if (warp == 0) {
+            if (NB == 1) issue(tile, 0);
+            else if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);
+        }
+        lz_mbar_wait(&full[buf], NB == 2 ? ((it >> 1) & 1) : (it & 1));
         const double *tv = vt + (size_t)buf * K * CF_R;
         double *tw = wt + buf * CF_R;
         const int rows_valid = (int)min((int64_t)CF_R, n - tile * CF_R);
@@ -315,9 +321,27 @@ k_cgs_update_project(int64_t n, int K, const double *__restrict__ V, int64_t ts,
     }
 }
 
-static inline size_t cgs_fused_smem(int K)
+static inline size_t cgs_fused_smem(int K, int NB)
 {
-    return sizeof(double) * (2 * (size_t)K * CF_R + 2 * CF_R + CF_THREADS + ((K + 1) & ~1)) + 16;
+    return sizeof(double) * ((size_t)NB * K * CF_R + (size_t)NB * CF_R + CF_THREADS + ((K + 1) & ~1)) + 16;
+}
+
+// CTAs per SM and tile buffers per CTA for the fused kernel: as many CTAs as shared memory allows (up to 4)
+// with double buffering for small K, two single-buffer CTAs for the rest
+static inline void cgs_fused_shape(int K, int *ctas, int *nb)
+{
+    const size_t budget = 214 * 1024;
+    static int order = -1;
+    if (order < 0) { const char *e = getenv("LZ_CGS_SHAPE_ORDER"); order = e ? atoi(e) : 1; }
+    static const int cand[3][6][2] = {
+        {{4, 2}, {2, 2}, {2, 1}, {1, 2}, {1, 2}, {1, 2}},
+        {{4, 2}, {4, 1}, {3, 1}, {2, 1}, {1, 2}, {1, 2}},
+        {{4, 2}, {3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 2}}};
+    for (int i = 0; i < 6; ++i) {
+        const int c = cand[order][i][0], b = cand[order][i][1];
+        if (c * (cgs_fused_smem(K, b) + 1024) <= budget) { *ctas = c; *nb = b; return; }
+    }
+    *ctas = 1; *nb = 2;
 }
 
 // c[k] = sum over CTAs of cpart[cta][k]  (fixed order); optionally all K in one small launch
@@ -444,7 +468,10 @@ static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, doub
 {
     // (a variant that gave each warp one tile and four adjacent columns per load -- fully contiguous 1 KB
     // reads of the tiled slab -- measured 4 % slower than this generic kernel: profiles/r01_cgs_fusion.md)
-    k_cgs_update<<<g.grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
+    static int mult = 0;
+    if (!mult) { const char *e = getenv("LZ_CGS_UPD_MULT"); mult = e ? atoi(e) : 3; }      // 3 CTAs/SM: 5.9 -> 6.6 TB/s on the row-tiled basis
+    const unsigned want = stream_grid(ctx, n, CGS_TILE), cap = (unsigned)(ctx->sm_count * mult);
+    k_cgs_update<<<want < cap ? want : cap, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
         n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
@@ -455,7 +482,11 @@ static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, doub
 // operands are not 16-byte aligned for the bulk copies.
 static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, bool sharded)
 {
-    const size_t smem = cgs_fused_smem(K);
+    int ctas = 1, NB = 2;
+    static int one_cta = -1;
+    if (one_cta < 0) one_cta = getenv("LZ_CGS_ONE_CTA") ? 1 : 0;
+    if (!one_cta) cgs_fused_shape(K, &ctas, &NB);
+    const size_t smem = cgs_fused_smem(K, NB);
     const bool ok = smem <= 220 * 1024 && K <= CF_MAXC * CF_THREADS && g.cs == CF_R && ((uintptr_t)w % 16 == 0) && !getenv("LZ_NO_CGS_FUSE");
     if (!ok) {
         LZ_TRY(cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded));
@@ -464,6 +495,7 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
     static bool attr_set = false;
     if (!attr_set) {
         LZ_CUDA(cudaFuncSetAttribute(k_cgs_update_project, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LZ_CUDA(cudaFuncSetAttribute(k_cgs_update_project, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     // sweep 1 projection
@@ -475,12 +507,12 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
     LZ_LAUNCH_CHECK(ctx);
     if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
     // sweep 1 update + sweep 2 projection, one basis stream
-    const unsigned fgrid = (unsigned)ctx->sm_count;
+    const unsigned fgrid = (unsigned)(ctx->sm_count * ctas);
     lz_prof_begin(ctx, LZ_K_UPDPROJ, 8.0 * (double)n * (K + 2));
     static int no_slices = -1;
     if (no_slices < 0) no_slices = getenv("LZ_CGS_NO_SLICES") ? 1 : 0;
     const int S = no_slices ? 1 : cgs_fused_slices(K);
-    k_cgs_update_project<<<fgrid, CF_THREADS, smem, ctx->stream>>>(n, K, g.V, g.ts, w, g.c, g.cpart, S);
+    k_cgs_update_project<<<fgrid, CF_THREADS, smem, ctx->stream>>>(n, K, g.V, g.ts, w, g.c, g.cpart, S, NB);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)fgrid * S, g.cpart, g.c, ctx->flags, 0);
@@ -528,7 +560,7 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
                                   ? stream_grid(ctx, n, CGS_TILE) : (unsigned)(ctx->sm_count * 2);
     size_t work_bytes = sizeof(double) * (size_t)stride * 3;
     // projection partials: one row of m per CTA; the fused kernel writes S * K <= CF_THREADS entries per CTA
-    const size_t cpart_len = std::max((size_t)cgs_grid * m, (size_t)ctx->sm_count * CF_THREADS);
+    const size_t cpart_len = std::max((size_t)cgs_grid * m, (size_t)ctx->sm_count * 4 * CF_THREADS);
     if (reorth) work_bytes += sizeof(double) * (cpart_len + m + 8);
     void *work;
     LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
