@@ -8,7 +8,7 @@ CMD="python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e"
 timeout 300 $CMD > gpurun_out/${R}_bench_plain.log 2>&1 || { echo "plain bench failed"; tail -5 gpurun_out/${R}_bench_plain.log; exit 1; }
 tail -1 gpurun_out/${R}_bench_plain.log | cut -c1-400
 # launch list of the timed solve (the warm-up solve's 2107 launches are skipped: same kernels, same sizes)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2107 -c 2107 --csv --log-file gpurun_out/${R}_bench_launches.csv $CMD > gpurun_out/${R}_ncu_launches.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2107 -c 2400 --csv --log-file gpurun_out/${R}_bench_launches.csv $CMD > gpurun_out/${R}_ncu_launches.log 2>&1
 echo "launch list rows: $(wc -l < gpurun_out/${R}_bench_launches.csv)"
 # full captures: one late launch (step 250 of the warm-up solve) of each dominant kernel
 for k in k_cgs_update_project k_cgs_update k_cgs_project k_csr_spmv_ws; do
