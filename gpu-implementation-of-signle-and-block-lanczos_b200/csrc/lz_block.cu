@@ -311,17 +311,10 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
 template <int BW>
 static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W)
 {
-    // dev-time knobs: LZ_SPMM_RUN = chunks per run of the chunk map (0: one contiguous range per CTA), LZ_SPMM_SHAPE
-    static int run = -1, shape = 0;
-    if (run < 0) {
-        const char *e = getenv("LZ_SPMM_RUN"); run = e ? atoi(e) : 1;
-        e = getenv("LZ_SPMM_SHAPE"); shape = e ? atoi(e) : 0;
-    }
-    if (shape == 1) return launch_spmm_ws_shape<BW, 8, 2, 3>(ctx, A, rowptr, n_rows, X, W, run);
-    if (shape == 2) return launch_spmm_ws_shape<BW, 12, 3, 2>(ctx, A, rowptr, n_rows, X, W, run);
-    if (shape == 3) return launch_spmm_ws_shape<BW, 14, 2, 2>(ctx, A, rowptr, n_rows, X, W, run);
-    if (shape == 4) return launch_spmm_ws_shape<BW, 10, 2, 3>(ctx, A, rowptr, n_rows, X, W, run);
-    if (shape == 5) return launch_spmm_ws_shape<BW, 16, 3, 1>(ctx, A, rowptr, n_rows, X, W, run);
+    // 12 compute warps, 2-slot ring, 2 CTAs per SM (other shapes: profiles/r01_spmv_variants.md).
+    // dev-time knob LZ_SPMM_RUN = chunks per run of the chunk map (default 1; 0: one contiguous range per CTA)
+    static int run = -1;
+    if (run < 0) { const char *e = getenv("LZ_SPMM_RUN"); run = e ? atoi(e) : 1; }
     return launch_spmm_ws_shape<BW, 12, 2, 2>(ctx, A, rowptr, n_rows, X, W, run);
 }
 

@@ -77,8 +77,7 @@ struct lz_ctx {
     cudaEvent_t *prof_ev;   // 2 * LZ_PROF_CAP events
     int *prof_cls;          // class id per pair
     double *prof_bytes;     // algorithmic bytes per pair
-    int spmv_variant;       // dev-time tuning knobs (env LZ_SPMV_VARIANT / LZ_SPMV_TILE)
-    int spmv_tile;
+    int spmv_variant;       // dev-time A/B knob (env LZ_SPMV_VARIANT: 3 coarse schedule, 20 fine schedule, 9 no staged SpMM)
 };
 
 #define LZ_PROF_CAP 16384

@@ -84,14 +84,8 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
 
 static int build_schedule(lz_ctx *ctx, lz_matrix *A)
 {
-    A->tile = ctx->spmv_tile > 0 ? ctx->spmv_tile : LZ_SPMV_TILE;
-    A->cap = A->tile <= 768 ? 1024 : A->tile <= 1536 ? 2048 : 4096;
-    {   // dev-time sweep knobs (profiles/r01_spmv_variants.md)
-        const int v = ctx->spmv_variant;
-        if (v == 3 || v == 7 || v == 8) { A->tile = 1536; A->cap = 2048; }
-        if (v == 11 || v == 19) { A->tile = 1280; A->cap = 1536; }
-        if (v == 1 || v == 5 || v == 6) { A->tile = 1536; A->cap = 1792; }
-    }
+    A->tile = LZ_SPMV_TILE;
+    A->cap = 1024;                       // shared-memory slots per ring stage of the fine-schedule kernel
     int *d_max = ctx->flags + 8;
     LZ_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
     k_max_row<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->rowptr, d_max);

@@ -52,7 +52,6 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     LZ_CUDA(cudaMemset(c->scalars, 0, sizeof(double) * LZ_SCALARS));
     LZ_CUDA(cudaMemset(c->flags, 0, sizeof(int) * LZ_FLAGS));
     if (const char *e = getenv("LZ_SPMV_VARIANT")) c->spmv_variant = atoi(e);
-    if (const char *e = getenv("LZ_SPMV_TILE")) c->spmv_tile = atoi(e);
     *out = c;
     return LZ_OK;
 }

@@ -4,7 +4,11 @@
 // and, in fused mode, the spmv + Vector::add + Vector::dot sequence of
 // methods/vector_lanczos.hpp:51-57 (one HBM pass instead of three).
 //
-// CSR kernel ("stream" scheduling): one CTA per row-aligned chunk of ~LZ_SPMV_TILE non-zeros.
+// Default CSR kernel (k_csr_spmv_ws, 16-byte aligned vals/colidx): persistent, warp-specialised CTAs walk a
+// schedule of row-aligned chunks -- a producer warp streams each chunk's vals/colidx slice into a
+// shared-memory ring with bulk async copies (cp.async.bulk + mbarrier), gather warps turn it into products
+// in place (x through LDG), row warps add the products of each row left to right and run the epilogue.
+// Fallback CSR kernel (k_csr_spmv, unaligned arrays): one CTA per row-aligned chunk.
 //   phase 1: the CTA walks its contiguous slice of vals/colidx with 128-bit/64-bit coalesced loads,
 //            gathers x and parks val*x products in shared memory (conflict-free 16-byte stores);
 //   phase 2: one thread per row adds its products left to right (the reference Host order,
@@ -217,188 +221,8 @@ __device__ __forceinline__ void lz_bulk_g2s_hint(void *dst_smem, const void *src
                  ::"r"(lz_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(lz_smem_u32(bar)), "l"(pol) : "memory");
 }
 
-#define LZ_TMA_ROWS_PER_THREAD 4
-
-template <int MODE, int THREADS, int STAGES, int CAP>
-__global__ void __launch_bounds__(THREADS)
-k_csr_spmv_tma(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
-               const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-               const LzPassA args)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // ring: STAGES x { double vals[CAP]; int cols[CAP]; }  then the mbarriers
-    double *vals_s = reinterpret_cast<double *>(smem_raw);
-    int *cols_s = reinterpret_cast<int *>(smem_raw + sizeof(double) * (size_t)CAP * STAGES);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(double) + sizeof(int)) * (size_t)CAP * STAGES);
-    __shared__ double red[32];
-    const int tid = threadIdx.x;
-    const LzRowEpi<MODE> epi(args);
-    double acc = 0.0;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) lz_mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // producer: slice [a0, a0+cnt4) of a chunk (nnz range [p0,p1)) into ring slot `slot`
-    auto issue = [&](int p0, int p1, int slot) {
-        const int a0 = p0 & ~3;
-        if (p1 - a0 > CAP) return;                     // long-row chunk: no staging
-        const int cnt4 = (p1 - a0) & ~3;
-        if (cnt4 == 0) return;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        lz_mbar_expect_tx(&full[slot], (uint32_t)cnt4 * 12u);
-        lz_bulk_g2s(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot]);
-        lz_bulk_g2s(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot]);
-    };
-
-    const int first = blockIdx.x, step = gridDim.x;
-    if (tid == 0) {
-        for (int s = 0; s < STAGES - 1; ++s) {
-            const int c = first + s * step;
-            if (c < n_chunks) issue(chunk_ptr[c], chunk_ptr[c + 1], s);
-        }
-    }
-    // chunk metadata runs one trip ahead in registers so its load latency is never exposed
-    int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0, ip0 = 0, ip1 = 0;
-    if (first < n_chunks) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
-    if (tid == 0) {
-        const int cn = first + (STAGES - 1) * step;
-        if (cn < n_chunks) { ip0 = chunk_ptr[cn]; ip1 = chunk_ptr[cn + 1]; }
-    }
-    uint32_t phase_bits = 0;                            // one parity bit per slot
-    int it = 0;
-    for (int c = first; c < n_chunks; c += step, ++it) {
-        const int slot = it % STAGES;
-        const int r0 = nr0, r1 = nr1, p0 = np0, p1 = np1;
-        // keep the ring full: chunk c + (STAGES-1)*step goes into the slot freed last trip
-        if (tid == 0) {
-            const int cn = c + (STAGES - 1) * step;
-            if (cn < n_chunks) issue(ip0, ip1, (it + STAGES - 1) % STAGES);
-            const int cnn = cn + step;
-            if (cnn < n_chunks) { ip0 = chunk_ptr[cnn]; ip1 = chunk_ptr[cnn + 1]; }
-        }
-        if (c + step < n_chunks) {
-            nr0 = chunk_row[c + step]; nr1 = chunk_row[c + step + 1];
-            np0 = chunk_ptr[c + step]; np1 = chunk_ptr[c + step + 1];
-        }
-        const int a0 = p0 & ~3;
-        if (r1 > r0) {
-            if (p1 - a0 <= CAP) {
-                double *vs = vals_s + (size_t)slot * CAP;
-                const int *cs = cols_s + (size_t)slot * CAP;
-                // per-row operands first: their latency overlaps the wait and the product phase
-                int rs[LZ_TMA_ROWS_PER_THREAD], re[LZ_TMA_ROWS_PER_THREAD];
-#pragma unroll
-                for (int u = 0; u < LZ_TMA_ROWS_PER_THREAD; ++u) {
-                    const int r = r0 + tid + u * THREADS;
-                    rs[u] = re[u] = 0;
-                    if (r < r1) { rs[u] = rowptr[r] - a0; re[u] = rowptr[r + 1] - a0; }
-                }
-                const int cnt = p1 - a0, cnt4 = cnt & ~3;
-                if (cnt4 > 0) {
-                    lz_mbar_wait(&full[slot], (phase_bits >> slot) & 1u);
-                    phase_bits ^= 1u << slot;
-                }
-                // tail (< 4 entries) that the 16-byte-granular bulk copies cannot carry
-                if (tid < cnt - cnt4) {
-                    const int k = cnt4 + tid;
-                    vs[k] = __dmul_rn(vals[a0 + k], epi.xs(__ldg(x + colidx[a0 + k])));
-                }
-                // products in place: all gathers of a thread are issued before the first use
-                constexpr int GPT = (CAP + THREADS - 1) / THREADS;     // gathers per thread, upper bound
-                double xv[GPT];
-#pragma unroll
-                for (int u = 0; u < GPT; ++u) {
-                    const int k = tid + u * THREADS;
-                    xv[u] = 0.0;
-                    if (k < cnt4) xv[u] = __ldg(x + cs[k]);
-                }
-#pragma unroll
-                for (int u = 0; u < GPT; ++u) {
-                    const int k = tid + u * THREADS;
-                    if (k < cnt4) vs[k] = __dmul_rn(vs[k], epi.xs(xv[u]));
-                }
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < LZ_TMA_ROWS_PER_THREAD; ++u) {
-                    const int r = r0 + tid + u * THREADS;
-                    if (r < r1) {
-                        const int s0 = rs[u], len = re[u] - rs[u];
-                        // short rows: up to 8 products fetched at once, summed left to right
-                        double pr[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) pr[k] = (k < len) ? vs[s0 + k] : 0.0;
-                        double t = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) if (k < len) t = __dadd_rn(t, pr[k]);
-                        for (int k = s0 + 8; k < re[u]; ++k) t = __dadd_rn(t, vs[k]);
-                        acc += epi.finish(r, t, y);
-                    }
-                }
-                for (int r = r0 + tid + LZ_TMA_ROWS_PER_THREAD * THREADS; r < r1; r += THREADS) {   // many short/empty rows
-                    const int s = rowptr[r] - a0, e = rowptr[r + 1] - a0;
-                    double t = 0.0;
-                    for (int k = s; k < e; ++k) t = __dadd_rn(t, vs[k]);
-                    acc += epi.finish(r, t, y);
-                }
-            } else {
-                // long-row chunk: walk global memory (warp per row, CTA per very long row)
-                const int lane = tid & 31, warp = tid >> 5;
-                for (int r = r0 + warp; r < r1; r += THREADS / 32) {
-                    const int s = rowptr[r], e = rowptr[r + 1];
-                    if (e - s > 4096) continue;
-                    double t = 0.0;
-                    for (int k = s + lane; k < e; k += 32) t += vals[k] * epi.xs(__ldg(x + colidx[k]));
-                    t = lz_warp_sum(t);
-                    if (lane == 0) acc += epi.finish(r, t, y);
-                }
-                for (int r = r0; r < r1; ++r) {
-                    const int s = rowptr[r], e = rowptr[r + 1];
-                    if (e - s <= 4096) continue;
-                    double t = 0.0;
-                    for (int k = s + tid; k < e; k += THREADS) t += vals[k] * epi.xs(__ldg(x + colidx[k]));
-                    t = lz_block_sum<THREADS>(t, red);
-                    if (tid == 0) acc += epi.finish(r, t, y);
-                }
-            }
-        }
-        __syncthreads();                               // slot may be refilled from here on
-    }
-    if (MODE == LZ_EPI_LANCZOS) {
-        acc = lz_block_sum<THREADS>(acc, red);
-        double total;
-        if (lz_grid_sum<THREADS, 1>(&acc, args.partials, args.ticket, red, &total)) {
-            if (tid == 0) {
-                *args.alpha_partial = total;
-                if (args.alpha_out) *args.alpha_out = total;
-            }
-        }
-    }
-}
-
-static inline size_t lz_tma_smem_bytes(int stages, int cap) { return (size_t)stages * cap * 12 + 8 * stages; }
-
-template <int MODE, int THREADS, int STAGES, int CAP>
-static inline int lz_launch_tma_variant(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int ctas_per_sm)
-{
-    static bool attr_set = false;
-    const size_t smem = lz_tma_smem_bytes(STAGES, CAP);
-    if (!attr_set) {
-        LZ_CUDA(cudaFuncSetAttribute(k_csr_spmv_tma<MODE, THREADS, STAGES, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    int grid = ctx->sm_count * ctas_per_sm;
-    if (grid > A->n_chunks) grid = A->n_chunks;
-    k_csr_spmv_tma<MODE, THREADS, STAGES, CAP><<<grid, THREADS, smem, ctx->stream>>>(
-        A->n_chunks, A->chunk_row, A->chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
-    return LZ_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
-// Warp-specialised variant of the TMA kernel: no CTA-wide barrier inside the chunk loop.
+// Warp-specialised streaming kernel: no CTA-wide barrier inside the chunk loop.
 //   warp 0          : producer -- waits for a free ring slot, issues the two bulk copies
 //   warps 1..GW     : gather   -- wait for the slice, turn it into products in place (x via LDG)
 //   warps GW+1..    : rows     -- wait for the products, add them per row, run the epilogue
@@ -639,29 +463,14 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
         const unsigned grid = (unsigned)((A->n_rows + LZ_SPMV_THREADS - 1) / LZ_SPMV_THREADS);
         k_ell4_spmv<MODE><<<grid, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->n_rows, A->ell_data, A->ell_idx, x, y, args);
     } else if (A->tma_ok) {
-        // A->cap is fixed when the schedule is built (lz_csr.cu); variant = dev-time tuning knob
-        // kernel shape per schedule (A->cap is fixed when the schedule is built, lz_csr.cu)
+        // fused modes: 1 producer + 3 gather + 5 row warps, 3-slot ring of 1024 entries, 5 CTAs per SM on the fine
+        // (768-entry) schedule.  A stand-alone SpMV (x not L2-resident from a preceding pass B) runs faster with
+        // 1 + 6 + 9 warps on the coarse (1536-entry) schedule.  LZ_SPMV_VARIANT=3 / 20 force coarse / fine for
+        // every mode (profiles/r01_spmv_variants.md).
         const int v = ctx->spmv_variant;
-        const int blk = 0;                       // strided chunk map: blocked ranges measured slower (profiles/r01_spmv_variants.md)
-        if (A->cap == 1024) {
-            // default: 1 producer + 3 gather + 5 row warps, 3-slot ring of 1024 entries, 5 CTAs per SM.
-            // A stand-alone SpMV (x not L2-resident from a preceding pass B) runs faster on the coarse schedule.
-            if (MODE == LZ_EPI_PLAIN && A->mm_chunk_row && v != 20) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, blk, true)));
-            else LZ_TRY((lz_launch_ws_variant<MODE, 3, 5, 3, 1024, 5>(ctx, A, x, y, args, 5, blk)));
-        } else if (A->cap == 2048) {
-            if (v == 7) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048, 2>(ctx, A, x, y, args, 2, 1)));
-            else if (v == 8) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 3, 2048, 3>(ctx, A, x, y, args, 3, 1)));
-            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, blk)));
-        } else if (A->cap == 1536) {
-            if (v == 19) LZ_TRY((lz_launch_ws_variant<MODE, 5, 8, 4, 1536, 3>(ctx, A, x, y, args, 3)));
-            else LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 4, 1536, 3>(ctx, A, x, y, args, 3)));
-        } else if (A->cap == 1792) {
-            if (v == 5) LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 4, 1792>(ctx, A, x, y, args, 2)));
-            else if (v == 6) LZ_TRY((lz_launch_ws_variant<MODE, 10, 9, 5, 1792>(ctx, A, x, y, args, 2)));
-            else LZ_TRY((lz_launch_ws_variant<MODE, 8, 7, 5, 1792>(ctx, A, x, y, args, 2)));
-        } else {
-            LZ_TRY((lz_launch_tma_variant<MODE, 1024, 2, 4096>(ctx, A, x, y, args, 2)));
-        }
+        const bool coarse = A->mm_chunk_row && (v == 3 || (MODE == LZ_EPI_PLAIN && v != 20));
+        if (coarse) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, 0, true)));
+        else LZ_TRY((lz_launch_ws_variant<MODE, 3, 5, 3, 1024, 5>(ctx, A, x, y, args, 5, 0, false)));
     } else {
         k_csr_spmv<MODE><<<A->n_chunks, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->chunk_row, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
     }
