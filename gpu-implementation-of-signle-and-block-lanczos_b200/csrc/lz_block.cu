@@ -497,6 +497,40 @@ __global__ void k_flag_init(int *flags) { flags[0] = 0x7fffffff; flags[2] = 0x7f
 
 extern "C" {
 
+__global__ void __launch_bounds__(256) k_euler_panel(int64_t count, double dt, double *__restrict__ U, const double *__restrict__ W)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < count) U[i] = fma(dt, W[i], U[i]);
+}
+
+// Block fdtd validator (methods/fdtd.hpp:33-56): U <- U + dt * A U, nsteps times; result = row lc of U.
+// Panels are kept row-major like everywhere inside the block path.
+int lz_fdtd_block(lz_ctx *ctx, const lz_matrix *A, const double *U0, int64_t ldu, int bw, int64_t nsteps, double t_end,
+                  int64_t lc, double *result_host)
+{
+    LZ_CHECK(ctx && A && U0 && result_host && nsteps >= 1 && bw >= 1 && bw <= 32, LZ_ERR_INVALID, "lz_fdtd_block: bad arguments");
+    const int64_t n = A->n_rows;
+    LZ_CHECK(A->n_cols == n && A->halo_lo == 0 && A->halo_hi == 0, LZ_ERR_INVALID, "lz_fdtd_block: operator must be square and unsharded");
+    LZ_CHECK(ldu >= n && lc >= 0 && lc < n, LZ_ERR_INVALID, "lz_fdtd_block: bad leading dimension or lc");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    const size_t panel = (size_t)((n * bw + 15) / 16 * 16);
+    void *work;
+    LZ_TRY(lz_ctx_workspace(ctx, sizeof(double) * panel * 2, &work));
+    double *U = (double *)work, *W = U + panel;
+    k_cm_to_rm<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, bw, U0, ldu, U);
+    LZ_LAUNCH_CHECK(ctx);
+    const double dt = t_end / (double)nsteps;
+    const int64_t count = n * bw;
+    for (int64_t i = 0; i < nsteps; ++i) {
+        LZ_TRY(spmm_rm(ctx, A, bw, U, W, nullptr, nullptr));
+        k_euler_panel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(count, dt, U, W);
+        LZ_LAUNCH_CHECK(ctx);
+    }
+    LZ_CUDA(cudaMemcpyAsync(result_host, U + lc * bw, sizeof(double) * bw, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
 int lz_spmm(lz_ctx *ctx, const lz_matrix *A, int b, const double *X, int64_t ldx, double *Y, int64_t ldy)
 {
     LZ_CHECK(ctx && A && X && Y && b >= 1, LZ_ERR_INVALID, "lz_spmm: bad arguments");

@@ -177,3 +177,85 @@ extern "C" int lz_ritz(int m, int bw, const double *alpha, const double *beta, c
     }
     return LZ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// expm of a small symmetric matrix.  The reference forms expm(T) as
+// V exp(Lambda) V^T from cusolverDnDsyevd (expm_cusolver, utils/lib_utils.hpp:542-590, and the
+// custom_mult kernel, kernels/dense_kernels.hpp:53-78: out[r,c] = sum_i V[r,i] exp(w_i) V[c,i]).
+// Same construction here, on the host: Householder tridiagonalisation, implicit QL with the full
+// eigenvector matrix, then the triple product.  Only the lower triangle of T is read (uplo = LOWER).
+// ---------------------------------------------------------------------------------------------
+static int sym_eig_full(int N, std::vector<double> &A /* col-major, destroyed */, std::vector<double> &d, std::vector<double> &Zt)
+{
+    for (int j = 0; j < N; ++j)
+        for (int i = j + 1; i < N; ++i) A[j + (size_t)i * N] = A[i + (size_t)j * N];
+    std::vector<double> e, Q;
+    if (N == 1) { d.assign(1, A[0]); Zt.assign(1, 1.0); return LZ_OK; }
+    householder_tridiag(N, A, d, e, Q);
+    // tridiag_ql carries rows of the accumulated transformation: row r of Zt = row r of Q, so that after
+    // the iteration Zt[r * N + i] = component r of eigenvector i
+    Zt.assign((size_t)N * N, 0.0);
+    for (int r = 0; r < N; ++r)
+        for (int j = 0; j < N; ++j) Zt[(size_t)r * N + j] = Q[r + (size_t)j * N];
+    if (!tridiag_ql(N, d, e, N, Zt)) {
+        lz_set_error("symmetric eigensolver: QL iteration did not converge");
+        return LZ_ERR_BREAKDOWN;
+    }
+    return LZ_OK;
+}
+
+extern "C" int lz_expm_sym(int n, double *T_host)
+{
+    LZ_CHECK(n >= 1 && T_host, LZ_ERR_INVALID, "lz_expm_sym: bad arguments");
+    LZ_CHECK(n <= 2048, LZ_ERR_UNSUPPORTED, "lz_expm_sym: dimension %d is too large for the host eigensolver", n);
+    std::vector<double> A(T_host, T_host + (size_t)n * n), d, Zt;
+    LZ_TRY(sym_eig_full(n, A, d, Zt));
+    std::vector<double> ex(n);
+    for (int i = 0; i < n; ++i) ex[i] = exp(d[i]);
+    for (int c = 0; c < n; ++c)
+        for (int r = 0; r < n; ++r) {
+            double s = 0.0;
+            const double *zr = &Zt[(size_t)r * n], *zc = &Zt[(size_t)c * n];
+            for (int i = 0; i < n; ++i) s += zr[i] * ex[i] * zc[i];
+            T_host[r + (size_t)c * n] = s;
+        }
+    return LZ_OK;
+}
+
+// solution = q^T expm(t_end T)[:, 0:bw] beta_0   (the harness post-processing, test_lanczos.cu:100-110 and
+// :270-283): bw = 1 gives the scalar beta_0 * sum_j expm(t_end T)[j,0] q[j]
+extern "C" int lz_lanczos_solution(int m, int bw, const double *alpha, const double *beta, const double *q, double t_end,
+                                   double *solution)
+{
+    LZ_CHECK(m >= 1 && bw >= 1 && alpha && beta && q && solution, LZ_ERR_INVALID, "lz_lanczos_solution: bad arguments");
+    const int N = m * bw;
+    LZ_CHECK(N <= 2048, LZ_ERR_UNSUPPORTED, "lz_lanczos_solution: T of dimension %d is too large", N);
+    std::vector<double> T((size_t)N * N, 0.0);
+    if (bw == 1) {
+        for (int i = 0; i < m; ++i) T[i + (size_t)i * N] = t_end * alpha[i];
+        for (int i = 0; i + 1 < m; ++i) T[(i + 1) + (size_t)i * N] = T[i + (size_t)(i + 1) * N] = t_end * beta[i + 1];
+    } else {
+        for (int blk = 0; blk < m; ++blk)
+            for (int i = 0; i < bw * bw; ++i) {
+                const int r = i % bw, c = i / bw;
+                T[(blk * bw + r) + (size_t)(blk * bw + c) * N] = t_end * alpha[(size_t)blk * bw * bw + i];
+                if (blk >= 1) {
+                    const double v = t_end * beta[(size_t)blk * bw * bw + i];
+                    T[((blk - 1) * bw + r) + (size_t)(blk * bw + c) * N] = v;
+                    T[(blk * bw + c) + (size_t)((blk - 1) * bw + r) * N] = v;
+                }
+            }
+    }
+    LZ_TRY(lz_expm_sym(N, T.data()));
+    // F1 = E[:, 0:bw] * beta_0 ; solution = q^T F1
+    for (int c = 0; c < bw; ++c) {
+        double s = 0.0;
+        for (int i = 0; i < N; ++i) {
+            double f = 0.0;
+            for (int k = 0; k < bw; ++k) f += T[i + (size_t)k * N] * (bw == 1 ? beta[0] : beta[k + (size_t)c * bw]);
+            s += q[i] * f;
+        }
+        solution[c] = s;
+    }
+    return LZ_OK;
+}

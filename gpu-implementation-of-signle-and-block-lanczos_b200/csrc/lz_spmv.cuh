@@ -20,7 +20,9 @@
 #pragma once
 #include "lz_common.cuh"
 
-enum { LZ_EPI_PLAIN = 0, LZ_EPI_LANCZOS = 1, LZ_EPI_SCALED = 2 };   // SCALED: gather scaling of LANCZOS, plain store
+// SCALED: gather scaling of LANCZOS, plain store.  EULER: y = x + dt * (A x), the time step of the fdtd
+// validator (methods/fdtd.hpp:17-25: spmv followed by Vector::add) in one pass.
+enum { LZ_EPI_PLAIN = 0, LZ_EPI_LANCZOS = 1, LZ_EPI_SCALED = 2, LZ_EPI_EULER = 3 };
 
 // Arguments of the fused Lanczos epilogue (pass A of step j):
 //   q_j[i]  = x_own[i] * invb[j]                 (lazy normalisation: the same product the reference
@@ -42,6 +44,7 @@ struct LzPassA {
     int first;              // step 0: no q_{-1} term
     double *partials;
     unsigned int *ticket;
+    double dt;              // EULER mode: step length
 };
 
 template <int MODE>
@@ -58,13 +61,14 @@ struct LzRowEpi {
         sx = 1.0; sprev = 0.0; beta = 0.0;
         x_own = args.x_own; u_prev = args.u_prev; vcol = args.vcol; vts = args.vts; qout = args.qout; lc = args.lc; first = args.first != 0;
         if (MODE == LZ_EPI_SCALED) sx = args.invb[args.j];
+        if (MODE == LZ_EPI_EULER) beta = args.dt;
         if (MODE == LZ_EPI_LANCZOS) {
             sx = args.invb[args.j];
             if (!first) { sprev = args.invb[args.j - 1]; beta = args.beta[args.j]; }
         }
     }
     // scale applied to every gathered x value
-    __device__ __forceinline__ double xs(double xv) const { return MODE != LZ_EPI_PLAIN ? __dmul_rn(xv, sx) : xv; }
+    __device__ __forceinline__ double xs(double xv) const { return (MODE == LZ_EPI_LANCZOS || MODE == LZ_EPI_SCALED) ? __dmul_rn(xv, sx) : xv; }
     // epilogue operands of row i (fetched early by the pipelined kernels)
     __device__ __forceinline__ void load(int64_t i, double &xo, double &up) const
     {
@@ -73,10 +77,12 @@ struct LzRowEpi {
             xo = x_own[i];
             if (!first) up = u_prev[i];
         }
+        if (MODE == LZ_EPI_EULER) xo = x_own[i];
     }
     // finish row i whose raw sum is t; returns the row's contribution to alpha
     __device__ __forceinline__ double finish(int64_t i, double t, double *__restrict__ y, double xo, double up) const
     {
+        if (MODE == LZ_EPI_EULER) { y[i] = fma(beta, t, xo); return 0.0; }
         if (MODE != LZ_EPI_LANCZOS) { y[i] = t; return 0.0; }
         const double qi = __dmul_rn(xo, sx);
         double w = t;

@@ -651,6 +651,36 @@ int lz_spmv(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y)
     return lz_spmv_any<LZ_EPI_PLAIN>(ctx, A, x, y, none);
 }
 
+// The fdtd validator of the harness (methods/fdtd.hpp:6-31): nsteps explicit Euler steps
+// u <- u + dt * A u, dt = t_end / nsteps, then u[lc].  The reference runs spmv + Vector::add per step
+// (two kernels, three vector passes); here one fused SpMV pass per step between two work vectors.
+int lz_fdtd_vector(lz_ctx *ctx, const lz_matrix *A, const double *u0, int64_t nsteps, double t_end, int64_t lc,
+                   double *result_host, double *u_out)
+{
+    LZ_CHECK(ctx && A && u0 && nsteps >= 1, LZ_ERR_INVALID, "lz_fdtd_vector: bad arguments");
+    const int64_t n = A->n_rows;
+    LZ_CHECK(A->n_cols == n && A->halo_lo == 0 && A->halo_hi == 0, LZ_ERR_INVALID, "lz_fdtd_vector: operator must be square and unsharded");
+    LZ_CHECK(lc >= -1 && lc < n && (lc >= 0) == (result_host != nullptr), LZ_ERR_INVALID, "lz_fdtd_vector: lc / result mismatch");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    const int64_t stride = round_up(n, 4);
+    void *work;
+    LZ_TRY(lz_ctx_workspace(ctx, sizeof(double) * (size_t)stride * 2, &work));
+    double *a = (double *)work, *b = a + stride;
+    LZ_CUDA(cudaMemcpyAsync(a, u0, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    LzPassA pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.dt = t_end / (double)nsteps;
+    for (int64_t i = 0; i < nsteps; ++i) {
+        pa.x_own = a;
+        LZ_TRY(lz_spmv_any<LZ_EPI_EULER>(ctx, A, a, b, pa));
+        std::swap(a, b);
+    }
+    if (u_out) LZ_CUDA(cudaMemcpyAsync(u_out, a, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (result_host) LZ_CUDA(cudaMemcpyAsync(result_host, a + lc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
 int lz_dot(lz_ctx *ctx, int64_t n, const double *x, const double *y, double *result_host)
 {
     LZ_CHECK(ctx && x && y && result_host && n > 0, LZ_ERR_INVALID, "lz_dot: bad arguments");

@@ -5,6 +5,7 @@
 // and the new options are real run-time flags:
 //   -N <grid points per dim>   -m <iterations>            (reference flags, :338-345)
 //   --matrix maxwell|lap2d|lap3d   --block <b>|--vector   --reorth none|full|dgks   --k <ritz pairs>
+//   --fdtd <steps> (run the fdtd validator and print the relative error, test_lanczos.cu:115-121, :287-299)   -T <T_end>
 //   --format ell|csr   --dump <file>  (alpha/beta/q in the parity tests' record format, for the parity tests)
 #ifndef N_COL
 #define N_COL 4
@@ -17,11 +18,12 @@
 #include "utils/lib_utils.hpp"
 #include "methods/vector_lanczos.hpp"
 #include "methods/block_lanczos.hpp"
+#include "methods/fdtd.hpp"
 #include "matrix_a/build_A_ell.hpp"
 #include "objects/tridiagonal_matrix.hpp"
 
 struct Options {
-    unsigned int N = 10, m = 5, k = 4, block = N_COL;
+    unsigned int N = 10, m = 5, k = 4, block = N_COL, fdtd_steps = 0;     // fdtd_steps = 0: skip the validator
     bool use_block = true, csr = false;
     std::string matrix = "maxwell", dump;
     double T_end = 1;
@@ -45,6 +47,9 @@ struct DeviceOperator {
     std::size_t rows = 0;
     lz_matrix *device_operator() const { return op; }
     std::size_t n_rows() const { return rows; }
+    // device-only operator: the Host branches of the drivers are never taken with it
+    void spmv(Vector<type_t> &, Vector<type_t> &) { std::cout << "implement later" << std::endl; std::abort(); }
+    void spmm(Dense_matrix<type_t> &, Dense_matrix<type_t> &) { std::cout << "implement later" << std::endl; std::abort(); }
 };
 
 template <typename type_t, typename Matrix>
@@ -76,6 +81,27 @@ void run_vector(Matrix &A, Vector<type_t> &b, const Options &o, unsigned int lc)
     Vector<type_t> qh = q.copy_to_host();
     put("alpha", 0, m, alpha.data(), 8); put("beta", 0, m, beta.data(), 8); put("q", 0, m, qh.data(), 8);
     put("theta", 0, k, theta.data(), 8);
+    // the approximate solution from T and q (test_lanczos.cu:97-110; the reference leaves T zero there,
+    // SURVEY appendix A-5 -- here T is assembled from alpha/beta)
+    Dense_matrix<type_t> T(m, m, MemorySpace::Host);
+    for (unsigned int i = 0; i < m; ++i) {
+        T(i + i * m) = alpha[i];
+        if (i + 1 < m) { T((i + 1) + i * m) = beta[i + 1]; T(i + (i + 1) * m) = beta[i + 1]; }
+    }
+    T.mult_scalar(o.T_end);
+    expm_cusolver(T);
+    Vector<type_t> e1(m, MemorySpace::Host);
+    copy_column_to_vector<type_t>(T, e1, 0);
+    type_t solution = e1.dot(qh);
+    solution = beta[0] * solution;
+    std::cout << "The solution for vector_lanczos " << std::endl << std::setprecision(14) << solution << std::endl;
+    put("solution", 0, 1, &solution, 8);
+    if (o.fdtd_steps) {                                                // :115-121
+        type_t fdtd_solution = fdtd_vector(A, b, o.fdtd_steps, o.T_end, lc);
+        std::cout << "Solution from fdtd " << fdtd_solution << std::endl;
+        std::cout << "Relative error for vector lanczos is " << std::abs(solution - fdtd_solution) / std::abs(fdtd_solution) << std::endl;
+        put("fdtd", 0, 1, &fdtd_solution, 8);
+    }
     CUBLAS_CHECK(cublasDestroy(cublasH));
 }
 
@@ -128,6 +154,32 @@ void run_block(Matrix &A, Dense_matrix<type_t> &B, const Options &o, unsigned in
     Dense_matrix<type_t> Th = T.copy_to_host();
     put("alpha", 0, a.size(), a.data(), 8); put("beta", 0, bt.size(), bt.data(), 8); put("q", 0, qh.size(), qh.data(), 8);
     put("theta", 0, k, theta.data(), 8); put("T", 0, Th.size(), Th.data(), 8);
+    // the approximate solution from T and q (test_lanczos.cu:266-283)
+    T.mult_scalar(o.T_end);
+    expm_cusolver(T);
+    Dense_matrix<type_t> F1(m * bw, bw, mem_cuda);
+    copy_columns_to_matrix<type_t>(T, F1, bw);
+    {
+        Dense_matrix<type_t> F0(F1);
+        mm_cublas(0, 1., F0, beta[0], F1, cublasH);                  // F1 = expm(T)[:, 0:b] * sqrtm(B^T B)
+    }
+    Vector<type_t> solution(bw, mem_cuda);
+    vm_cublas(F1, q, solution, cublasH);
+    std::cout << "Solution for block lanczos";
+    solution.print();
+    Vector<type_t> sh = solution.copy_to_host();
+    put("solution", 0, bw, sh.data(), 8);
+    if (o.fdtd_steps) {                                                // :287-299
+        std::cout << " start fdtd " << std::endl;
+        Vector<type_t> fdtd_solution = ftdt_block<type_t>(A, B, o.fdtd_steps, o.T_end, lc);
+        std::cout << "Solution from fdtd ";
+        fdtd_solution.print();
+        Vector<type_t> fh = fdtd_solution.copy_to_host();
+        put("fdtd", 0, bw, fh.data(), 8);
+        solution.sadd(1, -1, fdtd_solution);
+        type_t relative_error = solution.l2_norm() / fdtd_solution.l2_norm();
+        std::cout << "Relative error for block lanczos is " << relative_error << std::endl;
+    }
     CUBLAS_CHECK(cublasDestroy(cublasH));
     delete[] alpha;
     delete[] beta;
@@ -193,6 +245,8 @@ int main(int argc, char **argv)
         if (opt == "-N") o.N = (unsigned int)std::stod(next());
         else if (opt == "-m") o.m = (unsigned int)std::stod(next());
         else if (opt == "--k") o.k = (unsigned int)std::stod(next());
+        else if (opt == "--fdtd") o.fdtd_steps = (unsigned int)std::stod(next());
+        else if (opt == "-T") o.T_end = std::stod(next());
         else if (opt == "--matrix") o.matrix = next();
         else if (opt == "--block") { o.use_block = true; o.block = (unsigned int)std::stod(next()); }
         else if (opt == "--vector") o.use_block = false;

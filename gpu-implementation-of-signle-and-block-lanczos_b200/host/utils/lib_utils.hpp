@@ -85,6 +85,16 @@ inline void l2_norm_cublas(Vector<double> &vec, double *result, cublasHandle_t =
 }
 inline void mult_scalar_cublas(Vector<double> &vec, const double scalar, cublasHandle_t = nullptr) { vec.mult_scalar(scalar); }
 
+// T <- expm(T) = V exp(Lambda) V^T for the small symmetric projected matrix    (expm_cusolver :542-590 +
+// Dense_matrix::custom_mult; host arithmetic inside the library, lz_expm_sym)
+inline void expm_cusolver(Dense_matrix<double> &T)
+{
+    const bool dev = T.memory_space() == MemorySpace::CUDA;
+    Dense_matrix<double> h = dev ? T.copy_to_host() : T;
+    CUSOLVER_CHECK(lz_expm_sym((int)h.n_rows(), h.data()));
+    T = dev ? h.copy_to_device() : h;
+}
+
 // beta <- beta^{1/2}, beta_inv <- beta^{-1/2}      (sqrtm_cusolver :696-745, my_sqrtm_cusolver.hpp:366-376)
 inline void sqrtm_cusolver(Vector<double> &, Dense_matrix<double> &beta, Dense_matrix<double> &beta_inv, cusolver_args<double> &)
 {

@@ -77,6 +77,10 @@ def lib():
         "lz_vector_basis_copy": (i32, [vp, i32, i32, vp, i64]),
         "lz_block_lanczos": (i32, [vp, vp, vp, i64, i32, i32, i64, i32, vp, vp, vp]),
         "lz_ritz": (i32, [i32, i32, vp, vp, vp, i32, vp, vp]),
+        "lz_expm_sym": (i32, [i32, vp]),
+        "lz_lanczos_solution": (i32, [i32, i32, vp, vp, vp, dbl, vp]),
+        "lz_fdtd_vector": (i32, [vp, vp, vp, i64, dbl, i64, P(dbl), vp]),
+        "lz_fdtd_block": (i32, [vp, vp, vp, i64, i32, i64, dbl, i64, vp]),
         "lz_comm_unique_id": (i32, [vp]),
         "lz_comm_init": (i32, [vp, i32, i32, vp]),
         "lz_comm_destroy": (i32, [vp]),
@@ -305,3 +309,32 @@ def ritz(alpha, beta, k, bw=1, beta_last=None):
     check(lib().lz_ritz(m, bw, alpha.ctypes.data, beta.ctypes.data, None if bl is None else bl.ctypes.data, k,
                         theta.ctypes.data, resid.ctypes.data))
     return theta, resid
+
+
+def expm_sym(T):
+    """expm of a small symmetric matrix (host; V exp(Lambda) V^T as expm_cusolver does)."""
+    T = np.array(T, dtype=np.float64, order="F", copy=True)
+    check(lib().lz_expm_sym(T.shape[0], T.ctypes.data))
+    return T
+
+
+def lanczos_solution(alpha, beta, q, t_end=1.0, bw=1):
+    """q^T expm(t_end T)[:, :bw] beta_0: what the reference harness prints as the Lanczos solution."""
+    alpha = np.ascontiguousarray(alpha, np.float64); beta = np.ascontiguousarray(beta, np.float64)
+    q = np.ascontiguousarray(q, np.float64)
+    m = alpha.size // (bw * bw)
+    out = np.zeros(bw)
+    check(lib().lz_lanczos_solution(m, bw, alpha.ctypes.data, beta.ctypes.data, q.ctypes.data, float(t_end), out.ctypes.data))
+    return out if bw > 1 else float(out[0])
+
+
+def fdtd_vector(ctx, A, u0, nsteps, t_end=1.0, lc=0, u_out=None):
+    res = C.c_double(0.0)
+    check(lib().lz_fdtd_vector(ctx.h, A.h, _ptr(u0), nsteps, float(t_end), lc, C.byref(res), _ptr(u_out)))
+    return res.value
+
+
+def fdtd_block(ctx, A, U0, ldu, bw, nsteps, t_end=1.0, lc=0):
+    out = np.zeros(bw)
+    check(lib().lz_fdtd_block(ctx.h, A.h, _ptr(U0), ldu, bw, nsteps, float(t_end), lc, out.ctypes.data))
+    return out

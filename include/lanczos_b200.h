@@ -185,6 +185,26 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
 int lz_ritz(int m, int bw, const double *alpha_host, const double *beta_host,
             const double *beta_last_host, int k, double *theta_host, double *resid_host);
 
+/* ---- application path of the harness ---- */
+/* T <- expm(T) for a small symmetric matrix (n x n, column-major, host; only the lower triangle is read):
+ * V exp(Lambda) V^T, the construction of expm_cusolver + custom_mult (utils/lib_utils.hpp:542-590,
+ * kernels/dense_kernels.hpp:53-78).  Host arithmetic inside the library, n <= 2048. */
+int lz_expm_sym(int n, double *T_host);
+/* solution[bw] = q^T expm(t_end * T)[:, 0:bw] beta_0 with T assembled from alpha/beta exactly as
+ * Assemble_T does (test_lanczos.cu:100-110 for bw = 1, :270-283 for blocks).  alpha_host: m blocks,
+ * beta_host: beta_0 .. beta_{m-1} (at least m blocks), q_host: the m*bw receiver-row entries. */
+int lz_lanczos_solution(int m, int bw, const double *alpha_host, const double *beta_host, const double *q_host,
+                        double t_end, double *solution_host);
+/* fdtd validator (methods/fdtd.hpp:6-31): nsteps explicit Euler steps u <- u + (t_end/nsteps) A u from u0
+ * (device, n, not modified), one fused SpMV pass per step; *result_host = u[lc] (lc = -1 and NULL to skip),
+ * u_out (device, n) receives the final vector when not NULL. */
+int lz_fdtd_vector(lz_ctx *ctx, const lz_matrix *A, const double *u0, int64_t nsteps, double t_end, int64_t lc,
+                   double *result_host, double *u_out);
+/* block variant (ftdt_block, methods/fdtd.hpp:33-56): U0 column-major n x bw with leading dimension ldu;
+ * result_host[bw] = row lc of the final panel. */
+int lz_fdtd_block(lz_ctx *ctx, const lz_matrix *A, const double *U0, int64_t ldu, int bw, int64_t nsteps,
+                  double t_end, int64_t lc, double *result_host);
+
 /* ---- multi-GPU: one process per GPU, rows of A and of every Krylov vector sharded ---- */
 /* opaque 128-byte NCCL id minted by rank 0 and broadcast by the launcher (torch.distributed) */
 int lz_comm_unique_id(void *id128_host);

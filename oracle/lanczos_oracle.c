@@ -408,3 +408,67 @@ void orc_assemble_T(int m, int bw, const double *alpha, const double *beta, doub
             }
         }
 }
+
+/* ---- application path -------------------------------------------------------- */
+
+void orc_expm_sym(int n, double *T)
+{
+    double *A = (double *)malloc(sizeof(double) * n * n), *V = (double *)malloc(sizeof(double) * n * n);
+    double *w = (double *)malloc(sizeof(double) * n);
+    /* syevd with uplo = LOWER reads the lower triangle only (lib_utils.hpp:556) */
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) A[i + j * n] = i >= j ? T[i + j * n] : T[j + i * n];
+    orc_jacobi_eig(n, A, w, V);
+    for (int col = 0; col < n; ++col)
+        for (int row = 0; row < n; ++row) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s += V[row + i * n] * exp(w[i]) * V[col + i * n];   /* dense_kernels.hpp:64-69 */
+            T[row + col * n] = s;
+        }
+    free(A); free(V); free(w);
+}
+
+void orc_lanczos_solution(int m, int bw, const double *alpha, const double *beta, const double *q, double t_end,
+                          double *solution)
+{
+    const int N = m * bw;
+    double *T = (double *)calloc((size_t)N * N, sizeof(double));
+    orc_assemble_T(m, bw, alpha, beta, T);                                  /* test_lanczos.cu:270 */
+    for (int i = 0; i < N * N; ++i) T[i] *= t_end;                          /* :271 */
+    orc_expm_sym(N, T);                                                     /* :272 */
+    for (int c = 0; c < bw; ++c) {                                          /* :275-283 */
+        double s = 0.0;
+        for (int i = 0; i < N; ++i) {
+            double f = 0.0;
+            for (int k = 0; k < bw; ++k) f += T[i + (size_t)k * N] * beta[k + c * bw];
+            s += q[i] * f;
+        }
+        solution[c] = s;
+    }
+    free(T);
+}
+
+void orc_fdtd_vector(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *vals, double *u,
+                     int64_t nsteps, double t_end)
+{
+    const double dt = t_end / (double)nsteps;
+    double *dudt = (double *)malloc(sizeof(double) * n);
+    for (int64_t s = 0; s < nsteps; ++s) {
+        orc_csr_spmv(n, rowptr, colidx, vals, u, dudt);                     /* fdtd.hpp:21 */
+        for (int64_t i = 0; i < n; ++i) u[i] = u[i] + dt * dudt[i];         /* :22 */
+    }
+    free(dudt);
+}
+
+void orc_fdtd_block(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *vals, int b, double *U,
+                    int64_t ld, int64_t nsteps, double t_end)
+{
+    const double dt = t_end / (double)nsteps;
+    double *dU = (double *)malloc(sizeof(double) * ld * b);
+    for (int64_t s = 0; s < nsteps; ++s) {
+        orc_csr_spmm(n, rowptr, colidx, vals, b, U, ld, dU, ld);            /* fdtd.hpp:47 */
+        for (int c = 0; c < b; ++c)
+            for (int64_t i = 0; i < n; ++i) U[i + c * ld] = U[i + c * ld] + dt * dU[i + c * ld];   /* :48 */
+    }
+    free(dU);
+}

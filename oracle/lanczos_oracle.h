@@ -82,6 +82,20 @@ int orc_block_lanczos(int64_t n, const int32_t *rowptr, const int32_t *colidx, c
  * T: (m*bw)^2 column-major, zero-filled by the callee. */
 void orc_assemble_T(int m, int bw, const double *alpha, const double *beta, double *T);
 
+/* expm of a small symmetric matrix as the reference forms it: syevd then out[r,c] = sum_i V[r,i] exp(w_i) V[c,i]
+ * (expm_cusolver, utils/lib_utils.hpp:542-590; custom_mult, kernels/dense_kernels.hpp:53-78).  In place. */
+void orc_expm_sym(int n, double *T);
+/* the harness post-processing (test_lanczos.cu:100-110, :270-283): T = t_end * Assemble_T(alpha, beta),
+ * F1 = expm(T)[:, 0:bw] * beta_0, solution = F1^T q.  beta holds beta_0 .. beta_{m-1}. */
+void orc_lanczos_solution(int m, int bw, const double *alpha, const double *beta, const double *q, double t_end,
+                          double *solution);
+/* methods/fdtd.hpp:6-31: nsteps times { dudt = A u; u += dt * dudt }, dt = t_end / nsteps; u in place */
+void orc_fdtd_vector(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *vals, double *u,
+                     int64_t nsteps, double t_end);
+/* methods/fdtd.hpp:33-56, U column-major n x b with leading dimension ld, in place */
+void orc_fdtd_block(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *vals, int b, double *U,
+                    int64_t ld, int64_t nsteps, double t_end);
+
 /* thread control for the baseline timing (1 => strictly sequential, reference summation order) */
 void orc_set_threads(int t);
 int orc_get_threads(void);

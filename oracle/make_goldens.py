@@ -8,7 +8,9 @@ The fixtures pin (a) the Maxwell operator built by matrix_a/build_A_ell.hpp (D, 
 reference's column-major ELL layout) at N = 2, 3, 5, 10, (b) glibc-rand() start vectors exactly as
 test_lanczos.cu draws them (one rand() consumed for lc first), and (c) the alpha/beta/q series of
 methods/vector_lanczos.hpp:20-66 (m = 100) and methods/block_lanczos.hpp:105-166 (N_COL = 4 and 8,
-m = 25) executed over the reference's Host containers.
+m = 25) executed over the reference's Host containers, and (d) the harness' fdtd validator
+(methods/fdtd.hpp) run over the same containers: u[lc] after 100000 Euler steps (vector) and row lc of U
+after 20000 steps (block).
 """
 import os
 import sys
@@ -33,11 +35,13 @@ def main():
                             W_width=d["W_width"], ell_data=d["ell_data"], ell_idx=d["ell_idx"])
     d = orc.run_ref("vector", 10, 100)
     np.savez_compressed(os.path.join(GOLD, "maxwell_N10_vector_m100.npz"),
-                        N=10, m=100, lc=d["lc"], b=d["b"], alpha=d["alpha"], beta=d["beta"], q=d["q"])
+                        N=10, m=100, lc=d["lc"], b=d["b"], alpha=d["alpha"], beta=d["beta"], q=d["q"],
+                        fdtd_steps=d["fdtd_steps"], fdtd_u_lc=d["fdtd_u_lc"])
     for nc in (4, 8):
         d = orc.run_ref("block", 10, 25, n_col=nc)
         np.savez_compressed(os.path.join(GOLD, "maxwell_N10_block%d_m25.npz" % nc),
-                            N=10, m=25, lc=d["lc"], n_col=nc, B=d["B"], alpha=d["alpha"], beta=d["beta"], q=d["q"])
+                            N=10, m=25, lc=d["lc"], n_col=nc, B=d["B"], alpha=d["alpha"], beta=d["beta"], q=d["q"],
+                            fdtd_steps=d["fdtd_steps"], fdtd_row_lc=d["fdtd_row_lc"])
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -60,6 +60,10 @@ def lib():
     L.orc_block_lanczos.restype = i32
     L.orc_block_lanczos.argtypes = [i64, _i32p, _i32p, _f64p, _f64p, i32, i32, i64, i32, _f64p, _f64p, _f64p, vp]
     L.orc_assemble_T.argtypes = [i32, i32, _f64p, _f64p, _f64p]
+    L.orc_expm_sym.argtypes = [i32, _f64p]
+    L.orc_lanczos_solution.argtypes = [i32, i32, _f64p, _f64p, _f64p, dbl, _f64p]
+    L.orc_fdtd_vector.argtypes = [i64, _i32p, _i32p, _f64p, _f64p, i64, dbl]
+    L.orc_fdtd_block.argtypes = [i64, _i32p, _i32p, _f64p, i32, _f64p, i64, i64, dbl]
     L.orc_set_threads.argtypes = [i32]
     L.orc_get_threads.restype = i32
     _LIB = L
@@ -218,6 +222,43 @@ def ritz(alpha, beta, k, beta_last=None):
         bw = bl.shape[0]
         res = np.linalg.norm(bl @ Y[-bw:, sel], axis=0)
     return w[sel], res
+
+
+def expm_sym(T):
+    T = np.array(T, np.float64)
+    n = T.shape[0]
+    t = np.ascontiguousarray(T.T).reshape(-1).copy()          # column-major
+    lib().orc_expm_sym(n, t)
+    return t.reshape(n, n).T
+
+
+def lanczos_solution(alpha, beta, q, t_end=1.0):
+    """alpha (m,bw,bw) / beta (>=m,bw,bw) or 1-D series; returns the bw-vector (scalar for bw = 1)."""
+    alpha, beta = np.asarray(alpha, np.float64), np.asarray(beta, np.float64)
+    if alpha.ndim == 1:
+        alpha, beta = alpha.reshape(-1, 1, 1), beta.reshape(-1, 1, 1)
+    m, bw = alpha.shape[0], alpha.shape[1]
+    a = np.ascontiguousarray(alpha.transpose(0, 2, 1)).reshape(-1)
+    b = np.ascontiguousarray(beta[:m].transpose(0, 2, 1)).reshape(-1)
+    out = np.zeros(bw)
+    lib().orc_lanczos_solution(m, bw, a, b, np.ascontiguousarray(q, np.float64), float(t_end), out)
+    return out if bw > 1 else float(out[0])
+
+
+def fdtd_vector(csr, u0, nsteps, t_end=1.0):
+    rp, ci, va = csr
+    u = np.array(u0, np.float64).copy()
+    lib().orc_fdtd_vector(len(rp) - 1, rp, ci, va, u, nsteps, float(t_end))
+    return u
+
+
+def fdtd_block(csr, U0, nsteps, t_end=1.0):
+    """U0: (n, b) array; returns (n, b)."""
+    rp, ci, va = csr
+    n, b = U0.shape
+    U = np.ascontiguousarray(np.asarray(U0, np.float64).T).reshape(-1).copy()
+    lib().orc_fdtd_block(n, rp, ci, va, b, U, n, nsteps, float(t_end))
+    return U.reshape(b, n).T
 
 
 # ------------------------------------------------------------------------------- _ref dumps

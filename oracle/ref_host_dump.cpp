@@ -137,6 +137,21 @@ int main(int argc, char **argv)
         put_f64("alpha", m, alpha.data());
         put_f64("beta", m, beta.data());
         put_f64("q", m, q.data());
+        {   /* methods/fdtd.hpp:6-31 call for call (spmv(A,u,dudt) -> the Host member), T_end = 1,
+               Nsteps = 100000 as in test_lanczos.cu:118 */
+            const unsigned int Nsteps = 100000;
+            const double T_end = 1;
+            T dt = T_end / Nsteps;
+            Vector<T> dudt(b);
+            Vector<T> u(b);
+            for (unsigned int i = 0; i < Nsteps; ++i) {
+                A.spmv(u, dudt);
+                u.add(dt, dudt);
+            }
+            T result = u(lc);
+            put_i64("fdtd_steps", Nsteps);
+            put_f64("fdtd_u_lc", 1, &result);
+        }
     } else if (mode == "block") {
         Dense_matrix<T> B = random_matrix_B<T>(n);       /* test_lanczos.cu:154 (unpadded) */
         put_f64("B", (uint64_t)n * N_COL, B.data());
@@ -194,6 +209,22 @@ int main(int argc, char **argv)
         put_f64("alpha", a.size(), a.data());
         put_f64("beta", bt.size(), bt.data());
         put_f64("q", m * N_COL, q.data());
+        {   /* ftdt_block, methods/fdtd.hpp:33-56, call for call; 20000 steps keep the minting run short
+               (the harness default of 10^6, test_lanczos.cu:336, is the same loop) */
+            const unsigned int Nsteps = 20000;
+            const double T_end = 1;
+            T dt = T_end / Nsteps;
+            Dense_matrix<T> dUdT(B);
+            Dense_matrix<T> U(B);
+            for (unsigned int i = 0; i < Nsteps; ++i) {
+                A.spmm(U, dUdT);
+                U.sadd(1, dt, dUdT);
+            }
+            std::vector<T> row(N_COL);
+            for (unsigned int c = 0; c < N_COL; ++c) row[c] = U(lc + c * U.n_rows());
+            put_i64("fdtd_steps", Nsteps);
+            put_f64("fdtd_row_lc", N_COL, row.data());
+        }
     }
     std::fclose(g_out);
     return 0;

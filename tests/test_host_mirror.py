@@ -79,3 +79,27 @@ def test_harness_laplacian_full_reorth(host_built, orc, tmp_path):
     ref = orc.vector_lanczos(orc.lap2d(200, 200), orc.start_vector(200 * 200), 80, reorth=1)
     assert np.max(np.abs(d["alpha"][:50] - ref["alpha"][:50])) < 1e-10 * np.abs(ref["alpha"]).max()
     assert np.max(np.abs(d["beta"][:50] - ref["beta"][:50]) / ref["beta"][:50]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_harness_vector_application_path(host_built, orc, tmp_path):
+    """The post-processing of test_lanczos.cu:97-123 through the mirror: solution from expm(T) and q, the fdtd
+    validator with the reference's 100000 steps, and their relative error."""
+    stdout, out = run_harness(host_built, ["-N", "10", "-m", "100", "--vector", "--fdtd", "100000"], tmp_path)
+    d, g = orc.read_dump(out), load_gold("maxwell_N10_vector_m100.npz")
+    assert abs(d["fdtd"][0] - g["fdtd_u_lc"][0]) < 1e-11 * abs(g["fdtd_u_lc"][0])
+    assert abs(d["solution"][0] - orc.lanczos_solution(g["alpha"], g["beta"], g["q"], 1.0)) < 1e-10 * abs(d["solution"][0])
+    assert abs(d["solution"][0] - d["fdtd"][0]) < 1e-9 * abs(d["fdtd"][0])
+    assert "Relative error for vector lanczos is" in stdout and "Solution from fdtd" in stdout
+
+
+@pytest.mark.gpu
+def test_harness_block_application_path(host_built, orc, tmp_path):
+    stdout, out = run_harness(host_built, ["-N", "10", "-m", "25", "--block", "4", "--fdtd", "20000"], tmp_path)
+    d, g = orc.read_dump(out), load_gold("maxwell_N10_block4_m25.npz")
+    assert np.max(np.abs(d["fdtd"] - g["fdtd_row_lc"])) < 1e-11 * np.max(np.abs(g["fdtd_row_lc"]))
+    a = g["alpha"].reshape(25, 4, 4).transpose(0, 2, 1)
+    b = g["beta"].reshape(26, 4, 4).transpose(0, 2, 1)
+    ref = orc.lanczos_solution(a, b, g["q"], 1.0)
+    assert np.max(np.abs(d["solution"] - ref)) < 1e-9 * np.max(np.abs(ref))
+    assert "Relative error for block lanczos is" in stdout
