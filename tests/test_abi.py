@@ -59,3 +59,25 @@ def test_product_never_imports_oracle():
                 if re.search(r"oracle|liboracle|orc_", txt):
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_host_entry_points_validate_arguments():
+    """Host-side entry points (no device needed): error codes instead of crashes on bad input."""
+    import ctypes as C
+    import numpy as np
+    import lanczos_b200 as lz
+    L = lz.lib()
+    a = np.zeros(4); b = np.ones(4); th = np.zeros(2); rs = np.zeros(2)
+    assert L.lz_ritz(0, 1, a.ctypes.data, b.ctypes.data, None, 1, th.ctypes.data, rs.ctypes.data) != 0      # m < 1
+    assert L.lz_ritz(4, 1, a.ctypes.data, b.ctypes.data, None, 9, th.ctypes.data, rs.ctypes.data) != 0      # k > dim(T)
+    assert L.lz_expm_sym(0, a.ctypes.data) != 0 and L.lz_expm_sym(2, None) != 0
+    assert L.lz_expm_sym(4096, a.ctypes.data) != 0                                                          # too large for the host solver
+    assert L.lz_lanczos_solution(2, 1, a.ctypes.data, b.ctypes.data, None, 1.0, th.ctypes.data) != 0
+    lo, hi = C.c_int64(), C.c_int64()
+    assert L.lz_partition_rows(100, 7, 2, 0, C.byref(lo), C.byref(hi)) != 0                                 # rows not a multiple of the granule
+    assert L.lz_partition_rows(64, 32, 4, 0, C.byref(lo), C.byref(hi)) != 0                                 # fewer granules than ranks
+    assert L.lz_partition_rows(64, 8, 4, 3, C.byref(lo), C.byref(hi)) == 0 and (lo.value, hi.value) == (48, 64)
+    assert b"lz_" in L.lz_last_error() or len(L.lz_last_error()) > 0
+    # expm of a diagonal matrix is the elementwise exponential of the diagonal
+    D = np.diag([0.5, -1.0, 2.0])
+    assert np.allclose(lz.expm_sym(D), np.diag(np.exp([0.5, -1.0, 2.0])), rtol=1e-14, atol=1e-15)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # plain SpMV and fused Lanczos step per kernel variant (dev-time knob LZ_SPMV_VARIANT)
-for v in ${VARIANTS:-0 3 11}; do
+for v in ${VARIANTS:-0 3 20}; do
   LZ_SPMV_VARIANT=$v timeout 200 python tools/devbench.py spmv lanczos > /tmp/o.log 2>&1 || tail -3 /tmp/o.log
   python - <<PY
 import json

@@ -1,5 +1,5 @@
 #!/bin/bash
-for v in ${VARIANTS:-0 1 2 3 4}; do
+for v in ${VARIANTS:-0 3 20}; do   # 0 default, 3 coarse schedule everywhere, 20 fine schedule everywhere
   LZ_SPMV_VARIANT=$v timeout 200 python tools/run_configs.py cfg3v cfg2v > /tmp/o.log 2>&1 || tail -3 /tmp/o.log
   python - <<PY
 import json
