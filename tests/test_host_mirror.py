@@ -103,3 +103,20 @@ def test_harness_block_application_path(host_built, orc, tmp_path):
     ref = orc.lanczos_solution(a, b, g["q"], 1.0)
     assert np.max(np.abs(d["solution"] - ref)) < 1e-9 * np.max(np.abs(ref))
     assert "Relative error for block lanczos is" in stdout
+
+
+def test_host_space_fdtd_and_expm_bit_identical_to_reference_host(host_built, orc, tmp_path):
+    """Host-space branches of the mirror (no GPU): fdtd_vector / ftdt_block over the mirror's Host containers
+    reproduce the reference's own Host run bit for bit (goldens), expm_cusolver matches scipy."""
+    import scipy.linalg
+    out = str(tmp_path / "hs.bin")
+    g = load_gold("maxwell_N10_vector_m100.npz")
+    subprocess.run([os.path.join(host_built, "host_space_check"), "vector", "10", str(int(g["fdtd_steps"])), out], check=True)
+    d = orc.read_dump(out)
+    assert d["lc"] == int(g["lc"]) and d["fdtd"][0] == g["fdtd_u_lc"][0]
+    Ti, To = d["expm_in"].reshape(12, 12).T, d["expm_out"].reshape(12, 12).T
+    assert np.max(np.abs(To - scipy.linalg.expm(Ti))) < 1e-12 * np.max(np.abs(To))
+    gb = load_gold("maxwell_N10_block4_m25.npz")
+    subprocess.run([os.path.join(host_built, "host_space_check"), "block", "10", str(int(gb["fdtd_steps"])), out], check=True)
+    d = orc.read_dump(out)
+    assert np.array_equal(d["fdtd"], gb["fdtd_row_lc"])
