@@ -141,3 +141,49 @@ def test_sharded_recurrence_gloo_world2(tmp_path):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
         assert r.stdout.count("ok") == world
+
+
+GLOO_BLOCK_WORKER = GLOO_WORKER.split("b = orc.start_vector(n)[r0:r1]")[0] + r'''
+# ---- block recurrence (methods/block_lanczos.hpp:105-166) over the row slabs: panels are nl x bw, the halo
+# exchange moves bw-wide boundary planes, every b x b Gram block is all-reduced (what lz_block_lanczos does
+# on a context with a communicator)
+bw, mb = 3, 6
+def allsum_mat(M):
+    t = torch.from_numpy(np.ascontiguousarray(M)); dist.all_reduce(t); return t.numpy()
+def halo_panel(U):
+    return np.stack([halo(np.ascontiguousarray(U[:, c])) for c in range(bw)], axis=1)
+def local_spmm(Xbuf):
+    return np.stack([local_spmv(np.ascontiguousarray(Xbuf[:, c])) for c in range(bw)], axis=1)
+Bfull = orc.start_block(n, bw)
+B = Bfull[r0:r1]
+alpha, beta = np.zeros((mb, bw, bw)), np.zeros((mb + 1, bw, bw))
+S, Sinv = orc.sqrtm(allsum_mat(B.T @ B)); beta[0] = S
+Q0 = B @ Sinv
+W = local_spmm(halo_panel(Q0))
+G = allsum_mat(W.T @ Q0); alpha[0] = 0.5 * (G + G.T)
+W = W - Q0 @ alpha[0]
+for j in range(1, mb):
+    S, Sinv = orc.sqrtm(allsum_mat(W.T @ W)); beta[j] = S
+    Q1 = W @ Sinv
+    W = local_spmm(halo_panel(Q1)) - Q0 @ beta[j]
+    G = allsum_mat(W.T @ Q1); alpha[j] = 0.5 * (G + G.T)
+    W = W - Q1 @ alpha[j]
+    Q0 = Q1
+ref = orc.block_lanczos((rp, ci, va), Bfull, mb)
+assert np.max(np.abs(alpha - ref["alpha"])) < 1e-10 * np.abs(ref["alpha"]).max(), "block alpha"
+assert np.max(np.abs(beta[:mb] - ref["beta"][:mb])) < 1e-10 * np.abs(ref["beta"][:mb]).max(), "block beta"
+print("rank %d ok" % rank)
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_block_recurrence_gloo_world2(tmp_path):
+    """Block path, N > 1 host logic on CPU: slab partition, bw-wide halo planes and all-reduced b x b Gram
+    blocks reproduce the global block recurrence of the oracle (gloo, world_size 2)."""
+    script = tmp_path / "worker_block.py"
+    script.write_text(GLOO_BLOCK_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
