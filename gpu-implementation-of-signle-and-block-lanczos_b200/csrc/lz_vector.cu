@@ -332,7 +332,7 @@ static inline void cgs_fused_shape(int K, int *ctas, int *nb)
 {
     const size_t budget = 214 * 1024;
     static int order = -1;
-    if (order < 0) { const char *e = getenv("LZ_CGS_SHAPE_ORDER"); order = e ? atoi(e) : 1; }
+    if (order < 0) { const char *e = getenv("LZ_CGS_SHAPE_ORDER"); order = e ? atoi(e) : 1; if (order < 0 || order > 2) order = 1; }
     static const int cand[3][6][2] = {
         {{4, 2}, {2, 2}, {2, 1}, {1, 2}, {1, 2}, {1, 2}},
         {{4, 2}, {4, 1}, {3, 1}, {2, 1}, {1, 2}, {1, 2}},
