@@ -4,6 +4,7 @@
 // matrix.  Host-only: needs no GPU.  The CPU test suite compares the output with the goldens minted from
 // the reference's own Host code (bit for bit).
 // usage: host_space_check <vector|block> N steps out.bin
+//        host_space_check mtx <file.mtx> 0 out.bin     (MatrixMarket reader + Host-space Csr_matrix::spmv)
 #ifndef N_COL
 #define N_COL 4
 #endif
@@ -13,6 +14,7 @@
 #include "utils/lib_utils.hpp"
 #include "methods/fdtd.hpp"
 #include "matrix_a/build_A_ell.hpp"
+#include "matrix_a/matrix_market.hpp"
 
 static FILE *g_out;
 static void put(const char *name, int dtype, uint64_t count, const void *data, size_t elt)
@@ -27,9 +29,24 @@ int main(int argc, char **argv)
 {
     if (argc < 5) return 2;
     const std::string mode = argv[1];
-    const unsigned int N = (unsigned int)std::atoi(argv[2]), steps = (unsigned int)std::atoi(argv[3]);
     g_out = std::fopen(argv[4], "wb");
     if (!g_out) return 3;
+    if (mode == "mtx") {
+        Csr_matrix<double> M = read_matrix_market<double>(argv[2]);
+        const Csr_matrix<double> &Mc = M;
+        int64_t dims[3] = {(int64_t)M.n_rows(), (int64_t)M.n_cols(), (int64_t)M.nnz()};
+        put("dims", 2, 3, dims, 8);
+        put("row_ptr", 1, M.n_rows() + 1, Mc.row_ptr(), 4);
+        put("col_idx", 1, M.nnz(), Mc.col_idx(), 4);
+        put("data", 0, M.nnz(), Mc.data(), 8);
+        Vector<double> x((unsigned int)M.n_cols(), MemorySpace::Host), y((unsigned int)M.n_rows(), MemorySpace::Host);
+        for (unsigned int i = 0; i < M.n_cols(); ++i) x(i) = 1.0 + 0.25 * i;
+        M.spmv(x, y);
+        put("y", 0, M.n_rows(), y.data(), 8);
+        std::fclose(g_out);
+        return 0;
+    }
+    const unsigned int N = (unsigned int)std::atoi(argv[2]), steps = (unsigned int)std::atoi(argv[3]);
     const unsigned int lc = 1 + (rand() % 100);                       // test_lanczos.cu:326
     auto info = Matrix_A<double>(N, N, N);
     Ell_matrix<double> A = info.first, W = info.second;

@@ -4,7 +4,7 @@
 // Plain C++ linked against liblanczos_b200.so; N_COL and USE_BLAS keep their compile-time meaning,
 // and the new options are real run-time flags:
 //   -N <grid points per dim>   -m <iterations>            (reference flags, :338-345)
-//   --matrix maxwell|lap2d|lap3d   --block <b>|--vector   --reorth none|full|dgks   --k <ritz pairs>
+//   --matrix maxwell|lap2d|lap3d|mtx (--file <MatrixMarket file>)   --block <b>|--vector   --reorth none|full|dgks   --k <ritz pairs>
 //   --fdtd <steps> (run the fdtd validator and print the relative error, test_lanczos.cu:115-121, :287-299)   -T <T_end>
 //   --format ell|csr   --dump <file>  (alpha/beta/q in the parity tests' record format, for the parity tests)
 #ifndef N_COL
@@ -20,12 +20,13 @@
 #include "methods/block_lanczos.hpp"
 #include "methods/fdtd.hpp"
 #include "matrix_a/build_A_ell.hpp"
+#include "matrix_a/matrix_market.hpp"
 #include "objects/tridiagonal_matrix.hpp"
 
 struct Options {
     unsigned int N = 10, m = 5, k = 4, block = N_COL, fdtd_steps = 0;     // fdtd_steps = 0: skip the validator
     bool use_block = true, csr = false;
-    std::string matrix = "maxwell", dump;
+    std::string matrix = "maxwell", dump, file;
     double T_end = 1;
 };
 
@@ -212,6 +213,23 @@ void test_Lanczos(const Options &o, unsigned int lc)
         }
         return;
     }
+    if (o.matrix == "mtx") {                                           // symmetric operator from a MatrixMarket file
+        Csr_matrix<type_t> A = read_matrix_market<type_t>(o.file).copy_to_device();
+        if (A.n_rows() != A.n_cols()) { std::cout << "the operator must be square" << std::endl; std::abort(); }
+        std::cout << " the size of the problem is " << std::endl;
+        print(A.n_rows());
+        lc = lc % A.n_rows();
+        if (o.use_block) {
+            Dense_matrix<type_t> B(A.n_rows(), o.block, MemorySpace::CUDA);
+            AssertCuda(lz_gen_start_block(lanczos_context(), (int64_t)A.n_rows(), (int)o.block, (int64_t)A.n_rows(), 0x5EED, B.data()));
+            run_block<type_t>(A, B, o, lc);
+        } else {
+            Vector<type_t> b(A.n_rows(), MemorySpace::CUDA);
+            AssertCuda(lz_gen_start_vector(lanczos_context(), (int64_t)A.n_rows(), 0x5EED, b.data()));
+            run_vector<type_t>(A, b, o, lc);
+        }
+        return;
+    }
     DeviceOperator<type_t> A;
     if (o.matrix == "lap2d") { AssertCuda(lz_gen_laplacian2d(lanczos_context(), o.N, o.N, &A.op)); A.rows = (std::size_t)o.N * o.N; }
     else if (o.matrix == "lap3d") { AssertCuda(lz_gen_laplacian3d(lanczos_context(), o.N, o.N, o.N, &A.op)); A.rows = (std::size_t)o.N * o.N * o.N; }
@@ -248,6 +266,7 @@ int main(int argc, char **argv)
         else if (opt == "--fdtd") o.fdtd_steps = (unsigned int)std::stod(next());
         else if (opt == "-T") o.T_end = std::stod(next());
         else if (opt == "--matrix") o.matrix = next();
+        else if (opt == "--file") o.file = next();
         else if (opt == "--block") { o.use_block = true; o.block = (unsigned int)std::stod(next()); }
         else if (opt == "--vector") o.use_block = false;
         else if (opt == "--format") o.csr = next() == "csr";

@@ -120,3 +120,42 @@ def test_host_space_fdtd_and_expm_bit_identical_to_reference_host(host_built, or
     subprocess.run([os.path.join(host_built, "host_space_check"), "block", "10", str(int(gb["fdtd_steps"])), out], check=True)
     d = orc.read_dump(out)
     assert np.array_equal(d["fdtd"], gb["fdtd_row_lc"])
+
+
+def test_matrix_market_reader_matches_scipy(host_built, orc, tmp_path):
+    """coordinate files, general and symmetric, pattern and duplicate entries; the CSR arrays and
+    a Host-space Csr_matrix::spmv against scipy."""
+    import scipy.io
+    import scipy.sparse as sp
+    A = sp.random(40, 40, density=0.1, random_state=5, format="coo"); A = sp.coo_matrix(A + A.T)
+    B = sp.random(30, 50, density=0.15, random_state=6, format="coo")
+    scipy.io.mmwrite(str(tmp_path / "sym.mtx"), A, symmetry="symmetric")
+    scipy.io.mmwrite(str(tmp_path / "gen.mtx"), B, symmetry="general")
+    (tmp_path / "pat.mtx").write_text("%%MatrixMarket matrix coordinate pattern general\n% comment\n3 4 5\n1 1\n3 4\n2 2\n1 1\n3 1\n")
+    P = sp.csr_matrix(np.array([[2.0, 0, 0, 0], [0, 1.0, 0, 0], [1.0, 0, 0, 1.0]]))      # duplicate (1,1) summed
+    out = str(tmp_path / "m.bin")
+    for name, M in (("sym.mtx", sp.csr_matrix(A)), ("gen.mtx", sp.csr_matrix(B)), ("pat.mtx", P)):
+        subprocess.run([os.path.join(host_built, "host_space_check"), "mtx", str(tmp_path / name), "0", out], check=True)
+        d = orc.read_dump(out)
+        M.sort_indices()
+        assert tuple(d["dims"]) == (M.shape[0], M.shape[1], M.nnz)
+        assert np.array_equal(d["row_ptr"].astype(np.int64), M.indptr) and np.array_equal(d["col_idx"].astype(np.int64), M.indices)
+        assert np.allclose(d["data"], M.data, rtol=1e-15, atol=0)
+        x = 1.0 + 0.25 * np.arange(M.shape[1])
+        assert np.allclose(d["y"], M @ x, rtol=1e-14, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_harness_matrix_market_operator(host_built, orc, tmp_path):
+    """--matrix mtx: a symmetric MatrixMarket file through the harness vs the oracle on the same CSR."""
+    import scipy.io
+    import scipy.sparse as sp
+    rp, ci, va = orc.lap2d(40, 30)
+    n = len(rp) - 1
+    A = sp.csr_matrix((va, ci, rp), shape=(n, n))
+    scipy.io.mmwrite(str(tmp_path / "lap.mtx"), sp.coo_matrix(sp.tril(A)), symmetry="symmetric")
+    stdout, out = run_harness(host_built, ["--matrix", "mtx", "--file", str(tmp_path / "lap.mtx"), "-m", "40", "--vector", "--reorth", "full"], tmp_path)
+    d = orc.read_dump(out)
+    ref = orc.vector_lanczos((rp, ci, va), orc.start_vector(n), 40, reorth=1)
+    assert np.max(np.abs(d["alpha"] - ref["alpha"])) < 1e-10 * np.abs(ref["alpha"]).max()
+    assert np.max(np.abs(d["beta"] - ref["beta"]) / ref["beta"]) < 1e-10
