@@ -102,7 +102,8 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------- CPU arm
 
 def cpu_sample(wl, iters):
-    """The oracle's recurrence (OpenMP, all host threads) on the first `iters` iterations of the workload."""
+    """The oracle's recurrence (OpenMP, all host threads) on the first `iters` iterations of the workload.
+    Returns (iterations/s, seconds, threads, alpha, beta)."""
     import numpy as np
     from oracle import orc
     threads = os.cpu_count() or 1
@@ -114,7 +115,17 @@ def cpu_sample(wl, iters):
     r = orc.vector_lanczos(csr, b, iters, reorth=wl["reorth"])
     dt = time.perf_counter() - t0
     assert r["steps"] == iters and np.all(np.isfinite(r["alpha"]))
-    return iters / dt, dt, threads
+    return iters / dt, dt, threads, np.array(r["alpha"][:iters]), np.array(r["beta"][:iters])
+
+
+def coeff_err(alpha, beta, ra, rb):
+    """north_star tolerance form: |d alpha| relative to max(|alpha|, mean beta), beta relative."""
+    import numpy as np
+    k = min(len(ra), len(alpha))
+    scale = np.maximum(np.abs(ra[:k]), np.mean(np.abs(rb[1:k])) if k > 1 else 1.0)
+    ea = float(np.max(np.abs(alpha[:k] - ra[:k]) / scale))
+    eb = float(np.max(np.abs(beta[:k] - rb[:k]) / np.abs(rb[:k])))
+    return ea, eb
 
 
 def run_reference(args, wl, rank):
@@ -125,7 +136,7 @@ def run_reference(args, wl, rank):
         cpu_sample(wl, min(4, iters))
     vals, times, threads = [], [], 1
     for _ in range(args.steps):
-        v, dt, threads = cpu_sample(wl, iters)
+        v, dt, threads = cpu_sample(wl, iters)[:3]
         vals.append(v); times.append(dt)
     value = iters * len(times) / sum(times)
     sample = "first %d of %d iterations of %s (per-iteration cost grows with the basis, so this flatters the CPU)" % (
@@ -139,6 +150,125 @@ def run_reference(args, wl, rank):
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------- extra legs (N = 1)
+
+def _events():
+    import torch
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def fp64_dgemm_peak():
+    """cuBLAS DGEMM 8192^3 through torch, best of 5: the fp64 dense peak the reorthogonalisation GEMMs are held against."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = _events()
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def extra_legs(ctx, lz, peak):
+    """north_star targets and the reference-CUDA baseline, measured in the same process right after the headline
+    (outside its timed region): (a) fused single-vector step on 256^3 as a fraction of HBM peak; (b) block b = 16 step
+    on 256^3 without and with block CGS2, the reorthogonalisation GEMMs in TFLOP/s against the fp64 DGEMM peak measured
+    here and against min(peak, AI * HBM); (c) the reference's own CUDA build (sm_100) and this library's C++ mirror on
+    the reference's matrix (Maxwell N = 160)."""
+    import re
+    import torch
+    out = {}
+    A = lz.Matrix.laplacian3d(ctx, 256, 256, 256)
+    n, nnz = A.n_rows, A.nnz
+    # (a) fused vector step
+    m = 100
+    b = torch.empty(n, dtype=torch.float64, device="cuda")
+    lz.check(lz.lib().lz_gen_start_vector(ctx.h, n, 0x5EED, b.data_ptr()))
+    al = torch.zeros(m, dtype=torch.float64, device="cuda"); be = torch.zeros_like(al)
+    lz.vector_lanczos_async(ctx, A, b, m, al, be); ctx.sync()
+    e0, e1 = _events()
+    e0.record()
+    for _ in range(3):
+        lz.vector_lanczos_async(ctx, A, b, m, al, be)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3 / m
+    byt = 12.0 * nnz + 52.0 * n
+    out["cfg3_vector_step"] = {"workload": "3-D 7-pt Laplacian 256^3, single vector, no reorth, 100 steps",
+                               "ms_per_step": ms, "it_per_s": 1e3 / ms, "algorithmic_bytes": byt,
+                               "gbs": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak, "target_frac": 0.80}
+    del b, al, be
+    # (b) block step, b = 16
+    bw = 16
+    peak64 = fp64_dgemm_peak()
+    B = torch.empty(n * bw, dtype=torch.float64, device="cuda")
+    lz.check(lz.lib().lz_gen_start_block(ctx.h, n, bw, n, 0x5EED, B.data_ptr()))
+    for reorth, mb in ((0, 12), (1, 12)):
+        alb = torch.zeros(mb * bw * bw, dtype=torch.float64, device="cuda")
+        beb = torch.zeros((mb + 1) * bw * bw, dtype=torch.float64, device="cuda")
+        run = lambda: lz.block_lanczos(ctx, A, B, n, bw, mb, alb, beb, None, lc=-1, reorth=reorth)
+        run(); ctx.sync()
+        ctx.profile(True)
+        e0, e1 = _events()
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        prof = ctx.profile_read(); ctx.profile(False)
+        assert lz.block_status(ctx, mb) == mb and bool(torch.isfinite(alb).all())
+        ms = e0.elapsed_time(e1) / mb
+        rec = {"workload": "3-D 7-pt Laplacian 256^3, block b=16, %d blocks, %s" % (mb, "block CGS2" if reorth else "no reorth"),
+               "ms_per_step": ms, "it_per_s": 1e3 / ms,
+               "classes_ms_per_step": {k: round(v[1] / mb, 4) for k, v in prof.items() if v[0]}}
+        if not reorth:
+            byt = 12.0 * nnz + 4.0 * n + 10 * 8.0 * n * bw
+            rec.update({"algorithmic_bytes": byt, "frac": byt / ms / 1e6 / peak, "spmm_ms": prof["spmm"][1] / max(prof["spmm"][0], 1),
+                        "spmm_frac": prof["spmm"][2] / max(prof["spmm"][1], 1e-9) / 1e6 / peak})
+            out["cfg3_block_step"] = rec
+        else:
+            # two sweeps per step against J = j + 1 stored blocks: flops of one product = 2 n b (J b)
+            flops = sum(2 * 2.0 * n * bw * (j + 1) * bw for j in range(mb))
+            ai_roof = min(peak64, (bw / 4.0) * peak / 1e3)           # AI = b/4 flop per basis byte
+            for cls, name in (("cgs_project", "projection"), ("cgs_update", "update")):
+                tf = flops / (prof[cls][1] * 1e-3) / 1e12
+                rec[name + "_tflops"] = tf
+                rec[name + "_frac_of_fp64_peak"] = tf / peak64
+                rec[name + "_frac_of_min_peak_AIxHBM"] = tf / ai_roof
+            rec.update({"fp64_dgemm_peak_tflops": peak64, "min_peak_AIxHBM_tflops": ai_roof, "target_frac_of_fp64_peak": 0.60})
+            out["cfg3_block_reorth"] = rec
+        del alb, beb
+    del B
+    A.close()
+    # (c) the reference's CUDA build and this library's mirror harness on the reference's own operator
+    ref = {}
+    rdir = os.path.join(ROOT, "oracle", "_ref")
+    hdir = os.path.join(PKG, "host")
+
+    def run_cmd(cmd, pat):
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            mo = re.search(pat, r.stdout + r.stderr)
+            return float(mo.group(1)) if mo else None
+        except (OSError, subprocess.TimeoutExpired):
+            return None
+
+    N = 160
+    tmp = "/tmp/lz_ref_dump.bin"
+    for tag, nc, mode, mm in (("vector", 4, "vector", 50), ("block4", 4, "block", 10), ("block8", 8, "block", 10), ("block16", 16, "block", 10)):
+        exe = os.path.join(rdir, "ref_cuda_dump_%d" % nc)
+        if os.path.exists(exe):
+            ref["reference_cuda_%s_it_s" % tag] = run_cmd([exe, mode, str(N), str(mm), tmp], r"\(([0-9.]+) iterations/s\)")
+        hexe = os.path.join(hdir, "test_lanczos")
+        if os.path.exists(hexe):
+            cmd = [hexe, "-N", str(N), "-m", str(mm)] + (["--vector"] if mode == "vector" else ["--block", str(nc)])
+            ref["lanczos_b200_%s_it_s" % tag] = run_cmd(cmd, r"iterations/s:\s*([0-9.]+)")
+    ref["operator"] = "reference Matrix_A(160,160,160): Maxwell curl operator, n = 24 806 880, ELL width 4; cold single calls"
+    out["ref_cuda_baseline"] = ref
+    return out
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -159,6 +289,7 @@ def run_gpu(args, wl, rank, world):
     m, reorth = wl["m"], wl["reorth"]
     peak, peak_kind = peaks()
 
+    lo_row, hi_row = 0, int(np.prod(wl["dims"]))
     if world > 1:
         ident = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -175,26 +306,28 @@ def run_gpu(args, wl, rank, world):
         A = lz.Matrix.laplacian2d(ctx, *wl["dims"]) if wl["kind"] == "lap2d" else lz.Matrix.laplacian3d(ctx, *wl["dims"])
     n_local = A.n_rows
     n_global = int(np.prod(wl["dims"]))
+    granule = n_global // wl["dims"][-1]
     b = torch.empty(n_local, dtype=torch.float64, device="cuda")
     if world > 1:
         lo, hi = lz.C.c_int64(), lz.C.c_int64()
-        granule = n_global // wl["dims"][-1]
         lz.check(lz.lib().lz_partition_rows(n_global, granule, world, rank, lz.C.byref(lo), lz.C.byref(hi)))
+        lo_row, hi_row = lo.value, hi.value
         full = torch.empty(n_global, dtype=torch.float64, device="cuda")
         lz.check(lz.lib().lz_gen_start_vector(ctx.h, n_global, 0x5EED, full.data_ptr()))
         ctx.sync()
-        b.copy_(full[lo.value:hi.value])
+        b.copy_(full[lo_row:hi_row])
         del full
     else:
         lz.check(lz.lib().lz_gen_start_vector(ctx.h, n_local, 0x5EED, b.data_ptr()))
     alpha = torch.zeros(m, dtype=torch.float64, device="cuda")
     beta = torch.zeros(m, dtype=torch.float64, device="cuda")
 
-    def solve():
+    def solve(mat=None, rhs=None):
+        mat, rhs = mat or A, b if rhs is None else rhs
         if world > 1:
-            lz.check(lz.lib().lz_vector_lanczos_sharded(ctx.h, A.h, b.data_ptr(), m, reorth, alpha.data_ptr(), beta.data_ptr()))
+            lz.check(lz.lib().lz_vector_lanczos_sharded(ctx.h, mat.h, rhs.data_ptr(), m, reorth, alpha.data_ptr(), beta.data_ptr()))
         else:
-            lz.vector_lanczos_async(ctx, A, b, m, alpha, beta, reorth=reorth)
+            lz.vector_lanczos_async(ctx, mat, rhs, m, alpha, beta, reorth=reorth)
 
     def barrier():
         torch.cuda.synchronize()
@@ -228,41 +361,92 @@ def run_gpu(args, wl, rank, world):
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt)
         launches = int(lt.item())
-    a_host = alpha.cpu().numpy()
+    a_host, b_host = alpha.cpu().numpy(), beta.cpu().numpy()
     assert np.all(np.isfinite(a_host)), "non-finite alpha: the solve broke down"
     value = m * args.steps / (ms_total * 1e-3)
+    peer_mode = None
+    if world > 1:
+        peer_mode, timed_out = ctx.comm_status()
+        assert not timed_out, "a peer-memory wait timed out"
 
-    # ---- end-to-end through the C-ABI from pinned host buffers (single GPU path) --------------
+    # ---- parity: the first CPU_SAMPLE_ITERS coefficients of THIS solve against the CPU oracle (every rank checks) ----
+    parity, cpu = None, None
+    if not args.no_cpu:
+        k = min(CPU_SAMPLE_ITERS, m)
+        ref = torch.zeros(2 * k + 3, dtype=torch.float64)
+        if rank == 0:
+            v, dt, threads, ra, rb = cpu_sample(wl, k)
+            cpu = (v, dt, threads)
+            ref = torch.from_numpy(np.concatenate([ra, rb, [v, dt, threads]]))
+        if dist:
+            ref = ref.cuda()
+            dist.broadcast(ref, 0)
+            ref = ref.cpu()
+        ref = ref.numpy()
+        ea, eb = coeff_err(a_host, b_host, ref[:k], ref[k:2 * k])
+        assert ea < 1e-10 and eb < 1e-10, "rank %d: alpha/beta differ from the oracle: %.3e / %.3e" % (rank, ea, eb)
+        if dist:
+            t = torch.tensor([ea, eb], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ea, eb = float(t[0]), float(t[1])
+        parity = {"against": "oracle/lanczos_oracle.c (CPU restatement), first %d alpha/beta of the timed solve, every rank" % k,
+                  "max_rel_alpha": ea, "max_rel_beta": eb, "tolerance": 1e-10}
+
+    # ---- end-to-end through the C-ABI from pinned host buffers -----------------------------------
+    # every step: the rank's CSR slab and start vector go host -> device (lz_csr_create_host / lz_csr_create_shard_host
+    # + lz_memcpy), the solve runs, alpha/beta come back device -> host
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         rp, ci, va = A.csr_to_host()
         pin = lambda a: torch.from_numpy(a).pin_memory()
         rp_h, ci_h, va_h, b_h = pin(rp), pin(ci), pin(va), b.cpu().pin_memory()
         h2d = rp_h.numel() * 4 + ci_h.numel() * 4 + va_h.numel() * 8 + b_h.numel() * 8
         bd = torch.empty_like(b)
         a_out, b_out = np.zeros(m), np.zeros(m)
+        hlo = granule if (world > 1 and rank > 0) else 0
+        hhi = granule if (world > 1 and rank < world - 1) else 0
 
         def e2e_step():
-            A2 = lz.Matrix.from_csr_host(ctx, rp_h.numpy(), ci_h.numpy(), va_h.numpy())
+            if world > 1:
+                A2 = lz.Matrix.from_csr_shard_host(ctx, rp_h.numpy(), ci_h.numpy(), va_h.numpy(), hlo, hhi, n_global, lo_row,
+                                                   hlo, n_local - hhi)
+            else:
+                A2 = lz.Matrix.from_csr_host(ctx, rp_h.numpy(), ci_h.numpy(), va_h.numpy())
             lz.check(lz.lib().lz_memcpy(ctx.h, bd.data_ptr(), b_h.data_ptr(), b_h.numel() * 8, lz.H2D))
-            steps = lz.C.c_int(0)
-            lz.check(lz.lib().lz_vector_lanczos(ctx.h, A2.h, bd.data_ptr(), m, 0, reorth, a_out.ctypes.data,
-                                                b_out.ctypes.data, None, lz.C.byref(steps)))
+            if world > 1:
+                solve(A2, bd)
+                a_out[:] = alpha.cpu().numpy(); b_out[:] = beta.cpu().numpy()
+            else:
+                steps = lz.C.c_int(0)
+                lz.check(lz.lib().lz_vector_lanczos(ctx.h, A2.h, bd.data_ptr(), m, 0, reorth, a_out.ctypes.data,
+                                                    b_out.ctypes.data, None, lz.C.byref(steps)))
             A2.close()
         e2e_step()                                           # warm-up
-        torch.cuda.synchronize()
+        barrier()
         reps = max(1, min(args.steps, 2))
         t0 = time.perf_counter()
         for _ in range(reps):
             e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         dt = (time.perf_counter() - t0) / reps
         assert np.allclose(a_out, a_host, rtol=1e-9, atol=1e-12)
-        e2e = {"value": m / dt, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * m),
+        if dist:
+            t = torch.tensor([dt, float(h2d)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+            t2 = torch.tensor([float(h2d)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t2)
+            h2d = int(t2.item())
+        e2e = {"value": m / dt, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(16 * m * world),
                "ms_per_step": dt * 1e3}
+        del rp_h, ci_h, va_h, b_h, bd
+
+    extra = None
+    if world == 1 and not args.no_extra and args.workload == "cfg2":
+        extra = extra_legs(ctx, lz, peak)
 
     def teardown():
-        # identical order on every rank: library communicator first, then torch's
+        # identical order on every rank: operators, library communicator + context, then torch's
         A.close()
         ctx.close()
         if dist:
@@ -282,7 +466,10 @@ def run_gpu(args, wl, rank, world):
         tj = json.load(open(tpath)).get(dom)
         if tj:
             traffic = tj["dram_bytes_per_algorithmic_byte"] * kby / max(la, 1)
-    share = {k: round(v[1] / ms_total, 4) for k, v in prof.items() if v[0]}
+    # shares of the PROFILED time (sum of the per-class event times); the event ring is drained when it fills, so
+    # every launch of the timed region is counted
+    prof_ms = sum(v[1] for v in prof.values())
+    share = {k: round(v[1] / prof_ms, 4) for k, v in prof.items() if v[0]}
     line = {"metric": "lanczos_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -292,15 +479,25 @@ def run_gpu(args, wl, rank, world):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "launches": la, "kernel_ms": kms, "algorithmic_bytes_per_launch": kby / max(la, 1),
-                         "share_of_step": share},
+                         "share_of_step": share, "profiled_ms": prof_ms, "timed_ms": ms_total,
+                         "launches_by_class": {k: v[0] for k, v in prof.items() if v[0]}},
             "gpu_launches": launches, "clocks": clocks}
+    if world > 1:
+        line["comm"] = {"mode": "peer-memory (CUDA IPC over NVLink): one-shot all-reduces + pushed halos" if peer_mode else "nccl",
+                        "share_of_profiled_time": share.get("comm", 0.0),
+                        "note": "stand-alone all-reduce kernels only; scalar all-reduces run inside the last CTA of the "
+                                "producing kernel and the halo exchange overlaps the interior SpMV on a side stream"}
+    if parity:
+        line["parity"] = parity
     if e2e:
         line["e2e"] = e2e
-    if world == 1 and not args.no_cpu:
-        v, dt, threads = cpu_sample(wl, min(CPU_SAMPLE_ITERS, m))
-        line["cpu_baseline"] = {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port",
+    if cpu:
+        v, dt, threads = cpu
+        line["cpu_baseline"] = {"value": v, "unit": "iterations/s", "cores": int(threads), "kind": "port",
                                 "sample": "first %d of %d iterations of the same solve, oracle/lanczos_oracle.c with OpenMP (%.1f s)"
                                           % (min(CPU_SAMPLE_ITERS, m), m, dt)}
+    if extra:
+        line["extra"] = extra
     print(json.dumps(line), flush=True)
     teardown()
 
@@ -312,8 +509,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the north_star / reference-CUDA extra legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -171,12 +171,22 @@ __device__ __forceinline__ void lz_ld256_ro(const double *p, double &a, double &
 // A group of LW = BW/4 lanes owns a row and every lane carries FOUR adjacent columns (one 256-bit
 // load per gathered row): the kernel is bound by instruction issue, and four columns per lane halve
 // the instructions per non-zero against the two-column layout of k_spmm_rm.
-template <int BW, int CW, int STAGES, int CAP, int MINB>
+//
+// FSUB (BW = 16 only): W = A X - Q0 B in the same pass, the reference's order of the block recurrence
+// (W = A Q_j; W -= Q_{j-1} beta_j BEFORE alpha_j is formed, methods/block_lanczos.hpp:149-155).  With 4 lanes per
+// row a warp trip is an 8-row x 16-column tile whose accumulators already ARE the C fragments of two
+// mma.m8n8k4 n-tiles if the tile columns are labelled  n-tile t, slot s  <->  column 4(s>>1) + 2t + (s&1);
+// the Q0 row segment a lane loads (columns 4l..4l+3, one 256-bit load) is its A fragment for the K labelling
+// k-tile t, slot l  <->  column 4l + t.  The subtraction is then 8 DMMAs per trip with no data movement;
+// only the B fragments of -B (fragment-ordered in shared memory) follow the two labellings.
+template <int BW, int CW, int STAGES, int CAP, int MINB, bool FSUB>
 __global__ void __launch_bounds__((1 + CW) * 32, MINB)
 k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
           const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
-          const double *__restrict__ X, double *__restrict__ W, const int run, const int hint)
+          const double *__restrict__ X, double *__restrict__ W, const double *__restrict__ Q0, const double *__restrict__ Bm,
+          const LzChunkRange cr, const int run, const int hint)
 {
+    static_assert(!FSUB || BW == 16, "the fused subtraction is written for 16-column panels");
     constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *vals_s = reinterpret_cast<double *>(smem_raw);
@@ -184,30 +194,43 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     int *rptr_s = reinterpret_cast<int *>(smem_raw + 12 * (size_t)CAP * STAGES);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 12 * (size_t)CAP * STAGES + 4 * (size_t)SPMM_WS_RCAP * STAGES);
     uint64_t *freeb = full + STAGES;
+    __shared__ double sbs[FSUB ? 8 * 32 : 1];           // -B in fragment order: sbs[(kt*2 + nt)*32 + lane]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { lz_mbar_init(&full[s], 1); lz_mbar_init(&freeb[s], CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (FSUB) {
+        for (int e = tid; e < 8 * 32; e += (1 + CW) * 32) {
+            const int ln = e & 31, nt = (e >> 5) & 1, kt = e >> 6;
+            const int kk = ln & 3, mm = ln >> 2;
+            const int kphys = 4 * kk + kt, nphys = 4 * (mm >> 1) + 2 * nt + (mm & 1);
+            sbs[e] = -Bm[kphys + nphys * BW];
+        }
     }
     __syncthreads();
     // chunk -> CTA map: runs of `run` consecutive chunks dealt round-robin to the CTAs.  Inside a run the rows
     // gathered for the near neighbours of a stencil row are this CTA's own recent rows (L1 hits); all CTAs
     // together sweep a window of grid*run chunks, so the far (+-nx*ny) neighbours were touched one window
     // earlier and are still in L2 (with one contiguous range per CTA they were DRAM misses: ncu, L2 hit 15 %).
-    auto chunk_of = [&](int it) { return ((it / run) * (int)gridDim.x + (int)blockIdx.x) * run + (it % run); };
+    // Virtual chunk v of the launch is chunk cmap(v) of the schedule (interior / boundary launches of a shard).
+    const int n_virtual = cr.total;
+    auto vchunk = [&](int it) { return ((it / run) * (int)gridDim.x + (int)blockIdx.x) * run + (it % run); };
+    auto cmap = [&](int v) { return v < cr.n0 ? cr.c0 + v : cr.c1 + (v - cr.n0); };
+    (void)n_chunks;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             int p0 = 0, p1 = 0, r0 = 0, r1 = 0;
-            int c = chunk_of(0);
-            if (c < n_chunks) { p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1]; }
+            int v = vchunk(0);
+            if (v < n_virtual) { const int c = cmap(v); p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1]; }
             const uint64_t pol = lz_policy_evict_first();
-            for (int it = 0; c < n_chunks; ++it) {
+            for (int it = 0; v < n_virtual; ++it) {
                 const int slot = it % STAGES;
                 const int cp0 = p0, cp1 = p1, cr0 = r0, cr1 = r1;
-                c = chunk_of(it + 1);
-                if (c < n_chunks) { p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1]; }
+                v = vchunk(it + 1);
+                if (v < n_virtual) { const int c = cmap(v); p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1]; }
                 lz_mbar_wait(&freeb[slot], ((it / STAGES) & 1) ^ 1);
                 const int a0 = cp0 & ~3, cnt4 = (cp1 - a0) & ~3;
                 const int ra = cr0 & ~3;
@@ -230,15 +253,15 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     } else {
         // ------------------------------------------------------------------ compute warps
         const int sub = lane / LW, l = lane % LW;
-        const int gid = (warp - 1) * RPW + sub;
         int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
-        int c = chunk_of(0);
-        if (c < n_chunks) { nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
-        for (int it = 0; c < n_chunks; ++it) {
+        int v = vchunk(0);
+        if (v < n_virtual) { const int c = cmap(v); nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
+        for (int it = 0; v < n_virtual; ++it) {
             const int slot = it % STAGES;
             const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
-            c = chunk_of(it + 1);
-            if (c < n_chunks) {
+            v = vchunk(it + 1);
+            if (v < n_virtual) {
+                const int c = cmap(v);
                 nr0 = chunk_row[c]; nr1 = chunk_row[c + 1];
                 np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1];
             }
@@ -251,10 +274,20 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
             const int *cs = cols_s + (size_t)slot * CAP;
             const int *rs = rptr_s + (size_t)slot * SPMM_WS_RCAP;
             lz_mbar_wait(&full[slot], (it / STAGES) & 1);
-            for (int64_t r = (int64_t)r0 + gid; r < r1; r += NG) {
-                int s, e;
-                if (rows_ok) { s = rs[r - ra]; e = rs[r - ra + 1]; }
-                else { s = rowptr[r]; e = rowptr[r + 1]; }
+            // warp-uniform trips over the chunk's rows: RPW rows per trip, row of this lane group = rb + sub
+            for (int64_t rb = (int64_t)r0 + (warp - 1) * RPW; rb < r1; rb += NG) {
+                const int64_t r = rb + sub;
+                const bool valid = r < r1;
+                int s = 0, e = 0;
+                if (valid) {
+                    if (rows_ok) { s = rs[r - ra]; e = rs[r - ra + 1]; }
+                    else { s = rowptr[r]; e = rowptr[r + 1]; }
+                }
+                double q0, q1, q2, q3;
+                if (FSUB) {       // this lane's Q0 row segment = its A fragments; issued before the gathers
+                    q0 = q1 = q2 = q3 = 0.0;
+                    if (valid) lz_ld256_stream(Q0 + r * BW + 4 * l, q0, q1, q2, q3);
+                }
                 double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
                 const double *Xl = X + 4 * l;
                 for (int k0 = s; k0 < e; k0 += G) {
@@ -280,8 +313,17 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                         acc2 = fma(vv[g], x2[g], acc2); acc3 = fma(vv[g], x3[g], acc3);
                     }
                 }
-                if (hint) lz_st256_stream(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
-                else lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                if (FSUB) {
+                    // (acc0,acc1) / (acc2,acc3) are the C fragments of n-tiles 0 / 1, q0..q3 the A fragments of k-tiles 0..3
+                    lz_dmma(acc0, acc1, q0, sbs[(0 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q0, sbs[(0 * 2 + 1) * 32 + lane]);
+                    lz_dmma(acc0, acc1, q1, sbs[(1 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q1, sbs[(1 * 2 + 1) * 32 + lane]);
+                    lz_dmma(acc0, acc1, q2, sbs[(2 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q2, sbs[(2 * 2 + 1) * 32 + lane]);
+                    lz_dmma(acc0, acc1, q3, sbs[(3 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q3, sbs[(3 * 2 + 1) * 32 + lane]);
+                }
+                if (valid) {
+                    if (hint) lz_st256_stream(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                    else lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                }
             }
             __syncwarp();
             if (lane == 0) lz_mbar_arrive(&freeb[slot]);
@@ -289,33 +331,38 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     }
 }
 
-template <int BW, int CW, int STAGES, int MINB>
-static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W, int run)
+template <int BW, int CW, int STAGES, int MINB, bool FSUB>
+static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W,
+                                const double *Q0, const double *Bm, int run, int part)
 {
     constexpr int CAP = 2048;
     const size_t smem = (size_t)STAGES * (CAP * 12 + SPMM_WS_RCAP * 4) + 16 * STAGES;
-    static bool attr_set = false;
-    if (!attr_set) {
-        LZ_CUDA(cudaFuncSetAttribute(k_spmm_ws<BW, CW, STAGES, CAP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB>, (int)smem));
+    const int nch = A->mm_n_chunks;
+    LzChunkRange cr = {0, nch, 0, nch};
+    if (part == 1) cr = {A->mm_bnd_lo, A->mm_bnd_hi - A->mm_bnd_lo, 0, A->mm_bnd_hi - A->mm_bnd_lo};
+    if (part == 2) cr = {0, A->mm_bnd_lo, A->mm_bnd_hi, A->mm_bnd_lo + (nch - A->mm_bnd_hi)};
+    if (cr.total <= 0) return LZ_OK;
     int grid = ctx->sm_count * MINB;
-    if (grid > A->mm_n_chunks) grid = A->mm_n_chunks;
-    const int per_cta = (A->mm_n_chunks + grid - 1) / grid;
-    k_spmm_ws<BW, CW, STAGES, CAP, MINB><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
-        A->mm_n_chunks, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W, run > 0 ? run : per_cta,
-        getenv("LZ_SPMM_HINT") ? 1 : 0);      // evict-first streams: +5 % when the far neighbours miss L2, -3 % when they hit: off
+    if (grid > cr.total) grid = cr.total;
+    const int per_cta = (cr.total + grid - 1) / grid;
+    k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
+        nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
+        ctx->knobs.spmm_hint);      // evict-first streams: +5 % when the far neighbours miss L2, -3 % when they hit: off
     return LZ_OK;
 }
 
 template <int BW>
-static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W)
+static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W,
+                          const double *Q0, const double *Bm, int part)
 {
     // 12 compute warps, 2-slot ring, 2 CTAs per SM (other shapes: profiles/r01_spmv_variants.md).
     // dev-time knob LZ_SPMM_RUN = chunks per run of the chunk map (default 1; 0: one contiguous range per CTA)
-    static int run = -1;
-    if (run < 0) { const char *e = getenv("LZ_SPMM_RUN"); run = e ? atoi(e) : 1; }
-    return launch_spmm_ws_shape<BW, 12, 2, 2>(ctx, A, rowptr, n_rows, X, W, run);
+    const int run = ctx->knobs.spmm_run;
+    if constexpr (BW == 16) {
+        if (Q0) return launch_spmm_ws_shape<16, 12, 2, 2, true>(ctx, A, rowptr, n_rows, X, W, Q0, Bm, run, part);
+    }
+    return launch_spmm_ws_shape<BW, 12, 2, 2, false>(ctx, A, rowptr, n_rows, X, W, nullptr, nullptr, run, part);
 }
 
 // any bw <= 32 (odd widths, bw = 1): one lane per column
@@ -421,12 +468,22 @@ __global__ void __launch_bounds__(256) k_cm_to_rm(int64_t n, int bw, const doubl
     }
 }
 
+// can W = A X - Q0 B run as ONE pass on this operator?  (staged kernel with the DMMA subtraction: 16 columns)
+static bool spmm_can_fuse(const lz_ctx *ctx, const lz_matrix *A, int bw)
+{
+    return bw == 16 && A->rowptr && A->tma_ok && A->mm_chunk_row && !A->vrowptr && ctx->spmv_variant != 9;
+}
+
+// part: 0 all rows, 1 interior chunks of a shard, 2 its boundary chunks (staged kernel only)
 static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n, int bw, const double *X, double *W,
-                       const double *Q0, const double *Bm)
+                       const double *Q0, const double *Bm, int part = 0)
 {
     const bool fuse = Q0 != nullptr;
     lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 4.0 * (double)n + 16.0 * (double)n * bw + (fuse ? 8.0 * (double)n * bw : 0.0));
-    if (A->format == LZ_FMT_ELL4) {
+    // ELL4 operators carry a CSR shadow with a chunk schedule (lz_ell_create), so the block path runs the same
+    // staged kernel on them; the width-4 ELL kernel is only the last resort
+    if (A->format == LZ_FMT_ELL4 && !A->rowptr) {
+        LZ_CHECK(part == 0, LZ_ERR_INVALID, "spmm: partial launches need a chunk schedule");
         const unsigned grid = (unsigned)((n * bw + SPMM_THREADS - 1) / SPMM_THREADS);
 #define ELL_CASE(B)                                                                                               \
     if (fuse) k_spmm_rm_ell4<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, A->ell_data, A->ell_idx, X, W, Q0, Bm); \
@@ -439,15 +496,17 @@ static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, 
         int64_t want = (n + SPMM_SLAB - 1) / SPMM_SLAB;
         int64_t cap = (int64_t)ctx->sm_count * 8;
         const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
-        const bool ws = A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 && !fuse && ((uintptr_t)X % 32 == 0) && ((uintptr_t)W % 32 == 0);
+        const bool ws = A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 && (!fuse || spmm_can_fuse(ctx, A, bw)) &&
+                        ((uintptr_t)X % 32 == 0) && ((uintptr_t)W % 32 == 0) && (!fuse || (uintptr_t)Q0 % 32 == 0);
         if (ws && (bw == 8 || bw == 16 || bw == 32)) {
-            if (bw == 8) LZ_TRY(launch_spmm_ws<8>(ctx, A, rowptr, n, X, W));
-            else if (bw == 16) LZ_TRY(launch_spmm_ws<16>(ctx, A, rowptr, n, X, W));
-            else LZ_TRY(launch_spmm_ws<32>(ctx, A, rowptr, n, X, W));
+            if (bw == 8) LZ_TRY(launch_spmm_ws<8>(ctx, A, rowptr, n, X, W, Q0, Bm, part));
+            else if (bw == 16) LZ_TRY(launch_spmm_ws<16>(ctx, A, rowptr, n, X, W, Q0, Bm, part));
+            else LZ_TRY(launch_spmm_ws<32>(ctx, A, rowptr, n, X, W, Q0, Bm, part));
             LZ_LAUNCH_CHECK(ctx);
             lz_prof_end(ctx);
             return LZ_OK;
         }
+        LZ_CHECK(part == 0, LZ_ERR_INVALID, "spmm: partial launches need the staged kernel");
 #define CSR_CASE(B)                                                                                                     \
     if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->colidx, A->vals, X, W, Q0, Bm); \
     else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->colidx, A->vals, X, W, Q0, Bm)
@@ -479,9 +538,10 @@ k_split_combine_rows(int64_t n_rows, int bw, const int32_t *__restrict__ vstart,
     }
 }
 
-static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, double *W, const double *Q0, const double *Bm)
+static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, double *W, const double *Q0, const double *Bm, int part = 0)
 {
-    if (!A->vrowptr) return spmm_rm_rows(ctx, A, A->rowptr, A->n_rows, bw, X, W, Q0, Bm);
+    if (!A->vrowptr) return spmm_rm_rows(ctx, A, A->rowptr, A->n_rows, bw, X, W, Q0, Bm, part);
+    LZ_CHECK(part == 0, LZ_ERR_INVALID, "row-split operators cannot be launched in parts");
     // row-split operator: partial rows per virtual row, then an ordered combine
     LZ_CHECK(Q0 == nullptr, LZ_ERR_UNSUPPORTED, "fused subtraction is not available on a row-split operator");
     void *wbar;
@@ -545,10 +605,19 @@ int lz_spmm(lz_ctx *ctx, const lz_matrix *A, int b, const double *X, int64_t ldx
     return LZ_OK;
 }
 
+// copy of a b x b block (device -> device), used where the reference copies small matrices
+__global__ void k_copy_small(int count, const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (int e = threadIdx.x; e < count; e += blockDim.x) dst[e] = src[e];
+}
+
+enum { SB_GLAST = 4096, SB_BLAST = 4096 + 1024, SB_G1 = 4096 + 2048, SB_G2 = 4096 + 3072 };   // slots in ctx->scalars (b*b <= 1024 each)
+
 int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t ldb, int bw, int m, int64_t lc,
                      int reorth, double *alpha, double *beta, double *q)
 {
     LZ_CHECK(ctx && A && B && alpha && beta && m >= 1, LZ_ERR_INVALID, "lz_block_lanczos: bad arguments");
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_block_lanczos: the operator belongs to another (or a destroyed) context");
     LZ_CHECK(bw >= 1 && bw <= 32, LZ_ERR_INVALID, "lz_block_lanczos: block width %d outside 1..32", bw);
     const int64_t n = A->n_rows;
     // with a communicator attached (lz_comm_init) A is this rank's row slab, B holds the local rows, the
@@ -561,11 +630,30 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
     LZ_CHECK(reorth == LZ_REORTH_NONE || reorth == LZ_REORTH_FULL, LZ_ERR_INVALID, "lz_block_lanczos: reorth mode %d", reorth);
     LZ_CUDA(cudaSetDevice(ctx->device));
     const size_t pan = (size_t)n * bw, bb = (size_t)bw * bw;
-    const size_t pstride = (size_t)(hlo + n + hhi) * bw;                     // one panel incl. halo rows (multiple of bw doubles)
-    size_t work_bytes = sizeof(double) * (3 * pstride + (reorth ? 2 * bb * m : 0) + 64);
+    // panel layout [lower halo | local | upper halo]; sharded: identical offsets on every rank (peer halo pushes)
+    int64_t off_rows = hlo, span_rows = hlo + n + hhi, n_below = -1;
+    if (sharded) {
+        const int64_t mine[4] = {hlo, n, hhi, 0};
+        int64_t all[4 * LZ_MAX_RANKS];
+        LZ_TRY(lz_comm_gather4(ctx, mine, all));
+        const int world = lz_comm_world(ctx), rank = lz_comm_rank(ctx);
+        off_rows = 0; span_rows = 0;
+        for (int r = 0; r < world; ++r) off_rows = all[4 * r] > off_rows ? all[4 * r] : off_rows;
+        for (int r = 0; r < world; ++r) { const int64_t sp = off_rows + all[4 * r + 1] + all[4 * r + 2]; span_rows = sp > span_rows ? sp : span_rows; }
+        n_below = rank > 0 ? all[4 * (rank - 1) + 1] * bw : 0;
+    }
+    const size_t pstride = ((size_t)span_rows * bw + 15) & ~(size_t)15;      // one panel incl. halo rows, 128-byte multiple
+    // Unsharded full reorthogonalisation keeps Q_j only inside the stored basis (block j at V + j*pan): the
+    // normalisation writes it there and the SpMM gathers from there -- no per-step device-to-device copy.
+    const bool inplace = reorth && !sharded;
+    const size_t n_panels = inplace ? 1 : 3;
+    const size_t work_doubles = n_panels * pstride + (reorth ? 2 * bb * m : 0) + 64;
     void *work;
-    LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
-    double *Q0 = (double *)work + (size_t)hlo * bw, *Q1 = Q0 + pstride, *W = Q1 + pstride, *C = (double *)work + 3 * pstride;
+    if (sharded) LZ_TRY(lz_comm_arena(ctx, sizeof(double) * work_doubles, (size_t)(reorth ? m : 1) * bb + 8, &work));
+    else LZ_TRY(lz_ctx_workspace(ctx, sizeof(double) * work_doubles, &work));
+    double *W = (double *)work + (size_t)off_rows * bw;                     // W never needs halo rows; same offset keeps alignment
+    double *Qa = inplace ? nullptr : W + pstride, *Qb = inplace ? nullptr : Qa + pstride;
+    double *C = (double *)work + n_panels * pstride;
     double *V = nullptr;
     if (reorth) LZ_TRY(lz_ctx_basis_blocks(ctx, (int64_t)pan, m, &V));     // block j at V + j*pan, row-major
     double *binv = beta + bb * m;                                         // beta[m]: scratch inverse (block_lanczos.hpp:111)
@@ -574,56 +662,105 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
     LZ_LAUNCH_CHECK(ctx);
     auto reduce_small = [&](double *M) -> int { return sharded ? lz_comm_allreduce_sum(ctx, M, bb) : LZ_OK; };
     auto halo = [&](double *Q) -> int {
-        return sharded ? lz_comm_halo_exchange(ctx, Q, (int64_t)pan, hlo * bw, hhi * bw) : LZ_OK;
+        return sharded ? lz_comm_halo_exchange(ctx, Q, (int64_t)pan, hlo * bw, hhi * bw, n_below, false) : LZ_OK;
     };
     auto cgs2 = [&](int nblocks) -> int {
         for (int sweep = 0; sweep < 2; ++sweep) LZ_TRY(lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)pan, W, C, sharded));
         return LZ_OK;
     };
+    auto qslot = [&](int j) -> double * { return inplace ? V + pan * j : ((j & 1) ? Qb : Qa); };
     const bool qrow = q != nullptr && lc >= 0;
+    const bool fuse = spmm_can_fuse(ctx, A, bw);                           // W = A Q_j - Q_{j-1} beta_j in one pass
+    double *sc = ctx->scalars;
+    // where the next step's W^T W lands: straight in its beta slot (the square root is taken in place); the one
+    // after the last step goes to the context (lz_block_last_coupling) so that beta[m] keeps the last inverse
+    auto gslot = [&](int jn) -> double * { return jn < m ? beta + bb * jn : sc + SB_GLAST; };
 
     // W <- B in row-major; beta[0] = (B^T B)^{1/2}; Q0 = B beta[0]^{-1}                     (:106-114)
     k_cm_to_rm<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, bw, B, ldb, W);
     LZ_LAUNCH_CHECK(ctx);
     LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, beta, 0));
     LZ_TRY(reduce_small(beta));
-    LZ_TRY(lz_sqrtm_launch(ctx, bw, beta, binv, flag));
+    LZ_TRY(lz_sqrtm_launch(ctx, bw, beta, binv, flag, 0));
+    double *Q0 = qslot(0);
     LZ_TRY(lz_panel(ctx, n, bw, true, W, 0, binv, 0.0, 1.0, Q0, 0, nullptr));
     if (qrow) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q0, 0, q, 0));                     // :117
-    if (V) LZ_CUDA(cudaMemcpyAsync(V, Q0, sizeof(double) * pan, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (V && !inplace) LZ_CUDA(cudaMemcpyAsync(V, Q0, sizeof(double) * pan, cudaMemcpyDeviceToDevice, ctx->stream));
     LZ_TRY(halo(Q0));
     LZ_TRY(spmm_rm(ctx, A, bw, Q0 - hlo * bw, W, nullptr, nullptr));                          // :121
     LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q0, 0, alpha, 1));                                 // :124
     LZ_TRY(reduce_small(alpha));
-    double *G = ctx->scalars + 4096;                                                          // W^T W of the updated W
-    LZ_TRY(lz_panel(ctx, n, bw, true, Q0, 0, alpha, 1.0, -1.0, W, 0, reorth ? nullptr : G));  // :128 (+ :137 fused)
+    LZ_TRY(lz_panel(ctx, n, bw, true, Q0, 0, alpha, 1.0, -1.0, W, 0, reorth ? nullptr : gslot(1)));  // :128 (+ :137 fused)
     if (reorth) {
         LZ_TRY(cgs2(1));
-        LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, G, 0));
+        LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, gslot(1), 0));
     }
-    LZ_TRY(reduce_small(G));
+    LZ_TRY(reduce_small(gslot(1)));
     for (int j = 1; j < m; ++j) {                                                             // :132-166
-        double *bj = beta + bb * j, *aj = alpha + bb * j;
-        LZ_CUDA(cudaMemcpyAsync(bj, G, sizeof(double) * bb, cudaMemcpyDeviceToDevice, ctx->stream));   // :137
-        LZ_TRY(lz_sqrtm_launch(ctx, bw, bj, binv, flag));                                     // :142
+        double *bj = beta + bb * j, *aj = alpha + bb * j;                                     // bj holds W^T W (:137)
+        LZ_TRY(lz_sqrtm_launch(ctx, bw, bj, binv, flag, j));                                  // :142
+        double *Q1 = qslot(j);
         LZ_TRY(lz_panel(ctx, n, bw, true, W, 0, binv, 0.0, 1.0, Q1, 0, nullptr));             // :145
-        // W' = A Q1 (:149); alpha_j from W' (the reference forms it after subtracting Q0 beta_j, :152-155: the
-        // two differ by sym(beta_j^T Q0^T Q1), i.e. by rounding, because consecutive blocks are orthogonal);
-        // then ONE pass subtracts both Q0 beta_j and Q1 alpha_j and accumulates the next W^T W (:152,:159,:137)
+        if (qrow) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q1, 0, q, (int64_t)j * bw));   // :165
+        if (V && !inplace) LZ_CUDA(cudaMemcpyAsync(V + pan * j, Q1, sizeof(double) * pan, cudaMemcpyDeviceToDevice, ctx->stream));
         LZ_TRY(halo(Q1));
-        LZ_TRY(spmm_rm(ctx, A, bw, Q1 - hlo * bw, W, nullptr, nullptr));
-        LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q1, 0, aj, 1));
-        LZ_TRY(reduce_small(aj));
-        LZ_TRY(lz_panel2(ctx, n, bw, Q0, bj, Q1, aj, W, reorth ? nullptr : G));
-        double *t = Q0; Q0 = Q1; Q1 = t;                                                      // :162 (no copy)
-        if (qrow) LZ_TRY(lz_copy_row_launch(ctx, lc, bw, true, Q0, 0, q, (int64_t)j * bw));   // :165
-        if (V) {
-            LZ_CUDA(cudaMemcpyAsync(V + pan * j, Q0, sizeof(double) * pan, cudaMemcpyDeviceToDevice, ctx->stream));
-            LZ_TRY(cgs2(j + 1));
-            LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, G, 0));
+        double *gn = gslot(j + 1);
+        if (fuse) {
+            // the reference's order: W = A Q_j - Q_{j-1} beta_j (:149,:152), alpha_j = sym(W^T Q_j) (:155),
+            // W -= Q_j alpha_j (:159) with the next W^T W accumulated in the same pass (:137)
+            LZ_TRY(spmm_rm(ctx, A, bw, Q1 - hlo * bw, W, Q0, bj));
+            LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q1, 0, aj, 1));
+            LZ_TRY(reduce_small(aj));
+            LZ_TRY(lz_panel(ctx, n, bw, true, Q1, 0, aj, 1.0, -1.0, W, 0, reorth ? nullptr : gn));
+        } else {
+            // same quantities when the SpMM cannot subtract: G1 = Q_j^T (A Q_j) and G2 = Q_j^T Q_{j-1} from one pass,
+            // alpha_j = sym(G1 - G2 beta_j), then one pass subtracts both Q_{j-1} beta_j and Q_j alpha_j (+ next W^T W)
+            LZ_TRY(spmm_rm(ctx, A, bw, Q1 - hlo * bw, W, nullptr, nullptr));
+            LZ_TRY(lz_gram2(ctx, n, bw, Q1, W, Q0, sc + SB_G1, sc + SB_G2));
+            if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, sc + SB_G1, 2048));            // G1 and G2 sit back to back
+            LZ_TRY(lz_alpha_from_grams(ctx, bw, sc + SB_G1, sc + SB_G2, bj, aj));
+            LZ_TRY(lz_panel2(ctx, n, bw, Q0, bj, Q1, aj, W, reorth ? nullptr : gn));
         }
-        LZ_TRY(reduce_small(G));
+        Q0 = Q1;                                                                              // :162 (no copy)
+        if (V) {
+            LZ_TRY(cgs2(j + 1));
+            LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, gn, 0));
+        }
+        LZ_TRY(reduce_small(gn));
     }
+    // beta_m = (W_m^T W_m)^{1/2}: the coupling to the next (unbuilt) block, for residual estimates and restarts
+    k_copy_small<<<1, 256, 0, ctx->stream>>>((int)bb, sc + SB_GLAST, sc + SB_BLAST);
+    LZ_LAUNCH_CHECK(ctx);
+    LZ_TRY(lz_sqrtm_launch(ctx, bw, sc + SB_BLAST, sc + SB_G1, ctx->flags + 3, 0));
+    ctx->last_coupling_slot = SB_BLAST;
+    return LZ_OK;
+}
+
+// Number of valid blocks of the last lz_block_lanczos run on this context: m when every W^T W was positive
+// definite to working precision, otherwise the index j of the first beta_j that was singular or not finite
+// (alpha[0..j), beta[0..j] are valid, LZ_ERR_BREAKDOWN is returned).  Synchronises.
+int lz_block_status(lz_ctx *ctx, int m, int *blocks_done)
+{
+    LZ_CHECK(ctx && m >= 1, LZ_ERR_INVALID, "lz_block_status: bad arguments");
+    int flag = 0;
+    LZ_CUDA(cudaMemcpyAsync(&flag, ctx->flags + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int done = flag < m ? flag : m;
+    if (blocks_done) *blocks_done = done;
+    if (done < m) {
+        lz_set_error("lz_block_lanczos: breakdown, beta[%d] is singular or not finite", done);
+        return LZ_ERR_BREAKDOWN;
+    }
+    return LZ_OK;
+}
+
+// beta_m of the last run (bw = 1: the vector driver's beta_m; otherwise the bw x bw block, column-major) to HOST
+int lz_last_coupling(lz_ctx *ctx, int bw, double *beta_last_host)
+{
+    LZ_CHECK(ctx && beta_last_host && bw >= 1 && bw <= 32, LZ_ERR_INVALID, "lz_last_coupling: bad arguments");
+    const double *src = ctx->scalars + ctx->last_coupling_slot;
+    LZ_CUDA(cudaMemcpyAsync(beta_last_host, src, sizeof(double) * bw * bw, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     return LZ_OK;
 }
 

@@ -50,6 +50,18 @@ void lz_set_error(const char *fmt, ...);
 // ---- context -------------------------------------------------------------------------
 struct lz_comm;   // lz_multi.cu
 
+struct lz_matrix;
+#define LZ_ATTR_CAP 64
+struct LzKnobs {
+    int spmv_hint, spmm_hint, spmm_run, no_split, cgs_shape_order, cgs_upd_mult, cgs_one_cta, no_cgs_fuse, cgs_no_slices;
+    int comm_mode;          // LZ_COMM: 0 auto (peer memory when IPC works, else NCCL), 1 NCCL only, 2 peer required
+    int no_overlap;         // LZ_NO_OVERLAP: halo exchange on the compute stream, one SpMV launch
+    int no_fold;            // LZ_NO_FOLD: keep pass B + separate alpha in the full-reorth vector path
+    int spmm_kernel;        // LZ_SPMM_KERNEL: 0 default choice, 1 k_spmm_ws (round-robin chunks), 2 k_spmm_win (staged X window)
+    int block_cgs_fuse;     // LZ_BLOCK_CGS_FUSE: 1 (default) fused update+project in the block CGS2, 0 four streams
+    int rmat_reorder;       // LZ_REORDER: locality reordering at lz_csr_create time for power-law operators
+};
+
 struct lz_ctx {
     int device;
     int sm_count;
@@ -71,6 +83,7 @@ struct lz_ctx {
     int64_t basis_ts, basis_cs, basis_rows;   // element (i,k) at basis[(i>>5)*ts + k*cs + (i&31)]
     int basis_cols;
     lz_comm *comm;
+    int last_coupling_slot; // index into `scalars` of beta_m left by the last driver run (lz_last_coupling)
     // optional per-kernel-class timing (bench.py's roofline leg): CUDA events on ctx->stream
     int prof_on;
     int prof_used;
@@ -78,9 +91,26 @@ struct lz_ctx {
     int *prof_cls;          // class id per pair
     double *prof_bytes;     // algorithmic bytes per pair
     int spmv_variant;       // dev-time A/B knob (env LZ_SPMV_VARIANT: 3 coarse schedule, 20 fine schedule, 9 no staged SpMM)
+    // per-class sums drained from the event ring whenever it fills (lz_ctx.cu), so long timed regions are not truncated
+    int64_t prof_acc_launches[16];
+    double prof_acc_ms[16], prof_acc_bytes[16];
+    // environment knobs, read ONCE per context in lz_ctx_create -- no process-wide statics
+    LzKnobs knobs;
+    // kernels whose dynamic shared-memory opt-in has been applied on THIS context's device
+    // (cudaFuncSetAttribute is per device: a process-wide flag would leave a second GPU without it)
+    const void *attr_funcs[LZ_ATTR_CAP];
+    int n_attr;
+    // operators created on this context (intrusive list): lz_ctx_destroy orphans them, so destroying a
+    // matrix after its context is safe (lz_matrix_destroy never dereferences a dead context)
+    lz_matrix *matrices;
+    // side stream + events for the halo exchange overlapped with the interior SpMV (lz_multi.cu)
+    cudaStream_t side_stream;
+    cudaEvent_t ev_ready, ev_halo;
 };
 
-#define LZ_PROF_CAP 16384
+int lz_func_smem_optin(lz_ctx *ctx, const void *func, int bytes, bool carveout_max = false);
+
+#define LZ_PROF_CAP 32768
 // kernel classes for the profiler
 enum { LZ_K_SPMV = 0, LZ_K_PASSB = 1, LZ_K_PROJECT = 2, LZ_K_UPDATE = 3, LZ_K_SPMM = 4, LZ_K_GRAM = 5, LZ_K_PANEL = 6, LZ_K_SMALL = 7, LZ_K_COMM = 8, LZ_K_UPDPROJ = 9, LZ_K_CLASSES = 10 };
 static_assert(LZ_K_CLASSES == LZ_PROFILE_CLASSES, "profiler class count is part of the C-ABI");
@@ -91,6 +121,26 @@ void lz_prof_end(lz_ctx *ctx);
 #define LZ_SCALARS 8192
 #define LZ_FLAGS 64
 
+// ---- peer-memory communication (lz_multi.cu) ---------------------------------------------------
+// Every rank owns one cudaMalloc'ed ARENA that all other ranks of the box map through CUDA IPC:
+//   [flags | all-reduce slots (2 parities x world senders x cap doubles) | user region (work vectors / panels)]
+// Small reductions and the halo exchange are then plain NVLink stores into the peer's arena followed by a
+// release-store of a sequence number; the receiver spins on its own flag with acquire loads and adds the
+// deposits in rank order (bit-identical result on every rank).  The descriptor lives in device memory.
+#define LZ_MAX_RANKS 16
+struct LzPeerDesc {
+    int world, rank;
+    unsigned long long cap;                               // doubles per all-reduce slot
+    double *slot_at[2][LZ_MAX_RANKS];                     // where THIS rank deposits at peer q (q's slot[parity][rank])
+    unsigned long long *flag_at[2][LZ_MAX_RANKS];         // peer q's flag[parity][rank]
+    double *my_slot[2];                                   // my slot[parity][0]; sender r at + r * cap
+    unsigned long long *my_flag[2];                       // my flag[parity][0 .. world)
+    unsigned long long *halo_flag_at[2];                  // [0] lower neighbour's "from above" flag, [1] upper neighbour's "from below" flag
+    unsigned long long *my_halo_flag;                     // [0] set by my lower neighbour, [1] by my upper neighbour
+    int *err;                                             // set to 1 when a wait gave up (peer lost): results are garbage, no hang
+};
+#define LZ_PEER_SPIN_LIMIT (1u << 27)
+
 int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out);   // grow-only scratch
 int lz_ctx_basis(lz_ctx *ctx, int64_t rows, int cols, double **out);            // vector path: row-tiled slab
 int lz_ctx_basis_blocks(lz_ctx *ctx, int64_t pan, int blocks, double **out);  // block path: back-to-back panels
@@ -98,9 +148,26 @@ int lz_ctx_scratch(lz_ctx *ctx, size_t bytes, void **out);
 // communicator hooks (lz_multi.cu); all enqueue on ctx->stream
 int lz_comm_world(const lz_ctx *ctx);
 int lz_comm_rank(const lz_ctx *ctx);
-int lz_comm_allreduce_sum(lz_ctx *ctx, double *buf, size_t count);
-// u points at the local rows; hlo entries are received just below it, hhi entries just above u[n)
-int lz_comm_halo_exchange(lz_ctx *ctx, double *u, int64_t n, int64_t hlo, int64_t hhi);
+// epilogue applied by the LAST step of an all-reduce (inside the peer kernel, or a one-thread kernel after NCCL)
+struct LzArEpi {
+    double *copy_dst; int copy_idx;     // copy_dst[0] = buf[copy_idx]           (alpha_j = c1[j]); NULL: skip
+    double *beta, *invb; int *flags;    // beta[jn] = sqrt(buf[0]), invb[jn] = 1/beta[jn], breakdown flag; beta NULL: skip
+    int jn;
+};
+int lz_comm_allreduce_sum(lz_ctx *ctx, double *buf, size_t count, const LzArEpi *epi = nullptr);
+// u points at the local rows; hlo entries are received just below it, hhi entries just above u[n).
+// n_below = number of entries the LOWER neighbour owns (its upper halo starts n_below past its own u); peer mode only.
+// side: run on the context's side stream between ev_ready (recorded on the compute stream by the caller) and ev_halo
+int lz_comm_halo_exchange(lz_ctx *ctx, double *u, int64_t n, int64_t hlo, int64_t hhi, int64_t n_below = -1, bool side = false);
+// peer-memory mode: 1 when the arena is mapped on every rank
+int lz_comm_peer(const lz_ctx *ctx);
+const LzPeerDesc *lz_comm_desc(const lz_ctx *ctx);
+unsigned long long lz_comm_next_seq(lz_ctx *ctx);     // sequence number of the next in-kernel all-reduce
+// collective: a user region of at least user_bytes in the symmetric arena and all-reduce slots of ar_cap doubles
+// (falls back to the context's private workspace + NCCL when peer mapping is unavailable)
+int lz_comm_arena(lz_ctx *ctx, size_t user_bytes, size_t ar_cap, void **user);
+// host-side all-gather of four int64 per rank (layout negotiation at the start of a sharded solve)
+int lz_comm_gather4(lz_ctx *ctx, const int64_t mine[4], int64_t *all /* world * 4 */);
 
 // ---- sparse operator -----------------------------------------------------------------
 enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
@@ -113,7 +180,9 @@ enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
 #define LZ_SPMV_CAP 4096         // shared-memory product slots per CTA (32 KB)
 
 struct lz_matrix {
-    lz_ctx *ctx;
+    lz_ctx *ctx;             // NULL once the owning context has been destroyed (orphaned: only destroy is legal)
+    lz_matrix *next, *prev;  // the context's list of live operators
+    int device;              // copied at creation so destroy never needs the context
     int format;
     int64_t n_rows, n_cols, nnz;
     const int32_t *rowptr;   // CSR
@@ -138,6 +207,9 @@ struct lz_matrix {
     double *ybar;            // n_virtual
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
     int64_t halo_lo, halo_hi;        // halo entries below / above the local range
+    // chunks [bnd_lo, bnd_hi) of the fine schedule (mm_*: of the coarse one) hold only rows that reference no halo
+    // column: they can run while the halo exchange is still in flight (lz_multi.cu fills these for shards)
+    int has_split, bnd_lo, bnd_hi, mm_bnd_lo, mm_bnd_hi;
     int64_t global_rows, row_begin;  // position in the global operator
 };
 
@@ -205,6 +277,66 @@ __device__ __forceinline__ uint64_t lz_splitmix64(uint64_t x)
     return x ^ (x >> 31);
 }
 __device__ __forceinline__ double lz_u01(uint64_t x) { return (double)(x >> 11) * (1.0 / 9007199254740992.0); }
+
+// ---- system-scope flag traffic of the peer-memory collectives
+__device__ __forceinline__ void lz_st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lz_ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lz_ld_relaxed_sys(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lz_st_relaxed_sys(double *p, double v)
+{
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// wait until *flag >= seq (bounded: a lost peer must not hang the GPU)
+__device__ __forceinline__ void lz_peer_wait(const unsigned long long *flag, unsigned long long seq, int *err)
+{
+    unsigned int spins = 0;
+    while (lz_ld_acquire_sys(flag) < seq) {
+        if (++spins > LZ_PEER_SPIN_LIMIT) { *err = 1; break; }
+    }
+}
+// One thread all-reduces NS scalars over the ranks of the box: deposit at every peer, release the flag, wait
+// for every peer's deposit, add in rank order.  Called by thread 0 of the last CTA of a reduction kernel.
+template <int NS>
+__device__ __forceinline__ void lz_peer_sum_thread(const LzPeerDesc *pd, unsigned long long seq, double *v)
+{
+    const int p = (int)(seq & 1ull), R = pd->world, me = pd->rank;
+    for (int q = 0; q < R; ++q) {
+        if (q == me) continue;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) lz_st_relaxed_sys(pd->slot_at[p][q] + s, v[s]);
+    }
+    __threadfence_system();
+    for (int q = 0; q < R; ++q)
+        if (q != me) lz_st_release_sys(pd->flag_at[p][q], seq);
+    double acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+    for (int q = 0; q < R; ++q) {
+        if (q == me) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) acc[s] += v[s];
+        } else {
+            lz_peer_wait(pd->my_flag[p] + q, seq, pd->err);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) acc[s] += lz_ld_relaxed_sys(pd->my_slot[p] + (size_t)q * pd->cap + s);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) v[s] = acc[s];
+}
 
 // 256-bit global load of four doubles (sm_100: LDG.E.ENL2.256); pointer must be 32-byte aligned
 __device__ __forceinline__ void lz_ld256(const double *p, double &a, double &b, double &c, double &d)

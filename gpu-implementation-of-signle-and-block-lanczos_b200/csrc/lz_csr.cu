@@ -92,7 +92,7 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaMemcpyAsync(&A->max_row_nnz, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (A->max_row_nnz > A->cap - A->tile && !getenv("LZ_NO_SPLIT")) LZ_TRY(build_split(ctx, A));   // a long row would push chunks off the streaming path
+    if (A->max_row_nnz > A->cap - A->tile && !ctx->knobs.no_split) LZ_TRY(build_split(ctx, A));   // a long row would push chunks off the streaming path
     const int32_t *rp = A->vrowptr ? A->vrowptr : A->rowptr;
     const int64_t rows = A->vrowptr ? A->n_virtual : A->n_rows;
     int64_t nch = (A->nnz + A->tile - 1) / A->tile;
@@ -121,6 +121,10 @@ static lz_matrix *new_matrix(lz_ctx *ctx, int fmt, int64_t n_rows, int64_t n_col
     lz_matrix *A = new lz_matrix();
     memset(A, 0, sizeof(*A));
     A->ctx = ctx;
+    A->device = ctx->device;
+    A->next = ctx->matrices;                 // register with the context (lz_ctx_destroy orphans what is still alive)
+    if (ctx->matrices) ctx->matrices->prev = A;
+    ctx->matrices = A;
     A->format = fmt;
     A->n_rows = n_rows;
     A->n_cols = n_cols;
@@ -434,8 +438,12 @@ int lz_ell_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int width, int la
 int lz_matrix_destroy(lz_matrix *A)
 {
     if (!A) return LZ_OK;
-    cudaSetDevice(A->ctx->device);
-    cudaStreamSynchronize(A->ctx->stream);
+    cudaSetDevice(A->device);
+    if (A->ctx) {                            // still attached: wait for its stream and leave the context's list
+        cudaStreamSynchronize(A->ctx->stream);
+        if (A->prev) A->prev->next = A->next; else A->ctx->matrices = A->next;
+        if (A->next) A->next->prev = A->prev;
+    }                                        // orphaned (context destroyed first): cudaFree synchronises by itself
     if (A->owns) {
         cudaFree((void *)A->rowptr);
         cudaFree((void *)A->colidx);

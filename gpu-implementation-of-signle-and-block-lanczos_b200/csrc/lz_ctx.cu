@@ -52,9 +52,44 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     LZ_CUDA(cudaMemset(c->scalars, 0, sizeof(double) * LZ_SCALARS));
     LZ_CUDA(cudaMemset(c->flags, 0, sizeof(int) * LZ_FLAGS));
     if (const char *e = getenv("LZ_SPMV_VARIANT")) c->spmv_variant = atoi(e);
+    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    auto env_set = [](const char *name) { return getenv(name) ? 1 : 0; };
+    LzKnobs &k = c->knobs;
+    k.spmv_hint = env_set("LZ_SPMV_HINT");
+    k.spmm_hint = env_set("LZ_SPMM_HINT");
+    k.spmm_run = env_int("LZ_SPMM_RUN", 1);
+    k.no_split = env_set("LZ_NO_SPLIT");
+    k.cgs_shape_order = env_int("LZ_CGS_SHAPE_ORDER", 1);
+    if (k.cgs_shape_order < 0 || k.cgs_shape_order > 2) k.cgs_shape_order = 1;
+    k.cgs_upd_mult = env_int("LZ_CGS_UPD_MULT", 3);
+    if (k.cgs_upd_mult < 1) k.cgs_upd_mult = 1;
+    k.cgs_one_cta = env_set("LZ_CGS_ONE_CTA");
+    k.no_cgs_fuse = env_set("LZ_NO_CGS_FUSE");
+    k.cgs_no_slices = env_set("LZ_CGS_NO_SLICES");
+    k.comm_mode = env_int("LZ_COMM", 0);
+    k.no_overlap = env_set("LZ_NO_OVERLAP");
+    k.no_fold = env_set("LZ_NO_FOLD");
+    k.spmm_kernel = env_int("LZ_SPMM_KERNEL", 0);
+    k.block_cgs_fuse = env_int("LZ_BLOCK_CGS_FUSE", 1);
+    k.rmat_reorder = env_int("LZ_REORDER", 1);
     *out = c;
     return LZ_OK;
 }
+
+}  // extern "C"
+
+// one-time (per context, i.e. per device) opt-in to more than 48 KB of dynamic shared memory
+int lz_func_smem_optin(lz_ctx *ctx, const void *func, int bytes, bool carveout_max)
+{
+    for (int i = 0; i < ctx->n_attr; ++i)
+        if (ctx->attr_funcs[i] == func) return LZ_OK;
+    LZ_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (carveout_max) LZ_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (ctx->n_attr < LZ_ATTR_CAP) ctx->attr_funcs[ctx->n_attr++] = func;    // (a full table only costs repeated calls)
+    return LZ_OK;
+}
+
+extern "C" {
 
 int lz_ctx_destroy(lz_ctx *ctx)
 {
@@ -62,6 +97,16 @@ int lz_ctx_destroy(lz_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm) lz_comm_destroy(ctx);
+    // orphan the operators still alive: they keep their device arrays and can be destroyed later
+    for (lz_matrix *A = ctx->matrices; A;) {
+        lz_matrix *nx = A->next;
+        A->ctx = nullptr; A->next = A->prev = nullptr;
+        A = nx;
+    }
+    ctx->matrices = nullptr;
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
     cudaFree(ctx->partials);
     cudaFree(ctx->tickets);
     cudaFree(ctx->scalars);
@@ -126,9 +171,24 @@ int lz_memset(lz_ctx *ctx, void *dptr, int value, size_t bytes)
 
 }  // extern "C"
 
+// fold the recorded pairs into the per-class sums (waits for the last recorded event)
+static void prof_drain(lz_ctx *ctx)
+{
+    if (ctx->prof_used == 0) return;
+    cudaEventSynchronize(ctx->prof_ev[2 * (ctx->prof_used - 1) + 1]);
+    for (int i = 0; i < ctx->prof_used; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) != cudaSuccess) continue;
+        const int c = ctx->prof_cls[i];
+        ctx->prof_acc_launches[c]++; ctx->prof_acc_ms[c] += t; ctx->prof_acc_bytes[c] += ctx->prof_bytes[i];
+    }
+    ctx->prof_used = 0;
+}
+
 void lz_prof_begin(lz_ctx *ctx, int cls, double bytes)
 {
-    if (!ctx->prof_on || ctx->prof_used >= LZ_PROF_CAP) return;
+    if (!ctx->prof_on) return;
+    if (ctx->prof_used >= LZ_PROF_CAP) prof_drain(ctx);       // ring full: one host wait per LZ_PROF_CAP launches
     ctx->prof_cls[ctx->prof_used] = cls;
     ctx->prof_bytes[ctx->prof_used] = bytes;
     cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], ctx->stream);
@@ -154,7 +214,10 @@ int lz_ctx_profile(lz_ctx *ctx, int enable)
         for (int i = 0; i < 2 * LZ_PROF_CAP; ++i) LZ_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
     }
     ctx->prof_on = enable;
-    if (enable) ctx->prof_used = 0;
+    if (enable) {
+        ctx->prof_used = 0;
+        for (int c = 0; c < LZ_K_CLASSES; ++c) { ctx->prof_acc_launches[c] = 0; ctx->prof_acc_ms[c] = 0.0; ctx->prof_acc_bytes[c] = 0.0; }
+    }
     return LZ_OK;
 }
 
@@ -163,14 +226,11 @@ int lz_ctx_profile_read(lz_ctx *ctx, int64_t *launches, double *ms, double *byte
 {
     LZ_CHECK(ctx && launches && ms && bytes, LZ_ERR_INVALID, "lz_ctx_profile_read: NULL argument");
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int c = 0; c < LZ_K_CLASSES; ++c) { launches[c] = 0; ms[c] = 0.0; bytes[c] = 0.0; }
-    for (int i = 0; i < ctx->prof_used; ++i) {
-        float t = 0.f;
-        LZ_CUDA(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
-        const int c = ctx->prof_cls[i];
-        launches[c]++; ms[c] += t; bytes[c] += ctx->prof_bytes[i];
+    prof_drain(ctx);
+    for (int c = 0; c < LZ_K_CLASSES; ++c) {
+        launches[c] = ctx->prof_acc_launches[c]; ms[c] = ctx->prof_acc_ms[c]; bytes[c] = ctx->prof_acc_bytes[c];
+        ctx->prof_acc_launches[c] = 0; ctx->prof_acc_ms[c] = 0.0; ctx->prof_acc_bytes[c] = 0.0;
     }
-    ctx->prof_used = 0;
     return LZ_OK;
 }
 

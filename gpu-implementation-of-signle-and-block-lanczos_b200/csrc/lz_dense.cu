@@ -26,7 +26,7 @@ static int gram_launch(lz_ctx *ctx, int64_t n, int bw, const double *X, int64_t 
     else k_gram_simt<RMX, RMY><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, bw, X, ldx, Y, ldy, gpart);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    k_gram_reduce<<<1, 256, 0, ctx->stream>>>(bw, grid, gpart, G, mode);
+    k_gram_reduce<<<(bw * bw + 7) / 8, 256, 0, ctx->stream>>>(bw, grid, gpart, bw * bw, G, mode);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
@@ -61,7 +61,7 @@ static int panel_launch(lz_ctx *ctx, int64_t n, int bw, const double *T, int64_t
     lz_prof_end(ctx);
     if (gram) {
         if (bw == 8 || bw == 16 || bw == 32) {
-            k_gram_reduce<<<1, 256, 0, ctx->stream>>>(bw, grid, gpart, G, 0);
+            k_gram_reduce<<<(bw * bw + 7) / 8, 256, 0, ctx->stream>>>(bw, grid, gpart, bw * bw, G, 0);
             LZ_LAUNCH_CHECK(ctx);
         } else {
             return gram_launch<RM, RM>(ctx, n, bw, R, ldr, R, ldr, G, 0, gpart, grid);
@@ -99,9 +99,39 @@ int lz_panel2(lz_ctx *ctx, int64_t n, int bw, const double *T1, const double *S1
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     if (G_opt) {
-        k_gram_reduce<<<1, 256, 0, ctx->stream>>>(bw, grid, (const double *)w, G_opt, 0);
+        k_gram_reduce<<<(bw * bw + 7) / 8, 256, 0, ctx->stream>>>(bw, grid, (const double *)w, bw * bw, G_opt, 0);
         LZ_LAUNCH_CHECK(ctx);
     }
+    return LZ_OK;
+}
+
+// G1 = X^T Y1, G2 = X^T Y2 (row-major panels, one read of X); then alpha = sym(G1 - G2 Bm)
+int lz_gram2(lz_ctx *ctx, int64_t n, int bw, const double *X, const double *Y1, const double *Y2, double *G1, double *G2)
+{
+    if (!(bw == 8 || bw == 16 || bw == 32)) {
+        LZ_TRY(lz_gram(ctx, n, bw, true, X, 0, Y1, 0, G1, 0));
+        return lz_gram(ctx, n, bw, true, X, 0, Y2, 0, G2, 0);
+    }
+    const int grid = dense_grid(ctx, n);
+    void *w;
+    LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * 2 * bw * bw, &w));
+    lz_prof_begin(ctx, LZ_K_GRAM, 8.0 * (double)n * bw * 3.0);
+    if (bw == 8) k_gram2_dmma<8><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
+    else if (bw == 16) k_gram2_dmma<16><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
+    else k_gram2_dmma<32><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    k_gram_reduce<<<(bw * bw + 7) / 8, 256, 0, ctx->stream>>>(bw, grid, (const double *)w, 2 * bw * bw, G1, 0);
+    LZ_LAUNCH_CHECK(ctx);
+    k_gram_reduce<<<(bw * bw + 7) / 8, 256, 0, ctx->stream>>>(bw, grid, (const double *)w + bw * bw, 2 * bw * bw, G2, 0);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_alpha_from_grams(lz_ctx *ctx, int bw, const double *G1, const double *G2, const double *Bm, double *alpha)
+{
+    k_alpha_from_grams<<<1, 256, 0, ctx->stream>>>(bw, G1, G2, Bm, alpha);
+    LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
 
@@ -120,12 +150,13 @@ static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int6
     else k_block_project<BW, JB><<<dim3(gx, batches), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, W, gpart);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    if constexpr (BW >= 16) k_block_project_reduce_w<BW, JB><<<J, 256, 0, ctx->stream>>>(J, gx, gpart, C, Cf);
-    else k_block_project_reduce<JB><<<J, 256, 0, ctx->stream>>>(BW, J, gx, gpart, C);
+    if constexpr (BW >= 16) k_block_project_reduce_w<BW, JB><<<J, 1024, 0, ctx->stream>>>(J, gx, gpart, C);
+    else k_block_project_reduce<JB><<<J, 1024, 0, ctx->stream>>>(BW, J, gx, gpart, C);
     LZ_LAUNCH_CHECK(ctx);
-    if (sharded) {      // the coefficients of all ranks' row slabs add up (C and its fragment-ordered negative alike)
-        LZ_TRY(lz_comm_allreduce_sum(ctx, C, (size_t)J * bb));
-        if (BW >= 16) LZ_TRY(lz_comm_allreduce_sum(ctx, Cf, (size_t)J * bb));
+    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, C, (size_t)J * bb));      // the coefficients of all ranks' row slabs add up
+    if constexpr (BW >= 16) {        // fragment-ordered negative for the update kernel (local permutation)
+        k_block_coef_frag<BW><<<J, 256, 0, ctx->stream>>>(J, C, Cf);
+        LZ_LAUNCH_CHECK(ctx);
     }
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * BW * (J + 2));
     if constexpr (BW >= 16) k_block_update_w<BW><<<ugrid < 1 ? 1 : ugrid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, Cf, W);
@@ -156,7 +187,7 @@ int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t
 // sqrtm::My_sqrtm_cusolver (kernels/my_sqrtm_cusolver.hpp:174-361).  Reads the lower triangle.
 // ---------------------------------------------------------------------------------------------
 #define SQ_LD 33
-__global__ void __launch_bounds__(1024) k_sqrtm(int b, double *__restrict__ S, double *__restrict__ Sinv, int *flags)
+__global__ void __launch_bounds__(1024) k_sqrtm(int b, double *__restrict__ S, double *__restrict__ Sinv, int *flags, int jidx)
 {
     __shared__ double A[32 * SQ_LD], V[32 * SQ_LD], cs[32], sn[32], lam[32];
     __shared__ int pp[32], qq[32];
@@ -229,9 +260,14 @@ __global__ void __launch_bounds__(1024) k_sqrtm(int b, double *__restrict__ S, d
             __syncthreads();
         }
     }
+    if (tid < b) lam[tid] = fabs(A[tid + tid * SQ_LD]);
+    __syncthreads();
     if (tid < b) {
-        lam[tid] = fabs(A[tid + tid * SQ_LD]);
-        if (!(lam[tid] > 0.0) || !isfinite(lam[tid])) atomicMin(flags, 0);     // singular / non-finite block
+        // singular (to working precision) or non-finite block: remember the FIRST failing block index.
+        // W^T W of a rank-deficient W has eigenvalues at rounding level relative to the largest one.
+        double lmax = 0.0;
+        for (int i = 0; i < b; ++i) lmax = fmax(lmax, lam[i]);
+        if (!(lam[tid] > (double)b * 2.220446049250313e-16 * lmax) || !isfinite(lam[tid])) atomicMin(flags, jidx);
     }
     __syncthreads();
     if (act) {
@@ -246,11 +282,11 @@ __global__ void __launch_bounds__(1024) k_sqrtm(int b, double *__restrict__ S, d
     }
 }
 
-int lz_sqrtm_launch(lz_ctx *ctx, int b, double *S, double *Sinv, int *flag)
+int lz_sqrtm_launch(lz_ctx *ctx, int b, double *S, double *Sinv, int *flag, int jidx)
 {
     lz_prof_begin(ctx, LZ_K_SMALL, 0.0);
     int threads = ((b * b + 31) / 32) * 32;
-    k_sqrtm<<<1, threads, 0, ctx->stream>>>(b, S, Sinv, flag);
+    k_sqrtm<<<1, threads, 0, ctx->stream>>>(b, S, Sinv, flag, jidx);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     return LZ_OK;
@@ -312,7 +348,7 @@ int lz_mm_ts(lz_ctx *ctx, int64_t n, int b, double beta, double alpha, const dou
 int lz_sqrtm(lz_ctx *ctx, int b, double *S, double *Sinv)
 {
     LZ_CHECK(ctx && S && Sinv && b >= 1 && b <= 32, LZ_ERR_INVALID, "lz_sqrtm: bad arguments (b must be 1..32)");
-    return lz_sqrtm_launch(ctx, b, S, Sinv, ctx->flags + 2);
+    return lz_sqrtm_launch(ctx, b, S, Sinv, ctx->flags + 2, 0);
 }
 
 int lz_copy_row(lz_ctx *ctx, int64_t lc, int b, const double *Q, int64_t ld, double *q, int64_t off)

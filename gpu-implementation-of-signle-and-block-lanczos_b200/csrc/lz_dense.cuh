@@ -141,19 +141,103 @@ k_gram_simt(int64_t n, int bw, const double *__restrict__ X, int64_t ldx, const 
     }
 }
 
-// G = sum over CTA partials (fixed order).  mode 0: G as is; 1: 0.5*G + 0.5*G^T (mm_tt2, lib_utils.hpp:165-202)
-static __global__ void k_gram_reduce(int bw, int n_parts, const double *__restrict__ gpart, double *__restrict__ G, int mode)
+// G = sum over CTA partials (fixed order).  mode 0: G as is; 1: 0.5*G + 0.5*G^T (mm_tt2, lib_utils.hpp:165-202).
+// One warp per output entry: the lanes stride over the partials, then a fixed shuffle tree -- the serial
+// per-thread walk over ~600 partials this replaces cost more than the Gram kernel's own tail.
+// gstride: doubles between consecutive partials (bw*bw, or 2*bw*bw for the two-Gram kernel).
+static __global__ void __launch_bounds__(256)
+k_gram_reduce(int bw, int n_parts, const double *__restrict__ gpart, int gstride, double *__restrict__ G, int mode)
 {
-    __shared__ double tmp[32 * 32];
+    const int lane = threadIdx.x & 31, e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= bw * bw) return;
+    const int p = e % bw, q = e / bw, et = q + p * bw;
+    double s = 0.0, st = 0.0;
+    for (int i = lane; i < n_parts; i += 32) {
+        s += gpart[(size_t)i * gstride + e];
+        if (mode == 1) st += gpart[(size_t)i * gstride + et];
+    }
+    s = lz_warp_sum(s);
+    if (mode == 1) st = lz_warp_sum(st);
+    if (lane == 0) G[e] = mode == 0 ? s : 0.5 * s + 0.5 * st;
+}
+
+// two Gram matrices from one read of X:  G1_partial = X^T Y1,  G2_partial = X^T Y2   (row-major panels).
+// Used for the reference order of the block recurrence when the SpMM cannot subtract Q_{j-1} beta_j itself:
+// alpha_j = sym(Q_j^T (A Q_j - Q_{j-1} beta_j)) = sym(G1 - G2 beta_j) with G1 = Q_j^T (A Q_j), G2 = Q_j^T Q_{j-1}.
+template <int BW>
+__global__ void __launch_bounds__(LZ_DENSE_THREADS)
+k_gram2_dmma(int64_t n, const double *__restrict__ X, const double *__restrict__ Y1, const double *__restrict__ Y2,
+             double *__restrict__ gpart /* [cta][2][BW*BW] */)
+{
+    constexpr int T = BW / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = lane & 3, mm = lane >> 2;
+    double acc[2][T][T][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) acc[h][a][b][0] = acc[h][a][b][1] = 0.0;
+    const int64_t n_slabs = (n + 31) / 32;
+    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
+#pragma unroll 2
+        for (int g = 0; g < 8; ++g) {
+            const int64_t i = slab * 32 + g * 4 + kk;
+            const bool ok = i < n;
+            double xa[T], y1[T], y2[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                xa[t] = ok ? __ldg(X + i * BW + t * 8 + mm) : 0.0;
+                y1[t] = ok ? __ldg(Y1 + i * BW + t * 8 + mm) : 0.0;
+                y2[t] = ok ? __ldg(Y2 + i * BW + t * 8 + mm) : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < T; ++a)
+#pragma unroll
+                for (int b = 0; b < T; ++b) {
+                    lz_dmma(acc[0][a][b][0], acc[0][a][b][1], xa[a], y1[b]);
+                    lz_dmma(acc[1][a][b][0], acc[1][a][b][1], xa[a], y2[b]);
+                }
+        }
+    }
+    __shared__ double sm[BW * BW];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        for (int w = 0; w < LZ_DENSE_WARPS; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int p = a * 8 + mm, q = b * 8 + 2 * kk;
+                        if (w == 0) { sm[p + q * BW] = acc[h][a][b][0]; sm[p + (q + 1) * BW] = acc[h][a][b][1]; }
+                        else { sm[p + q * BW] += acc[h][a][b][0]; sm[p + (q + 1) * BW] += acc[h][a][b][1]; }
+                    }
+            }
+            __syncthreads();
+        }
+        for (int e = threadIdx.x; e < BW * BW; e += LZ_DENSE_THREADS) gpart[((size_t)blockIdx.x * 2 + h) * BW * BW + e] = sm[e];
+        __syncthreads();
+    }
+}
+
+// alpha = sym(G1 - G2 B): one CTA, b x b column-major matrices
+static __global__ void __launch_bounds__(256)
+k_alpha_from_grams(int bw, const double *__restrict__ G1, const double *__restrict__ G2, const double *__restrict__ Bm, double *__restrict__ alpha)
+{
+    __shared__ double t[32 * 32];
     for (int e = threadIdx.x; e < bw * bw; e += blockDim.x) {
-        double s = 0.0;
-        for (int p = 0; p < n_parts; ++p) s += gpart[(size_t)p * bw * bw + e];
-        tmp[e] = s;
+        const int p = e % bw, q = e / bw;
+        double s = G1[e];
+        for (int k = 0; k < bw; ++k) s = fma(-G2[p + k * bw], Bm[k + q * bw], s);
+        t[e] = s;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < bw * bw; e += blockDim.x) {
         const int p = e % bw, q = e / bw;
-        G[e] = mode == 0 ? tmp[e] : 0.5 * tmp[p + q * bw] + 0.5 * tmp[q + p * bw];
+        alpha[e] = 0.5 * t[p + q * bw] + 0.5 * t[q + p * bw];
     }
 }
 
@@ -361,15 +445,18 @@ k_block_project(int64_t n, int J, const double *__restrict__ V, int64_t pan, con
     }
 }
 
-// C[j] = sum over CTAs of the partials of stored block j (fixed order)
+// C[j] = sum over CTAs of the partials of stored block j (fixed order): one warp per entry, lanes stride over the partials
 template <int JB>
-static __global__ void k_block_project_reduce(int bw, int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C)
+static __global__ void __launch_bounds__(1024)
+k_block_project_reduce(int bw, int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C)
 {
     const int j = blockIdx.x, batch = j / JB, jb = j % JB;
-    for (int e = threadIdx.x; e < bw * bw; e += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = warp; e < bw * bw; e += nw) {
         double s = 0.0;
-        for (int p = 0; p < n_parts; ++p) s += gpart[(((size_t)batch * n_parts + p) * JB + jb) * bw * bw + e];
-        C[(size_t)j * bw * bw + e] = s;
+        for (int p = lane; p < n_parts; p += 32) s += gpart[(((size_t)batch * n_parts + p) * JB + jb) * bw * bw + e];
+        s = lz_warp_sum(s);
+        if (lane == 0) C[(size_t)j * bw * bw + e] = s;
     }
 }
 
@@ -512,25 +599,33 @@ k_block_project_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, c
     }
 }
 
-// C[j] = sum of partials (fixed order); Cf[j][kt][nt][lane] = -C_j[16c+4kk+e, 8nt+mm] with kt = 4c+e
+// C[j] = sum of partials (fixed order, one warp per entry)
 template <int BW, int JB>
-static __global__ void k_block_project_reduce_w(int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C,
-                                                double *__restrict__ Cf)
+static __global__ void __launch_bounds__(1024)
+k_block_project_reduce_w(int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C)
+{
+    const int j = blockIdx.x, batch = j / JB, jb = j % JB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = warp; e < BW * BW; e += nw) {
+        double s = 0.0;
+        for (int p = lane; p < n_parts; p += 32) s += gpart[(((size_t)batch * n_parts + p) * JB + jb) * BW * BW + e];
+        s = lz_warp_sum(s);
+        if (lane == 0) C[(size_t)j * BW * BW + e] = s;
+    }
+}
+
+// Cf[j][kt][nt][lane] = -C_j[16c+4kk+e, 8nt+mm] with kt = 4c+e: the update kernel's B fragments.  A separate (local)
+// step so that sharded runs all-reduce C once and permute afterwards.
+template <int BW>
+static __global__ void __launch_bounds__(256)
+k_block_coef_frag(int J, const double *__restrict__ C, double *__restrict__ Cf)
 {
     constexpr int KT = BW / 4, NT = BW / 8;
-    __shared__ double cs[BW * BW];
-    const int j = blockIdx.x, batch = j / JB, jb = j % JB;
-    for (int e = threadIdx.x; e < BW * BW; e += blockDim.x) {
-        double s = 0.0;
-        for (int p = 0; p < n_parts; ++p) s += gpart[(((size_t)batch * n_parts + p) * JB + jb) * BW * BW + e];
-        C[(size_t)j * BW * BW + e] = s;
-        cs[e] = s;
-    }
-    __syncthreads();
+    const int j = blockIdx.x;
     for (int e = threadIdx.x; e < KT * NT * 32; e += blockDim.x) {
         const int lane = e % 32, nt = (e / 32) % NT, kt = e / (32 * NT);
         const int kk = lane & 3, mm = lane >> 2, c = kt / 4, el = kt % 4;
-        Cf[(size_t)j * BW * BW + e] = -cs[(16 * c + 4 * kk + el) + (nt * 8 + mm) * BW];
+        Cf[(size_t)j * BW * BW + e] = -C[(size_t)j * BW * BW + (16 * c + 4 * kk + el) + (nt * 8 + mm) * BW];
     }
 }
 

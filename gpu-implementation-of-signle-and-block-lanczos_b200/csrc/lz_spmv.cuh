@@ -45,7 +45,27 @@ struct LzPassA {
     double *partials;
     unsigned int *ticket;
     double dt;              // EULER mode: step length
+    // sharded runs (peer-memory mode): the last CTA all-reduces the alpha partial over the ranks before publishing it
+    const LzPeerDesc *pd;
+    unsigned long long seq;
+    int alpha_accum;        // add to *alpha_partial instead of overwriting it (second launch of an interior/boundary pair)
+    int alpha_hold;         // first launch of such a pair: only leave the partial, no all-reduce, no alpha_out
 };
+
+// what the last CTA of a fused SpMV does with the grid total of w.q
+__device__ __forceinline__ void lz_alpha_publish(const LzPassA &a, double total)
+{
+    if (a.alpha_accum) total += *a.alpha_partial;
+    if (a.alpha_hold) { *a.alpha_partial = total; return; }
+    if (a.pd) lz_peer_sum_thread<1>(a.pd, a.seq, &total);
+    *a.alpha_partial = total;
+    if (a.alpha_out) *a.alpha_out = total;
+}
+
+// contiguous sub-ranges of the chunk schedule a launch works on: virtual chunk v < n0 is chunk c0 + v, the rest
+// c1 + (v - n0).  Whole operator: {0, n_chunks, 0, n_chunks}.  Sharded operators launch the interior chunks
+// (no halo columns) while the halo exchange is in flight and the two boundary ranges afterwards.
+struct LzChunkRange { int c0, n0, c1, total; };
 
 template <int MODE>
 struct LzRowEpi {
@@ -107,10 +127,7 @@ __device__ __forceinline__ void lz_spmv_finalize(double acc, const LzPassA &a, d
     acc = lz_block_sum<LZ_SPMV_THREADS>(acc, red);
     double total;
     if (lz_grid_sum<LZ_SPMV_THREADS, 1>(&acc, a.partials, a.ticket, red, &total)) {
-        if (threadIdx.x == 0) {
-            *a.alpha_partial = total;
-            if (a.alpha_out) *a.alpha_out = total;
-        }
+        if (threadIdx.x == 0) lz_alpha_publish(a, total);
     }
 }
 
@@ -242,11 +259,13 @@ __device__ __forceinline__ void lz_mbar_arrive(uint64_t *bar)
 
 template <int MODE, int GW, int RW, int STAGES, int CAP, int MINB = 1>
 __global__ void __launch_bounds__((1 + GW + RW) * 32, MINB)
-k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
+k_csr_spmv_ws(const LzChunkRange cr, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
               const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
               const LzPassA args, const int blocked, const int hint)
 {
+    const int n_chunks = cr.total;
+    auto cmap = [&](int v) { return v < cr.n0 ? cr.c0 + v : cr.c1 + (v - cr.n0); };
     constexpr int THREADS = (1 + GW + RW) * 32, GT = GW * 32, RT = RW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *vals_s = reinterpret_cast<double *>(smem_raw);
@@ -275,13 +294,13 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             int p0 = 0, p1 = 0;
-            if (first < last) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
+            if (first < last) { p0 = chunk_ptr[cmap(first)]; p1 = chunk_ptr[cmap(first) + 1]; }
             int it = 0;
             const uint64_t pol = lz_policy_evict_first();
             for (int c = first; c < last; c += step, ++it) {
                 const int slot = it % STAGES;
                 const int cp0 = p0, cp1 = p1;
-                if (c + step < last) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
+                if (c + step < last) { p0 = chunk_ptr[cmap(c + step)]; p1 = chunk_ptr[cmap(c + step) + 1]; }
                 lz_mbar_wait(&freeb[slot], ((it / STAGES) & 1) ^ 1);
                 const int a0 = cp0 & ~3;
                 const int cnt4 = (cp1 - a0) & ~3;
@@ -301,12 +320,12 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
         // ------------------------------------------------------------------ gather warps
         const int gtid = tid - 32;
         int p0 = 0, p1 = 0;
-        if (first < last) { p0 = chunk_ptr[first]; p1 = chunk_ptr[first + 1]; }
+        if (first < last) { p0 = chunk_ptr[cmap(first)]; p1 = chunk_ptr[cmap(first) + 1]; }
         int it = 0;
         for (int c = first; c < last; c += step, ++it) {
             const int slot = it % STAGES;
             const int cp0 = p0, cp1 = p1;
-            if (c + step < last) { p0 = chunk_ptr[c + step]; p1 = chunk_ptr[c + step + 1]; }
+            if (c + step < last) { p0 = chunk_ptr[cmap(c + step)]; p1 = chunk_ptr[cmap(c + step) + 1]; }
             const int a0 = cp0 & ~3, cnt = cp1 - a0, cnt4 = cnt & ~3;
             double *vs = vals_s + (size_t)slot * CAP;
             const int *cs = cols_s + (size_t)slot * CAP;
@@ -338,14 +357,14 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
         // ------------------------------------------------------------------ row warps
         const int rtid = tid - 32 * (1 + GW), rwarp = rtid >> 5;
         int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
-        if (first < last) { nr0 = chunk_row[first]; nr1 = chunk_row[first + 1]; np0 = chunk_ptr[first]; np1 = chunk_ptr[first + 1]; }
+        if (first < last) { nr0 = chunk_row[cmap(first)]; nr1 = chunk_row[cmap(first) + 1]; np0 = chunk_ptr[cmap(first)]; np1 = chunk_ptr[cmap(first) + 1]; }
         int it = 0;
         for (int c = first; c < last; c += step, ++it) {
             const int slot = it % STAGES;
             const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
             if (c + step < last) {
-                nr0 = chunk_row[c + step]; nr1 = chunk_row[c + step + 1];
-                np0 = chunk_ptr[c + step]; np1 = chunk_ptr[c + step + 1];
+                nr0 = chunk_row[cmap(c + step)]; nr1 = chunk_row[cmap(c + step) + 1];
+                np0 = chunk_ptr[cmap(c + step)]; np1 = chunk_ptr[cmap(c + step) + 1];
             }
             const int a0 = cp0 & ~3, cnt = cp1 - a0;
             const double *vs = vals_s + (size_t)slot * CAP;
@@ -409,32 +428,31 @@ k_csr_spmv_ws(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t
         acc = lz_block_sum<THREADS>(acc, red);
         double total;
         if (lz_grid_sum<THREADS, 1>(&acc, args.partials, args.ticket, red, &total)) {
-            if (tid == 0) {
-                *args.alpha_partial = total;
-                if (args.alpha_out) *args.alpha_out = total;
-            }
+            if (tid == 0) lz_alpha_publish(args, total);
         }
     }
 }
 
 template <int MODE, int GW, int RW, int STAGES, int CAP, int MINB = 1>
 static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int ctas_per_sm,
-                                       int blocked = 0, bool coarse = false)
+                                       int blocked = 0, bool coarse = false, int part = 0)
 {
     // coarse: the LZ_SPMM_TILE schedule (plain SpMV prefers the larger chunks, profiles/r01_spmv_variants.md)
     const int n_chunks = coarse ? A->mm_n_chunks : A->n_chunks;
     const int32_t *chunk_row = coarse ? A->mm_chunk_row : A->chunk_row, *chunk_ptr = coarse ? A->mm_chunk_ptr : A->chunk_ptr;
-    static bool attr_set = false;
     const size_t smem = (size_t)STAGES * CAP * 12 + 24 * STAGES;
-    if (!attr_set) {
-        LZ_CUDA(cudaFuncSetAttribute(k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB>, (int)smem));
+    // part 0: all chunks; 1: interior chunks of a sharded operator; 2: its two boundary ranges
+    const int lo = coarse ? A->mm_bnd_lo : A->bnd_lo, hi = coarse ? A->mm_bnd_hi : A->bnd_hi;
+    LzChunkRange cr = {0, n_chunks, 0, n_chunks};
+    if (part == 1) cr = {lo, hi - lo, 0, hi - lo};
+    if (part == 2) cr = {0, lo, hi, lo + (n_chunks - hi)};
+    if (cr.total <= 0) return LZ_OK;
     int grid = ctx->sm_count * ctas_per_sm;
-    if (grid > n_chunks) grid = n_chunks;
+    if (grid > cr.total) grid = cr.total;
     k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
-        n_chunks, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked,
-        getenv("LZ_SPMV_HINT") ? 1 : 0);      // evict-first on the matrix streams measured 4-5 % slower: off
+        cr, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked,
+        ctx->knobs.spmv_hint);      // evict-first on the matrix streams measured 4-5 % slower: off
     return LZ_OK;
 }
 
@@ -463,8 +481,12 @@ k_ell4_spmv(int64_t n_rows, const double *__restrict__ data, const uint32_t *__r
 
 // host-side launcher shared by lz_spmv() and the drivers
 template <int MODE>
-static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args)
+static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int part = 0)
 {
+    if (part != 0 && !(A->format == LZ_FMT_CSR && A->tma_ok && A->has_split)) {
+        lz_set_error("interior/boundary launches need a sharded CSR operator with a chunk split");
+        return LZ_ERR_INVALID;
+    }
     if (A->format == LZ_FMT_ELL4) {
         const unsigned grid = (unsigned)((A->n_rows + LZ_SPMV_THREADS - 1) / LZ_SPMV_THREADS);
         k_ell4_spmv<MODE><<<grid, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->n_rows, A->ell_data, A->ell_idx, x, y, args);
@@ -475,8 +497,8 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
         // every mode (profiles/r01_spmv_variants.md).
         const int v = ctx->spmv_variant;
         const bool coarse = A->mm_chunk_row && (v == 3 || (MODE == LZ_EPI_PLAIN && v != 20));
-        if (coarse) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, 0, true)));
-        else LZ_TRY((lz_launch_ws_variant<MODE, 3, 5, 3, 1024, 5>(ctx, A, x, y, args, 5, 0, false)));
+        if (coarse) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, 0, true, part)));
+        else LZ_TRY((lz_launch_ws_variant<MODE, 3, 5, 3, 1024, 5>(ctx, A, x, y, args, 5, 0, false, part)));
     } else {
         k_csr_spmv<MODE><<<A->n_chunks, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->chunk_row, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
     }
@@ -511,18 +533,16 @@ k_split_combine(int64_t n_rows, const int32_t *__restrict__ vstart, const double
         acc = lz_block_sum<256>(acc, red);
         double total;
         if (lz_grid_sum<256, 1>(&acc, args.partials, args.ticket, red, &total)) {
-            if (threadIdx.x == 0) {
-                *args.alpha_partial = total;
-                if (args.alpha_out) *args.alpha_out = total;
-            }
+            if (threadIdx.x == 0) lz_alpha_publish(args, total);
         }
     }
 }
 
 template <int MODE>
-static inline int lz_spmv_any(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args)
+static inline int lz_spmv_any(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y, const LzPassA &args, int part = 0)
 {
-    if (!A->vrowptr) return lz_launch_spmv<MODE>(ctx, A, x, y, args);
+    if (!A->vrowptr) return lz_launch_spmv<MODE>(ctx, A, x, y, args, part);
+    LZ_CHECK(part == 0, LZ_ERR_INVALID, "row-split operators cannot be launched in parts");
     if (MODE == LZ_EPI_LANCZOS) LZ_TRY(lz_launch_spmv<LZ_EPI_SCALED>(ctx, A, x, A->ybar, args));
     else LZ_TRY(lz_launch_spmv<LZ_EPI_PLAIN>(ctx, A, x, A->ybar, args));
     int64_t want = (A->n_rows + 255) / 256, cap = (int64_t)ctx->sm_count * 8;

@@ -66,11 +66,14 @@ struct LzFinal {
     double *nrm2_out;    // raw total
     int *flags;
     int jn;              // j + 1
-    int finalize;        // 0: only publish the raw local total (sharded runs all-reduce it first)
+    int finalize;        // 0: only publish the raw local total (NCCL-mode sharded runs all-reduce it afterwards)
+    const LzPeerDesc *pd;        // peer-memory mode: the last CTA all-reduces the total over the ranks, then finalises
+    unsigned long long seq;
 };
 
 __device__ __forceinline__ void lz_finalize_beta(const LzFinal &f, double total)
 {
+    if (f.pd) lz_peer_sum_thread<1>(f.pd, f.seq, &total);
     *f.nrm2_out = total;
     if (!f.finalize) return;
     const double b = sqrt(total);
@@ -328,11 +331,9 @@ static inline size_t cgs_fused_smem(int K, int NB)
 
 // CTAs per SM and tile buffers per CTA for the fused kernel: as many CTAs as shared memory allows (up to 4)
 // with double buffering for small K, two single-buffer CTAs for the rest
-static inline void cgs_fused_shape(int K, int *ctas, int *nb)
+static inline void cgs_fused_shape(int K, int order, int *ctas, int *nb)
 {
     const size_t budget = 214 * 1024;
-    static int order = -1;
-    if (order < 0) { const char *e = getenv("LZ_CGS_SHAPE_ORDER"); order = e ? atoi(e) : 1; if (order < 0 || order > 2) order = 1; }
     static const int cand[3][6][2] = {
         {{4, 2}, {2, 2}, {2, 1}, {1, 2}, {1, 2}, {1, 2}},
         {{4, 2}, {4, 1}, {3, 1}, {2, 1}, {1, 2}, {1, 2}},
@@ -347,7 +348,7 @@ static inline void cgs_fused_shape(int K, int *ctas, int *nb)
 // c[k] = sum over CTAs of cpart[cta][k]  (fixed order); optionally all K in one small launch
 __global__ void __launch_bounds__(VT)
 k_cgs_reduce(int K, int n_parts, const double *__restrict__ cpart, double *__restrict__ c,
-             const int *__restrict__ flags, int need_flag)
+             const int *__restrict__ flags, int need_flag, double *__restrict__ alpha_out /* alpha_j = c[K-1] (folded pass B) or NULL */)
 {
     if (need_flag && flags[F_SECOND_SWEEP] == 0) return;
     __shared__ double red[32];
@@ -355,7 +356,10 @@ k_cgs_reduce(int K, int n_parts, const double *__restrict__ cpart, double *__res
     double s = 0.0;
     for (int p = threadIdx.x; p < n_parts; p += VT) s += cpart[(size_t)p * K + k];
     s = lz_block_sum<VT>(s, red);
-    if (threadIdx.x == 0) c[k] = s;
+    if (threadIdx.x == 0) {
+        c[k] = s;
+        if (alpha_out && k == K - 1) *alpha_out = s;
+    }
 }
 
 __global__ void __launch_bounds__(VT)
@@ -439,131 +443,162 @@ __global__ void k_finalize_first(const double *nrm2, double *beta, double *invb,
 // ---------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-struct LzCgs;
-static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, int need_flag, int dgks_test);
-
 struct LzCgs {
     double *V; int64_t ts, cs; double *cpart; double *c; unsigned grid;      // basis element (i,k): V[(i>>5)*ts + k*cs + (i&31)]
 };
 
-// one CGS sweep of w against the first K basis columns; the update's epilogue finalises beta[jn]
+// Sharded runs: a kernel whose last CTA finalises a norm either all-reduces it in place over peer memory (the
+// sequence number is drawn HERE, immediately before the launch, so every rank issues its collectives in the same
+// order) or -- NCCL mode -- only publishes the local total, and finish_norm() adds the all-reduce + finalisation.
+static LzFinal arm_final(lz_ctx *ctx, const LzFinal &fin, bool sharded, bool want_norm)
+{
+    LzFinal f = fin;
+    f.pd = nullptr; f.seq = 0;
+    if (!want_norm) { f.finalize = 0; f.beta = nullptr; return f; }
+    if (sharded) {
+        if (lz_comm_peer(ctx)) { f.pd = lz_comm_desc(ctx); f.seq = lz_comm_next_seq(ctx); f.finalize = 1; }
+        else f.finalize = 0;
+    }
+    return f;
+}
+
+static int finish_norm(lz_ctx *ctx, const LzFinal &f, bool sharded, bool want_norm)
+{
+    if (!sharded || !want_norm || lz_comm_peer(ctx)) return LZ_OK;
+    LzArEpi e;
+    memset(&e, 0, sizeof(e));
+    e.beta = f.beta; e.invb = f.invb; e.flags = f.flags + F_BREAKDOWN; e.jn = f.jn;
+    return lz_comm_allreduce_sum(ctx, f.nrm2_out, 1, &e);
+}
+
+static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, int need_flag, int dgks_test,
+                             bool sharded, bool want_norm)
+{
+    // (a variant that gave each warp one tile and four adjacent columns per load -- fully contiguous 1 KB
+    // reads of the tiled slab -- measured 4 % slower than this generic kernel: profiles/r01_cgs_fusion.md)
+    const int mult = ctx->knobs.cgs_upd_mult;      // default 3 CTAs/SM: 5.9 -> 6.6 TB/s on the row-tiled basis
+    const unsigned want = stream_grid(ctx, n, CGS_TILE), cap = (unsigned)(ctx->sm_count * mult);
+    const LzFinal f = arm_final(ctx, fin, sharded, want_norm);
+    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
+    k_cgs_update<<<want < cap ? want : cap, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
+        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, f, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    return finish_norm(ctx, f, sharded, want_norm);
+}
+
+// partial coefficients -> c (fixed order), all-reduced over the ranks when sharded; alpha_out (optional) receives
+// c[K-1]: with pass B folded into the first sweep, c1[j] = q_j . w IS alpha_j
+static int cgs_reduce(lz_ctx *ctx, const LzCgs &g, int K, int n_parts, int need_flag, bool sharded, double *alpha_out)
+{
+    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, n_parts, g.cpart, g.c, ctx->flags, need_flag, sharded ? nullptr : alpha_out);
+    LZ_LAUNCH_CHECK(ctx);
+    if (!sharded) return LZ_OK;
+    LzArEpi e;
+    memset(&e, 0, sizeof(e));
+    e.copy_dst = alpha_out; e.copy_idx = K - 1;
+    return lz_comm_allreduce_sum(ctx, g.c, (size_t)K, alpha_out ? &e : nullptr);
+}
+
+// one CGS sweep of w against the first K basis columns; the update's epilogue finalises beta[jn] when want_norm
 static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin,
-                     int need_flag, int dgks_test, bool sharded)
+                     int need_flag, int dgks_test, bool sharded, bool want_norm, double *alpha_out)
 {
     const size_t smem_p = sizeof(double) * (VT / 32) * (size_t)K;
     lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
     k_cgs_project<<<g.grid, VT, smem_p, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, need_flag);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)g.grid, g.cpart, g.c, ctx->flags, need_flag);
-    LZ_LAUNCH_CHECK(ctx);
-    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
-    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
-    LZ_TRY(launch_cgs_update(ctx, g, n, K, w, fin, need_flag, dgks_test));
-    lz_prof_end(ctx);
-    return LZ_OK;
-}
-
-static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, int need_flag, int dgks_test)
-{
-    // (a variant that gave each warp one tile and four adjacent columns per load -- fully contiguous 1 KB
-    // reads of the tiled slab -- measured 4 % slower than this generic kernel: profiles/r01_cgs_fusion.md)
-    static int mult = 0;
-    if (!mult) { const char *e = getenv("LZ_CGS_UPD_MULT"); mult = e ? atoi(e) : 3; }      // 3 CTAs/SM: 5.9 -> 6.6 TB/s on the row-tiled basis
-    const unsigned want = stream_grid(ctx, n, CGS_TILE), cap = (unsigned)(ctx->sm_count * mult);
-    k_cgs_update<<<want < cap ? want : cap, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
-        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, fin, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE);
-    LZ_LAUNCH_CHECK(ctx);
-    return LZ_OK;
+    LZ_TRY(cgs_reduce(ctx, g, K, (int)g.grid, need_flag, sharded, alpha_out));
+    return launch_cgs_update(ctx, g, n, K, w, fin, need_flag, dgks_test, sharded, want_norm);
 }
 
 // CGS2 with the middle two basis streams fused: project, [update + project], update.
 // Falls back to two plain sweeps when the tile does not fit in shared memory (large K) or the
 // operands are not 16-byte aligned for the bulk copies.
-static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, bool sharded)
+static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, bool sharded, double *alpha_out)
 {
     int ctas = 1, NB = 2;
-    static int one_cta = -1;
-    if (one_cta < 0) one_cta = getenv("LZ_CGS_ONE_CTA") ? 1 : 0;
-    if (!one_cta) cgs_fused_shape(K, &ctas, &NB);
+    if (!ctx->knobs.cgs_one_cta) cgs_fused_shape(K, ctx->knobs.cgs_shape_order, &ctas, &NB);
     const size_t smem = cgs_fused_smem(K, NB);
-    const bool ok = smem <= 220 * 1024 && K <= CF_MAXC * CF_THREADS && g.cs == CF_R && ((uintptr_t)w % 16 == 0) && !getenv("LZ_NO_CGS_FUSE");
+    const bool ok = smem <= 220 * 1024 && K <= CF_MAXC * CF_THREADS && g.cs == CF_R && ((uintptr_t)w % 16 == 0) && !ctx->knobs.no_cgs_fuse;
     if (!ok) {
-        LZ_TRY(cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded));
-        return cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded);
+        LZ_TRY(cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded, false, alpha_out));
+        return cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded, true, nullptr);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        LZ_CUDA(cudaFuncSetAttribute(k_cgs_update_project, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        LZ_CUDA(cudaFuncSetAttribute(k_cgs_update_project, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
-    }
+    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_cgs_update_project, 220 * 1024, true));
     // sweep 1 projection
     lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
     k_cgs_project<<<g.grid, VT, sizeof(double) * (VT / 32) * (size_t)K, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, 0);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)g.grid, g.cpart, g.c, ctx->flags, 0);
-    LZ_LAUNCH_CHECK(ctx);
-    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
+    LZ_TRY(cgs_reduce(ctx, g, K, (int)g.grid, 0, sharded, alpha_out));
     // sweep 1 update + sweep 2 projection, one basis stream
     const unsigned fgrid = (unsigned)(ctx->sm_count * ctas);
     lz_prof_begin(ctx, LZ_K_UPDPROJ, 8.0 * (double)n * (K + 2));
-    static int no_slices = -1;
-    if (no_slices < 0) no_slices = getenv("LZ_CGS_NO_SLICES") ? 1 : 0;
-    const int S = no_slices ? 1 : cgs_fused_slices(K);
+    const int S = ctx->knobs.cgs_no_slices ? 1 : cgs_fused_slices(K);
     k_cgs_update_project<<<fgrid, CF_THREADS, smem, ctx->stream>>>(n, K, g.V, g.ts, w, g.c, g.cpart, S, NB);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    k_cgs_reduce<<<K, VT, 0, ctx->stream>>>(K, (int)fgrid * S, g.cpart, g.c, ctx->flags, 0);
-    LZ_LAUNCH_CHECK(ctx);
-    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, g.c, (size_t)K));
+    LZ_TRY(cgs_reduce(ctx, g, K, (int)fgrid * S, 0, sharded, nullptr));
     // sweep 2 update (+ ||w||^2, beta finalisation)
-    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
-    LZ_TRY(launch_cgs_update(ctx, g, n, K, w, fin, 0, 0));
-    lz_prof_end(ctx);
-    return LZ_OK;
+    return launch_cgs_update(ctx, g, n, K, w, fin, 0, 0, sharded, true);
 }
 
 __global__ void k_copy_scalar(const double *src, double *dst) { *dst = *src; }
 
-// sharded runs: the local partial has been all-reduced into *nrm2; finalise beta[jn] from it
-__global__ void k_finalize_beta(const double *nrm2, double *beta, double *invb, int *flags, int jn)
-{
-    const LzFinal f = {beta, invb, const_cast<double *>(nrm2), flags, jn, 1};
-    lz_finalize_beta(f, *nrm2);
-}
-
 // The single-vector driver.  Device arrays: alpha[m], beta[m+1], invb[m+1].
 // With a communicator attached to the context (lz_comm_init) the operator is this rank's row slab,
 // b holds the local rows, every gather source carries [lower halo | local | upper halo] and every
-// reduction is completed by an all-reduce before it is consumed; without one the same code runs the
+// reduction is completed over the ranks before it is consumed; without one the same code runs the
 // single-GPU path with no collective at all.
+//
+// Step j (full reorthogonalisation, the default "fold"): pass A  w = A q_j - beta_j q_{j-1} (+ basis column j),
+// then CGS2 against columns 0..j.  The first sweep's coefficient c1[j] = q_j . w is alpha_j, so the reference's
+// separate  w -= alpha_j q_j  pass (vector_lanczos.hpp:60) and its reduction are part of the sweep: three basis
+// streams and -- sharded -- three small collectives per step (c1, c2, ||w||^2).
+// Sharded, overlapped: the boundary planes of q_{j+1} leave for the neighbours on a side stream as soon as the last
+// update of step j retires, the interior chunks of the next pass A (no halo column) run meanwhile, the two
+// boundary chunk ranges follow once the halo has landed.
 static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
                                double *alpha, double *beta, double *invb, double *q)
 {
     const int64_t n = A->n_rows;
     const bool sharded = ctx->comm != nullptr && lz_comm_world(ctx) > 1;
     const int64_t hlo = A->halo_lo, hhi = A->halo_hi;
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_vector_lanczos: the operator belongs to another (or a destroyed) context");
     LZ_CHECK(A->n_cols == n + hlo + hhi, LZ_ERR_INVALID, "lz_vector_lanczos: operator must be square (%lld x %lld)", (long long)n, (long long)A->n_cols);
     LZ_CHECK(sharded || (hlo == 0 && hhi == 0), LZ_ERR_INVALID, "lz_vector_lanczos: a sharded operator needs lz_comm_init");
     LZ_CHECK(lc >= -1 && lc < n, LZ_ERR_INVALID, "lz_vector_lanczos: lc %lld out of range", (long long)lc);
     LZ_CHECK(reorth >= LZ_REORTH_NONE && reorth <= LZ_REORTH_FULL_DGKS, LZ_ERR_INVALID, "lz_vector_lanczos: reorth mode %d", reorth);
     LZ_CHECK(!(sharded && reorth == LZ_REORTH_FULL_DGKS), LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: DGKS reorthogonalisation is single-GPU only");
-    const int64_t ld = round_up(n, 4);
     // three rotating work vectors (the reference's q0, q1, w: test_lanczos.cu:57-59), each laid out
-    // [pad | lower halo | local rows | upper halo] with the local part 32-byte aligned
-    const int64_t off = round_up(hlo, 4);
-    const int64_t stride = round_up(off + n + hhi, 4);
+    // [pad | lower halo | local rows | upper halo] with the local part 32-byte aligned.  Sharded: the layout is
+    // made IDENTICAL on every rank (largest halo / span), so a neighbour's halo region is found by offset.
+    int64_t off = round_up(hlo, 4), span = off + n + hhi, n_below = -1;
+    if (sharded) {
+        const int64_t mine[4] = {hlo, n, hhi, 0};
+        int64_t all[4 * LZ_MAX_RANKS];
+        LZ_TRY(lz_comm_gather4(ctx, mine, all));
+        const int world = lz_comm_world(ctx), rank = lz_comm_rank(ctx);
+        int64_t max_hlo = 0;
+        for (int r = 0; r < world; ++r) max_hlo = all[4 * r] > max_hlo ? all[4 * r] : max_hlo;
+        off = round_up(max_hlo, 4);
+        span = 0;
+        for (int r = 0; r < world; ++r) { const int64_t sp = off + all[4 * r + 1] + all[4 * r + 2]; span = sp > span ? sp : span; }
+        n_below = rank > 0 ? all[4 * (rank - 1) + 1] : 0;
+    }
+    const int64_t stride = round_up(span, 4);
     LzCgs g = {nullptr, 0, 0, nullptr, nullptr, 0};
     const unsigned cgs_grid = stream_grid(ctx, n, CGS_TILE) < (unsigned)(ctx->sm_count * 2)
                                   ? stream_grid(ctx, n, CGS_TILE) : (unsigned)(ctx->sm_count * 2);
     size_t work_bytes = sizeof(double) * (size_t)stride * 3;
     // projection partials: one row of m per CTA; the fused kernel writes S * K <= CF_THREADS entries per CTA
-    const size_t cpart_len = std::max((size_t)cgs_grid * m, (size_t)ctx->sm_count * 4 * CF_THREADS);
+    const size_t cpart_len = std::max((size_t)ctx->sm_count * 2 * m, (size_t)ctx->sm_count * 4 * CF_THREADS);
     if (reorth) work_bytes += sizeof(double) * (cpart_len + m + 8);
     void *work;
-    LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
+    if (sharded) LZ_TRY(lz_comm_arena(ctx, work_bytes, (size_t)m + 8, &work));
+    else LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
     double *u_prev = (double *)work + off, *u_cur = u_prev + stride, *w = u_cur + stride;
     if (reorth) {
         LZ_CHECK(sizeof(double) * (VT / 32) * (size_t)m <= 200 * 1024, LZ_ERR_UNSUPPORTED,
@@ -573,13 +608,13 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         g.grid = cgs_grid;
         LZ_TRY(lz_ctx_basis(ctx, n, m, &g.V));
         g.ts = ctx->basis_ts; g.cs = ctx->basis_cs;
-        static bool attr_set = false;
-        if (!attr_set) {
-            LZ_CUDA(cudaFuncSetAttribute(k_cgs_project, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
+        LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_cgs_project, 200 * 1024));
     }
     double *sc = ctx->scalars;
+    const bool peer = sharded && lz_comm_peer(ctx);
+    const bool fold = reorth == LZ_REORTH_FULL && !ctx->knobs.no_fold;
+    // interior chunks exist and the operator knows them: overlap the halo exchange with them
+    const bool overlap = sharded && !ctx->knobs.no_overlap && A->has_split && A->bnd_hi > A->bnd_lo && A->format == LZ_FMT_CSR && A->tma_ok && !A->vrowptr;
     LZ_CUDA(cudaMemcpyAsync(u_cur, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     // beta[0] = ||b||  (vector_lanczos.hpp:21)
     LZ_TRY(dot_async(ctx, n, b, b, sc + S_NRM2));
@@ -588,45 +623,58 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
     LZ_LAUNCH_CHECK(ctx);
 
     for (int j = 0; j < m; ++j) {
-        if (sharded) LZ_TRY(lz_comm_halo_exchange(ctx, u_cur, n, hlo, hhi));     // neighbours' boundary planes of q_j
+        // neighbours' boundary planes of q_j (unnormalised, like everything in the rotating buffers)
+        if (sharded) LZ_TRY(lz_comm_halo_exchange(ctx, u_cur, n, hlo, hhi, n_below, overlap));
         LzPassA pa;
+        memset(&pa, 0, sizeof(pa));
         pa.x_own = u_cur; pa.u_prev = u_prev; pa.invb = invb; pa.beta = beta;
-        pa.alpha_out = sharded ? nullptr : alpha + j; pa.alpha_partial = sc + S_ALPHA_LOCAL;
+        pa.alpha_out = (sharded || fold) ? nullptr : alpha + j; pa.alpha_partial = sc + S_ALPHA_LOCAL;
         pa.vcol = reorth ? g.V + (size_t)j * g.cs : nullptr;
         pa.vts = g.ts;
         pa.qout = (q && lc >= 0) ? q + j : nullptr;
         pa.lc = lc; pa.j = j; pa.first = (j == 0);
         pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
         lz_prof_begin(ctx, LZ_K_SPMV, 12.0 * (double)A->nnz + 28.0 * (double)n + (reorth ? 8.0 * (double)n : 0.0));
-        LZ_TRY(lz_spmv_any<LZ_EPI_LANCZOS>(ctx, A, u_cur - hlo, w, pa));    // :51,:54,:57
-        lz_prof_end(ctx);
-        if (sharded) {
-            LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_ALPHA_LOCAL, 1));
-            k_copy_scalar<<<1, 1, 0, ctx->stream>>>(sc + S_ALPHA_LOCAL, alpha + j);
-            LZ_LAUNCH_CHECK(ctx);
+        if (overlap) {
+            pa.alpha_hold = 1;
+            LZ_TRY(lz_spmv_any<LZ_EPI_LANCZOS>(ctx, A, u_cur - hlo, w, pa, 1));       // interior chunks: no halo column
+            LZ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+            pa.alpha_hold = 0; pa.alpha_accum = 1;
+            if (peer && !fold) { pa.pd = lz_comm_desc(ctx); pa.seq = lz_comm_next_seq(ctx); pa.alpha_out = alpha + j; }
+            LZ_TRY(lz_spmv_any<LZ_EPI_LANCZOS>(ctx, A, u_cur - hlo, w, pa, 2));       // the two boundary chunk ranges
+        } else {
+            if (peer && !fold) { pa.pd = lz_comm_desc(ctx); pa.seq = lz_comm_next_seq(ctx); pa.alpha_out = alpha + j; }
+            LZ_TRY(lz_spmv_any<LZ_EPI_LANCZOS>(ctx, A, u_cur - hlo, w, pa));          // :51,:54,:57
         }
-        LzFinal fin = {beta, invb, sc + (reorth ? S_NRM2_BEFORE : S_NRM2), ctx->flags, j + 1, sharded ? 0 : 1};
-        lz_prof_begin(ctx, LZ_K_PASSB, 24.0 * (double)n);
-        LZ_TRY(launch_pass_b(ctx, n, w, u_cur, alpha, invb, j, fin));          // :60,:44
         lz_prof_end(ctx);
+        if (sharded && !peer && !fold) {
+            LzArEpi e;
+            memset(&e, 0, sizeof(e));
+            e.copy_dst = alpha + j; e.copy_idx = 0;
+            LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_ALPHA_LOCAL, 1, &e));
+        }
+        const LzFinal fin = {beta, invb, sc + (reorth ? S_NRM2_BEFORE : S_NRM2), ctx->flags, j + 1, 1, nullptr, 0};
+        if (!fold) {
+            const LzFinal fb = arm_final(ctx, fin, sharded, true);
+            lz_prof_begin(ctx, LZ_K_PASSB, 24.0 * (double)n);
+            LZ_TRY(launch_pass_b(ctx, n, w, u_cur, alpha, invb, j, fb));              // :60,:44
+            lz_prof_end(ctx);
+            LZ_TRY(finish_norm(ctx, fb, sharded, true));
+        }
         if (reorth) {
-            LzFinal f2 = {beta, invb, sc + S_NRM2, ctx->flags, j + 1, sharded ? 0 : 1};
+            const LzFinal f2 = {beta, invb, sc + S_NRM2, ctx->flags, j + 1, 1, nullptr, 0};
             if (reorth == LZ_REORTH_FULL) {
-                LZ_TRY(cgs2_fused(ctx, g, n, j + 1, w, f2, sharded));
+                LZ_TRY(cgs2_fused(ctx, g, n, j + 1, w, f2, sharded, fold ? alpha + j : nullptr));
             } else {
-                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, 1, sharded));
-                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 1, 0, sharded));
+                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, 1, sharded, true, nullptr));
+                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 1, 0, sharded, true, nullptr));
             }
-        }
-        if (sharded) {
-            LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_NRM2, 1));
-            k_finalize_beta<<<1, 1, 0, ctx->stream>>>(sc + S_NRM2, beta, invb, ctx->flags, j + 1);
-            LZ_LAUNCH_CHECK(ctx);
         }
         double *t = u_prev; u_prev = u_cur; u_cur = w; w = t;                  // :62 (pointer rotation, no copy)
     }
     k_copy_scalar<<<1, 1, 0, ctx->stream>>>(beta + m, sc + S_BETA_LAST);
     LZ_LAUNCH_CHECK(ctx);
+    ctx->last_coupling_slot = S_BETA_LAST;
     return LZ_OK;
 }
 

@@ -21,6 +21,11 @@ void block_lanczos_blas(Matrix &A, Dense_matrix<type_t> &B, const unsigned int m
     AssertCuda(lz_block_lanczos(lanczos_context(), A.device_operator(), reinterpret_cast<const double *>(B.data()), (int64_t)B.n_rows(), (int)bw,
                                 (int)m, lc, mode, reinterpret_cast<double *>(a.data()), reinterpret_cast<double *>(bt.data()),
                                 reinterpret_cast<double *>(q.data())));
+    // the reference never looks at the eigen-solver's info (utils/lib_utils.hpp:650-745) and carries Inf/NaN on;
+    // here a singular W^T W is reported (the coefficients before the named block are valid)
+    int blocks_done = 0;
+    if (lz_block_status(lanczos_context(), (int)m, &blocks_done) != LZ_OK)
+        std::fprintf(stderr, "block_lanczos: %s (%d of %u blocks valid)\n", lz_last_error(), blocks_done, m);
     for (unsigned int j = 0; j < m; ++j) lzb::dcopy(alpha[j].data(), a.data() + j * bb, bb * sizeof(type_t), LZ_D2D);
     for (unsigned int j = 0; j <= m; ++j) lzb::dcopy(beta[j].data(), bt.data() + j * bb, bb * sizeof(type_t), LZ_D2D);
 }

@@ -75,10 +75,15 @@ void run_vector(Matrix &A, Vector<type_t> &b, const Options &o, unsigned int lc)
     std::cout << "iterations/s: " << m / time.duration() << std::endl;
     const unsigned int k = std::min(o.k, m);
     std::vector<double> theta(k), resid(k);
-    AssertCuda(lz_ritz((int)m, 1, alpha.data(), beta.data(), nullptr, (int)k, theta.data(), resid.data()));
+    double beta_m = 0.0;                                              // coupling to the unbuilt q_{m+1}: residual estimates
+    AssertCuda(lz_last_coupling(lanczos_context(), 1, &beta_m));
+    AssertCuda(lz_ritz((int)m, 1, alpha.data(), beta.data(), &beta_m, (int)k, theta.data(), resid.data()));
     std::cout << "Ritz values (" << k << " extremal): ";
     for (double t : theta) std::cout << std::setprecision(14) << t << " ";
+    std::cout << std::endl << "residual estimates |beta_m y_m|: ";
+    for (double r : resid) std::cout << std::setprecision(4) << r << " ";
     std::cout << std::endl;
+    put("resid", 0, k, resid.data(), 8);
     Vector<type_t> qh = q.copy_to_host();
     put("alpha", 0, m, alpha.data(), 8); put("beta", 0, m, beta.data(), 8); put("q", 0, m, qh.data(), 8);
     put("theta", 0, k, theta.data(), 8);
@@ -147,10 +152,15 @@ void run_block(Matrix &A, Dense_matrix<type_t> &B, const Options &o, unsigned in
     for (unsigned int i = 0; i <= m; ++i) lzb::dcopy(&bt[i * bb], beta[i].data(), bb * 8, LZ_D2H);
     const unsigned int k = std::min<unsigned int>(o.k, m * bw);
     std::vector<double> theta(k), resid(k);
-    AssertCuda(lz_ritz((int)m, (int)bw, a.data(), bt.data(), nullptr, (int)k, theta.data(), resid.data()));
+    std::vector<double> beta_m(bb);                                   // coupling to the unbuilt block: residual estimates
+    AssertCuda(lz_last_coupling(lanczos_context(), (int)bw, beta_m.data()));
+    AssertCuda(lz_ritz((int)m, (int)bw, a.data(), bt.data(), beta_m.data(), (int)k, theta.data(), resid.data()));
     std::cout << "Ritz values (" << k << " extremal): ";
     for (double t : theta) std::cout << std::setprecision(14) << t << " ";
+    std::cout << std::endl << "residual estimates ||beta_m Y_m||: ";
+    for (double r : resid) std::cout << std::setprecision(4) << r << " ";
     std::cout << std::endl;
+    put("resid", 0, k, resid.data(), 8);
     Vector<type_t> qh = q.copy_to_host();
     Dense_matrix<type_t> Th = T.copy_to_host();
     put("alpha", 0, a.size(), a.data(), 8); put("beta", 0, bt.size(), bt.data(), 8); put("q", 0, qh.size(), qh.data(), 8);

@@ -76,6 +76,9 @@ def lib():
         "lz_vector_basis_info": (i32, [vp, P(i64), P(i32)]),
         "lz_vector_basis_copy": (i32, [vp, i32, i32, vp, i64]),
         "lz_block_lanczos": (i32, [vp, vp, vp, i64, i32, i32, i64, i32, vp, vp, vp]),
+        "lz_block_status": (i32, [vp, i32, P(i32)]),
+        "lz_last_coupling": (i32, [vp, i32, vp]),
+        "lz_comm_status": (i32, [vp, P(i32), P(i32)]),
         "lz_ritz": (i32, [i32, i32, vp, vp, vp, i32, vp, vp]),
         "lz_expm_sym": (i32, [i32, vp]),
         "lz_lanczos_solution": (i32, [i32, i32, vp, vp, vp, dbl, vp]),
@@ -88,6 +91,7 @@ def lib():
         "lz_gen_laplacian3d_shard": (i32, [vp, i64, i64, i64, i32, i32, P(vp)]),
         "lz_gen_laplacian2d_shard": (i32, [vp, i64, i64, i32, i32, P(vp)]),
         "lz_vector_lanczos_sharded": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+        "lz_csr_create_shard_host": (i32, [vp, i64, i64, vp, vp, vp, i64, i64, i64, i64, i64, i64, P(vp)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -114,9 +118,17 @@ def _ptr(t):
 
 class Context:
     def __init__(self, device=0, stream=None):
+        import weakref
         self.h = C.c_void_p()
         check(lib().lz_ctx_create(int(device), stream, C.byref(self.h)))
         self.device = device
+        self._children = weakref.WeakSet()        # operators created on this context: closed before it
+
+    def comm_status(self):
+        """(peer_mode, timed_out) of the communicator attached with lz_comm_init."""
+        pm, to = C.c_int(0), C.c_int(0)
+        check(lib().lz_comm_status(self.h, C.byref(pm), C.byref(to)))
+        return pm.value, to.value
 
     def sync(self):
         check(lib().lz_ctx_sync(self.h))
@@ -138,6 +150,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for child in list(self._children):     # children first; the C library also tolerates the other order
+                child.close()
             lib().lz_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -153,6 +167,7 @@ class Matrix:
 
     def __init__(self, ctx, handle, keep=()):
         self.ctx, self.h, self._keep = ctx, handle, keep
+        ctx._children.add(self)
         nr, nc, nnz = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib().lz_matrix_info(self.h, C.byref(nr), C.byref(nc), C.byref(nnz)))
         self.n_rows, self.n_cols, self.nnz = nr.value, nc.value, nnz.value
@@ -234,6 +249,15 @@ class Matrix:
         check(lib().lz_gen_laplacian2d_shard(ctx.h, nx, ny, world_size, rank, C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def from_csr_shard_host(cls, ctx, rowptr, colidx, vals, halo_lo, halo_hi, global_rows, row_begin, bnd_lo_rows=0, bnd_hi_rows=None):
+        """Row slab from host arrays (numpy / pinned torch CPU tensors), local column index space."""
+        n = len(rowptr) - 1
+        h = C.c_void_p()
+        check(lib().lz_csr_create_shard_host(ctx.h, n, len(vals), _ptr(rowptr), _ptr(colidx), _ptr(vals), halo_lo, halo_hi,
+                                             global_rows, row_begin, bnd_lo_rows, n if bnd_hi_rows is None else bnd_hi_rows, C.byref(h)))
+        return cls(ctx, h)
+
     def csr_to_host(self):
         """(rowptr, colidx, vals) numpy copies of the device CSR arrays."""
         rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -298,6 +322,22 @@ def vector_lanczos_async(ctx, A, b, m, alpha_dev, beta_dev, lc=0, reorth=REORTH_
 
 def block_lanczos(ctx, A, B, ldb, bw, m, alpha, beta, q, lc=0, reorth=REORTH_NONE):
     check(lib().lz_block_lanczos(ctx.h, A.h, _ptr(B), ldb, bw, m, lc, reorth, _ptr(alpha), _ptr(beta), _ptr(q)))
+
+
+def block_status(ctx, m):
+    """blocks of the last block run that are valid (m unless a beta_j was singular / non-finite)."""
+    done = C.c_int(0)
+    st = lib().lz_block_status(ctx.h, m, C.byref(done))
+    if st != LZ_OK and st != -4:
+        check(st)
+    return done.value
+
+
+def last_coupling(ctx, bw=1):
+    """beta_m of the last run on this context, (bw, bw) numpy array (row, col)."""
+    out = np.zeros(bw * bw)
+    check(lib().lz_last_coupling(ctx.h, bw, out.ctypes.data))
+    return out.reshape(bw, bw).T.copy()
 
 
 def ritz(alpha, beta, k, bw=1, beta_last=None):

@@ -176,6 +176,16 @@ int lz_vector_basis_copy(lz_ctx *ctx, int j0, int ncols, double *dst, int64_t ld
 int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t ldb, int bw, int m,
                      int64_t lc, int reorth, double *alpha, double *beta, double *q);
 
+/* Outcome of the last lz_block_lanczos run on this context (synchronises).  *blocks_done = m when every
+ * W^T W was positive definite to working precision; otherwise the index j of the first singular / non-finite
+ * beta_j -- alpha[0..j) and beta[0..j] are valid -- and the call returns LZ_ERR_BREAKDOWN.  The reference never
+ * looks (cusolver info is ignored, utils/lib_utils.hpp:650-745); the vector driver reports the same through
+ * steps_done. */
+int lz_block_status(lz_ctx *ctx, int m, int *blocks_done);
+/* beta_m of the last run on this context -- the coupling to the next, unbuilt Lanczos vector / block -- copied to
+ * HOST (bw*bw doubles, column-major; bw = 1 after a vector run).  Input of lz_ritz's residual estimate. */
+int lz_last_coupling(lz_ctx *ctx, int bw, double *beta_last_host);
+
 /* ---- Ritz extraction (the syevd(T) inside expm_cusolver, lib_utils.hpp:542-590) ---- */
 /* alpha_host/beta_host: m blocks of bw*bw each (bw = 1: the scalar series; beta[0] is ignored, the
  * coupling blocks are beta[1..m-1]); beta_last_host: the bw*bw block beta_m coupling to the next
@@ -210,6 +220,10 @@ int lz_fdtd_block(lz_ctx *ctx, const lz_matrix *A, const double *U0, int64_t ldu
 int lz_comm_unique_id(void *id128_host);
 int lz_comm_init(lz_ctx *ctx, int world_size, int rank, const void *id128_host);
 int lz_comm_destroy(lz_ctx *ctx);
+/* *peer_mode = 1 when small reductions and halo exchanges run over CUDA-IPC peer memory (NVLink stores + flags)
+ * instead of NCCL; *timed_out = 1 when a peer-memory wait gave up because a rank disappeared (every result since
+ * is invalid).  Synchronises.  LZ_COMM=1 in the environment forces NCCL, LZ_COMM=2 makes peer memory mandatory. */
+int lz_comm_status(lz_ctx *ctx, int *peer_mode, int *timed_out);
 /* contiguous row-block partition (host logic): rows are dealt in whole granules (a grid plane /
  * line for the stencil operators, 1 for anything else); rank r owns rows [begin,end) */
 int lz_partition_rows(int64_t n_rows, int64_t granule, int world_size, int rank, int64_t *begin, int64_t *end);
@@ -219,6 +233,15 @@ int lz_partition_rows(int64_t n_rows, int64_t granule, int world_size, int rank,
 int lz_gen_laplacian3d_shard(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int world_size,
                              int rank, lz_matrix **out);
 int lz_gen_laplacian2d_shard(lz_ctx *ctx, int64_t nx, int64_t ny, int world_size, int rank,
+                             lz_matrix **out);
+/* row slab of ANY square operator from HOST CSR arrays (the sharded twin of lz_csr_create_host): rows
+ * [row_begin, row_begin + n_local) of a global_rows x global_rows operator, column ids already shifted into the local
+ * index space [lower halo | local | upper halo] with halo_lo / halo_hi entries owned by ranks r-1 / r+1 (contiguous
+ * row-block partitions of banded operators).  Rows [0, bnd_lo_rows) are those that touch the lower halo, rows
+ * [bnd_hi_rows, n_local) the upper one: the chunks in between run while the halo exchange is in flight. */
+int lz_csr_create_shard_host(lz_ctx *ctx, int64_t n_local, int64_t nnz, const int32_t *rowptr_host,
+                             const int32_t *colidx_host, const double *vals_host, int64_t halo_lo, int64_t halo_hi,
+                             int64_t global_rows, int64_t row_begin, int64_t bnd_lo_rows, int64_t bnd_hi_rows,
                              lz_matrix **out);
 /* sharded single-vector Lanczos: b_local holds this rank's rows; halo exchange with the two
  * neighbouring ranks before every SpMV, packed all-reduce of the alpha / beta^2 partials.

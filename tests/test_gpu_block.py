@@ -173,6 +173,79 @@ def test_block_lanczos_laplacian_vs_oracle(lz, ctx, orc, bw):
         assert th[0] > 0 and th[-1] < 12
 
 
+def test_block_breakdown_is_reported(lz, ctx, orc):
+    """A rank-deficient start block (two equal columns): B^T B is singular, the reference would carry Inf/NaN on
+    silently; lz_block_status names the first failing block and returns LZ_ERR_BREAKDOWN."""
+    nx, ny, nz, bw, m = 12, 10, 8, 8, 4
+    n = nx * ny * nz
+    A = lz.Matrix.laplacian3d(ctx, nx, ny, nz)
+    B = orc.start_block(n, bw)
+    good = run_block(lz, ctx, A, B, m, 0)
+    assert lz.block_status(ctx, m) == m and np.all(np.isfinite(good[0]))
+    B[:, 3] = B[:, 1]
+    run_block(lz, ctx, A, B, m, 0)
+    assert lz.block_status(ctx, m) == 0
+    import ctypes as C
+    done = C.c_int(-1)
+    assert lz.lib().lz_block_status(ctx.h, m, C.byref(done)) == -4 and done.value == 0
+
+
+@pytest.mark.parametrize("bw", [8, 16])
+def test_block_recurrence_order_long_run_without_reorth(lz, ctx, orc, bw):
+    """200 blocks without reorthogonalisation against the oracle, which follows the reference's order (W -= Q0 beta_j
+    BEFORE alpha_j is formed, methods/block_lanczos.hpp:152-155).  bw = 16 runs the SpMM with the fused DMMA
+    subtraction, bw = 8 the two-Gram formulation alpha_j = sym(G1 - G2 beta_j): both must reproduce the reference
+    order to 1e-10 over the first 12 blocks (50 scalar steps at b = 4) and keep T's Ritz values to 1e-8 over the
+    whole run, where round 1's pre-subtraction alpha let sym(beta_j^T Q0^T Q1) leak into alpha_j."""
+    nx, ny, nz, m = 16, 14, 12, 200 if bw == 8 else 120
+    csr = orc.lap3d(nx, ny, nz)
+    n = nx * ny * nz
+    B = orc.start_block(n, bw)
+    A = lz.Matrix.laplacian3d(ctx, nx, ny, nz)
+    ref = orc.block_lanczos(csr, B, m, lc=3, reorth=0)
+    a, b, q = run_block(lz, ctx, A, B, m, 3, reorth=0)
+    assert lz.block_status(ctx, m) == m
+    assert block_err(a, ref["alpha"], 12) < 1e-10 and block_err(b, ref["beta"], 12) < 1e-10
+    # alpha_j stays symmetric and T's extremal Ritz values agree over the whole run
+    assert max(np.max(np.abs(a[j] - a[j].T)) for j in range(m)) < 1e-12
+    th = np.linalg.eigvalsh(orc.assemble_T(a, b))
+    tr = np.linalg.eigvalsh(orc.assemble_T(ref["alpha"], ref["beta"]))
+    assert abs(th[0] - tr[0]) < 1e-8 and abs(th[-1] - tr[-1]) < 1e-8
+    # beta_m (coupling to the unbuilt block) is exposed for residual estimates
+    bl = lz.last_coupling(ctx, bw)
+    assert np.all(np.isfinite(bl)) and np.max(np.abs(bl - bl.T)) < 1e-10 * np.abs(bl).max()
+
+
+@pytest.mark.parametrize("reorth", [0, 1])
+def test_full_size_config3_parity(lz, ctx, orc, reorth):
+    """BASELINE config 3 at FULL size (256^3, b = 16): 6 blocks against the oracle on the same operator and start
+    block, block coefficients to 1e-10 (north_star tolerance), with and without block CGS2."""
+    nx, bw, m = 256, 16, 6
+    n = nx ** 3
+    orc.set_threads(__import__("os").cpu_count() or 4)
+    try:
+        csr = orc.lap3d(nx, nx, nx)
+        B = orc.start_block(n, bw)
+        ref = orc.block_lanczos(csr, B, m, lc=12345, reorth=reorth)
+    finally:
+        orc.set_threads(1)
+    del csr
+    A = lz.Matrix.laplacian3d(ctx, nx, nx, nx)
+    Bd = torch.empty(n * bw, dtype=torch.float64, device="cuda")
+    lz.check(lz.lib().lz_gen_start_block(ctx.h, n, bw, n, 0x5EED, Bd.data_ptr()))
+    alpha = torch.zeros(m * bw * bw, dtype=torch.float64, device="cuda")
+    beta = torch.zeros((m + 1) * bw * bw, dtype=torch.float64, device="cuda")
+    q = torch.zeros(m * bw, dtype=torch.float64, device="cuda")
+    lz.block_lanczos(ctx, A, Bd, n, bw, m, alpha, beta, q, lc=12345, reorth=reorth)
+    assert lz.block_status(ctx, m) == m
+    a = alpha.cpu().numpy().reshape(m, bw, bw).transpose(0, 2, 1)
+    b = beta.cpu().numpy().reshape(m + 1, bw, bw).transpose(0, 2, 1)
+    assert block_err(a, ref["alpha"], m) < 1e-10, block_err(a, ref["alpha"], m)
+    assert block_err(b, ref["beta"], m) < 1e-10, block_err(b, ref["beta"], m)
+    assert np.max(np.abs(q.cpu().numpy() - ref["q"])) < 1e-10 * np.abs(ref["q"]).max()
+    A.close()
+
+
 def test_full_size_config3_properties(lz, ctx):
     """BASELINE config 3 shape: 256^3 7-point Laplacian (16.7 M rows), b = 16.  Size-independent checks:
     beta blocks symmetric positive definite, alpha symmetric, Ritz values inside (0, 12), and the
@@ -206,7 +279,21 @@ def test_rmat_device_build_matches_oracle_and_block_parity(lz, ctx, orc):
     """config 4 shape at reduced scale: R-MAT graph Laplacian (power-law rows; the reference's ELL cannot
     hold it).  The device-built CSR equals the oracle's numpy construction exactly, SpMV agrees on the
     hub rows (long-row paths), and block Lanczos b = 32 matches the oracle."""
-    scale = 12
+    _rmat_case(lz, ctx, orc, 12, 6, 40)
+
+
+def test_rmat_scale18_parity(lz, ctx, orc):
+    """config 4 at the largest scale the CPU oracle finishes quickly (2^18 rows, 8 M non-zeros, hub rows of
+    tens of thousands of entries): device-built CSR identical to the oracle's, SpMV on the row-split schedule,
+    block Lanczos b = 32 (6 blocks) and 40 reorthogonalised vector steps to 1e-10."""
+    orc.set_threads(__import__("os").cpu_count() or 4)
+    try:
+        _rmat_case(lz, ctx, orc, 18, 6, 40)
+    finally:
+        orc.set_threads(1)
+
+
+def _rmat_case(lz, ctx, orc, scale, m, mv):
     rp, ci, va = orc.rmat_laplacian(scale)
     A = lz.Matrix.rmat_laplacian(ctx, scale)
     got = A.csr_to_host()
@@ -220,14 +307,14 @@ def test_rmat_device_build_matches_oracle_and_block_parity(lz, ctx, orc):
     ctx.sync()
     ref = orc.spmv((rp, ci, va), x)
     assert np.max(np.abs(y.cpu().numpy() - ref)) < 1e-11 * np.abs(ref).max()
-    bw, m = 32, 6
+    bw = 32
     B = orc.start_block(n, bw)
     o = orc.block_lanczos((rp, ci, va), B, m, lc=7)
     a, b, q = run_block(lz, ctx, A, B, m, 7)
     assert block_err(a, o["alpha"], m) < 1e-10 and block_err(b, o["beta"], m) < 1e-10
     # without reorthogonalisation two roundings of this recurrence part ways once the dominant Ritz value
     # has converged (~15 steps on this spectrum), so the 40-step comparison runs with full reorth
-    al, be, steps = lz.vector_lanczos(ctx, A, dev(B[:, 0].copy()), 40, reorth=1)
-    ov = orc.vector_lanczos((rp, ci, va), B[:, 0].copy(), 40, reorth=1)
+    al, be, steps = lz.vector_lanczos(ctx, A, dev(B[:, 0].copy()), mv, reorth=1)
+    ov = orc.vector_lanczos((rp, ci, va), B[:, 0].copy(), mv, reorth=1)
     assert np.max(np.abs(al - ov["alpha"])) < 1e-10 * np.abs(ov["alpha"]).max()
     assert np.max(np.abs(be - ov["beta"]) / ov["beta"]) < 1e-10

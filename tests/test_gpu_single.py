@@ -196,6 +196,27 @@ def test_vector_lanczos_breakdown_reported(lz, ctx, orc):
     assert steps == 1 and alpha[0] == 2.0 and beta[0] == 8.0
 
 
+def test_full_size_config2_parity(lz, ctx, orc):
+    """BASELINE config 2 at FULL size (4096^2, 16.7 M rows, CGS2 against the stored basis): the first 50 steps
+    against the oracle on the same operator and start vector, alpha/beta to relative 1e-10 (north_star)."""
+    nx = ny = 4096
+    n, m = nx * ny, 50
+    orc.set_threads(__import__("os").cpu_count() or 4)
+    try:
+        ref = orc.vector_lanczos(orc.lap2d(nx, ny), orc.start_vector(n), m, reorth=1)
+    finally:
+        orc.set_threads(1)
+    A = lz.Matrix.laplacian2d(ctx, nx, ny)
+    b = torch.empty(n, dtype=torch.float64, device="cuda")
+    lz.check(lz.lib().lz_gen_start_vector(ctx.h, n, 0x5EED, b.data_ptr()))
+    alpha, beta, steps = lz.vector_lanczos(ctx, A, b, m, reorth=1)
+    assert steps == m
+    ea, eb = coeff_err(alpha, beta, ref["alpha"], ref["beta"], 50)
+    assert ea < 1e-10 and eb < 1e-10, (ea, eb)
+    # the same solve with pass B kept separate (LZ_NO_FOLD path) is exercised in tests/test_gpu_paths.py
+    A.close()
+
+
 def test_full_size_config2_properties(lz, ctx):
     """BASELINE config 2 shape (4096^2, 16.7 M rows): size-independent properties only.
     T's eigenvalues lie inside the analytic spectrum; the extreme Ritz values move monotonically
