@@ -162,10 +162,34 @@ k_spmm_rm(int64_t n_rows, const int32_t *__restrict__ rowptr, const int32_t *__r
 // per row.  A group of LW lanes owns a row, two rows per group in flight.
 // ---------------------------------------------------------------------------------------------
 #define SPMM_WS_RCAP 1024      // rowptr entries staged per chunk
+// default L2 policy bits of the fused (A X - Q0 B) kernel: the extra Q0 stream otherwise pushes the gathered panel's
+// reuse window out of L2 (3.2 ms instead of 1.4 ms on 256^3, b = 16: profiles/r02_spmm.md)
+#define LZ_SPMM_HINT_FUSED 15
 
 __device__ __forceinline__ void lz_ld256_ro(const double *p, double &a, double &b, double &c, double &d)
 {
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// the same loads / stores with an L2 eviction policy (createpolicy descriptor): the gathered panel is the only
+// operand of the SpMM that is re-read, so it can be pinned (evict-last) while the streams pass through (evict-first)
+__device__ __forceinline__ void lz_ld256_ro_pol(const double *p, double &a, double &b, double &c, double &d, uint64_t pol)
+{
+    asm("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void lz_ld256_stream_pol(const double *p, double &a, double &b, double &c, double &d, uint64_t pol)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void lz_st256_pol(double *p, double a, double b, double c, double d, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t lz_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 
 // A group of LW = BW/4 lanes owns a row and every lane carries FOUR adjacent columns (one 256-bit
@@ -239,7 +263,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                 if (cp1 - a0 > CAP || cnt4 == 0) { lz_mbar_arrive(&full[slot]); continue; }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 lz_mbar_expect_tx(&full[slot], (uint32_t)cnt4 * 12u + (rows_ok ? (uint32_t)rcnt * 4u : 0u));
-                if (hint) {
+                if (hint & 1) {
                     lz_bulk_g2s_hint(vals_s + (size_t)slot * CAP, vals + a0, (uint32_t)cnt4 * 8u, &full[slot], pol);
                     lz_bulk_g2s_hint(cols_s + (size_t)slot * CAP, colidx + a0, (uint32_t)cnt4 * 4u, &full[slot], pol);
                     if (rows_ok) lz_bulk_g2s_hint(rptr_s + (size_t)slot * SPMM_WS_RCAP, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot], pol);
@@ -253,6 +277,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     } else {
         // ------------------------------------------------------------------ compute warps
         const int sub = lane / LW, l = lane % LW;
+        const uint64_t pol_first = lz_policy_evict_first(), pol_last = lz_policy_evict_last();
         int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
         int v = vchunk(0);
         if (v < n_virtual) { const int c = cmap(v); nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
@@ -286,7 +311,10 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                 double q0, q1, q2, q3;
                 if (FSUB) {       // this lane's Q0 row segment = its A fragments; issued before the gathers
                     q0 = q1 = q2 = q3 = 0.0;
-                    if (valid) lz_ld256_stream(Q0 + r * BW + 4 * l, q0, q1, q2, q3);
+                    if (valid) {
+                        if (hint & 4) lz_ld256_stream_pol(Q0 + r * BW + 4 * l, q0, q1, q2, q3, pol_first);
+                        else lz_ld256_stream(Q0 + r * BW + 4 * l, q0, q1, q2, q3);
+                    }
                 }
                 double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
                 const double *Xl = X + 4 * l;
@@ -305,7 +333,10 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         x0[g] = x1[g] = x2[g] = x3[g] = 0.0;
-                        if (cc[g] >= 0) lz_ld256_ro(Xl + (int64_t)cc[g] * BW, x0[g], x1[g], x2[g], x3[g]);
+                        if (cc[g] >= 0) {
+                            if (hint & 8) lz_ld256_ro_pol(Xl + (int64_t)cc[g] * BW, x0[g], x1[g], x2[g], x3[g], pol_last);
+                            else lz_ld256_ro(Xl + (int64_t)cc[g] * BW, x0[g], x1[g], x2[g], x3[g]);
+                        }
                     }
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
@@ -314,6 +345,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                     }
                 }
                 if (FSUB) {
+                    __syncwarp();     // the gather loop above has per-row trip counts: the MMAs need the whole warp
                     // (acc0,acc1) / (acc2,acc3) are the C fragments of n-tiles 0 / 1, q0..q3 the A fragments of k-tiles 0..3
                     lz_dmma(acc0, acc1, q0, sbs[(0 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q0, sbs[(0 * 2 + 1) * 32 + lane]);
                     lz_dmma(acc0, acc1, q1, sbs[(1 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q1, sbs[(1 * 2 + 1) * 32 + lane]);
@@ -321,7 +353,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                     lz_dmma(acc0, acc1, q3, sbs[(3 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q3, sbs[(3 * 2 + 1) * 32 + lane]);
                 }
                 if (valid) {
-                    if (hint) lz_st256_stream(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                    if (hint & 2) lz_st256_pol(W + r * BW + 4 * l, acc0, acc1, acc2, acc3, pol_first);
                     else lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
                 }
             }
@@ -348,7 +380,7 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
     const int per_cta = (cr.total + grid - 1) / grid;
     k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
         nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
-        ctx->knobs.spmm_hint);      // evict-first streams: +5 % when the far neighbours miss L2, -3 % when they hit: off
+        ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : (FSUB ? LZ_SPMM_HINT_FUSED : 0));
     return LZ_OK;
 }
 
@@ -403,8 +435,12 @@ k_spmm_rm_ell4(int64_t n_rows, const double *__restrict__ data, const uint32_t *
     W[r * BW + c] = a;
 }
 
-// column-major SpMM of the C-ABI (reference layout): one thread per row keeps its row of A in
-// registers and walks the b columns; gathers are coalesced across rows for banded operators.
+// column-major SpMM of the C-ABI (reference layout, spmm(): kernels/spmv_spmm.hpp:262-333): one thread per row keeps
+// its row of A in registers and walks the b columns FOUR at a time, so 4 x (row length) independent gathers are in
+// flight per thread; for banded operators the gathers of a warp's 32 consecutive rows coalesce into 256-byte
+// segments of each column, and Y is written in full lines.  Products and sums are separate roundings in the
+// row's storage order (the reference Host loop, objects/ell_matrix.hpp:246-251): bit-exact against the oracle.
+template <int CG>
 __global__ void __launch_bounds__(SPMM_THREADS)
 k_spmm_cm(int64_t n_rows, int b, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
           const double *__restrict__ vals, const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy)
@@ -416,7 +452,24 @@ k_spmm_cm(int64_t n_rows, int b, const int32_t *__restrict__ rowptr, const int32
         int c[8]; double v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { c[k] = (s + k < e) ? colidx[s + k] : 0; v[k] = (s + k < e) ? vals[s + k] : 0.0; }
-        for (int col = 0; col < b; ++col) {
+        int col = 0;
+        for (; col + CG <= b; col += CG) {
+            double t[CG], x[CG][8];
+#pragma unroll
+            for (int u = 0; u < CG; ++u) {
+                const double *xc = X + (int64_t)(col + u) * ldx;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[u][k] = (s + k < e) ? __ldg(xc + c[k]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < CG; ++u) {
+                t[u] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (s + k < e) t[u] = __dadd_rn(t[u], __dmul_rn(v[k], x[u][k]));
+                Y[r + (int64_t)(col + u) * ldy] = t[u];
+            }
+        }
+        for (; col < b; ++col) {
             const double *xc = X + (int64_t)col * ldx;
             double t = 0.0;
 #pragma unroll
@@ -570,6 +623,7 @@ int lz_fdtd_block(lz_ctx *ctx, const lz_matrix *A, const double *U0, int64_t ldu
 {
     LZ_CHECK(ctx && A && U0 && result_host && nsteps >= 1 && bw >= 1 && bw <= 32, LZ_ERR_INVALID, "lz_fdtd_block: bad arguments");
     const int64_t n = A->n_rows;
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_fdtd_block: the operator belongs to another (or a destroyed) context");
     LZ_CHECK(A->n_cols == n && A->halo_lo == 0 && A->halo_hi == 0, LZ_ERR_INVALID, "lz_fdtd_block: operator must be square and unsharded");
     LZ_CHECK(ldu >= n && lc >= 0 && lc < n, LZ_ERR_INVALID, "lz_fdtd_block: bad leading dimension or lc");
     LZ_CUDA(cudaSetDevice(ctx->device));
@@ -596,10 +650,11 @@ int lz_spmm(lz_ctx *ctx, const lz_matrix *A, int b, const double *X, int64_t ldx
     LZ_CHECK(ctx && A && X && Y && b >= 1, LZ_ERR_INVALID, "lz_spmm: bad arguments");
     LZ_CHECK(ldx >= A->n_cols && ldy >= A->n_rows, LZ_ERR_INVALID, "lz_spmm: leading dimensions too small");
     LZ_CHECK(X != Y, LZ_ERR_INVALID, "lz_spmm: X and Y must not alias");
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_spmm: the operator belongs to another (or a destroyed) context");
     const unsigned grid = (unsigned)((A->n_rows + SPMM_THREADS - 1) / SPMM_THREADS);
     lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 4.0 * (double)A->n_rows + 16.0 * (double)A->n_rows * b);
     if (A->format == LZ_FMT_ELL4) k_spmm_cm_ell4<<<grid, SPMM_THREADS, 0, ctx->stream>>>(A->n_rows, b, A->ell_data, A->ell_idx, X, ldx, Y, ldy);
-    else k_spmm_cm<<<grid, SPMM_THREADS, 0, ctx->stream>>>(A->n_rows, b, A->rowptr, A->colidx, A->vals, X, ldx, Y, ldy);
+    else k_spmm_cm<2><<<grid, SPMM_THREADS, 0, ctx->stream>>>(A->n_rows, b, A->rowptr, A->colidx, A->vals, X, ldx, Y, ldy);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     return LZ_OK;

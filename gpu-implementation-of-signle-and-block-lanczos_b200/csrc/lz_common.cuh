@@ -51,9 +51,10 @@ void lz_set_error(const char *fmt, ...);
 struct lz_comm;   // lz_multi.cu
 
 struct lz_matrix;
+struct LzVecRun;
 #define LZ_ATTR_CAP 64
 struct LzKnobs {
-    int spmv_hint, spmm_hint, spmm_run, no_split, cgs_shape_order, cgs_upd_mult, cgs_one_cta, no_cgs_fuse, cgs_no_slices;
+    int spmv_hint, spmm_hint /* -1 auto; bits: 1 matrix streams evict-first, 2 W stores evict-first, 4 Q0 evict-first, 8 X gathers evict-last */, spmm_run, no_split, cgs_shape_order, cgs_upd_mult, cgs_one_cta, no_cgs_fuse, cgs_no_slices;
     int comm_mode;          // LZ_COMM: 0 auto (peer memory when IPC works, else NCCL), 1 NCCL only, 2 peer required
     int no_overlap;         // LZ_NO_OVERLAP: halo exchange on the compute stream, one SpMV launch
     int no_fold;            // LZ_NO_FOLD: keep pass B + separate alpha in the full-reorth vector path
@@ -83,6 +84,7 @@ struct lz_ctx {
     int64_t basis_ts, basis_cs, basis_rows;   // element (i,k) at basis[(i>>5)*ts + k*cs + (i&31)]
     int basis_cols;
     lz_comm *comm;
+    LzVecRun *vrun;         // state of the current single-vector run (lz_vector_lanczos_begin / _advance / checkpoints)
     int last_coupling_slot; // index into `scalars` of beta_m left by the last driver run (lz_last_coupling)
     // optional per-kernel-class timing (bench.py's roofline leg): CUDA events on ctx->stream
     int prof_on;
@@ -109,6 +111,25 @@ struct lz_ctx {
 };
 
 int lz_func_smem_optin(lz_ctx *ctx, const void *func, int bytes, bool carveout_max = false);
+
+// ---- persistent state of a single-vector run (lz_vector.cu): begin once, advance in pieces, checkpoint, restart
+struct LzCgs {
+    double *V; int64_t ts, cs; double *cpart; double *c; unsigned grid;      // basis element (i,k): V[(i>>5)*ts + k*cs + (i&31)]
+};
+struct LzVecRun {
+    const lz_matrix *A;
+    int64_t n, hlo, hhi, n_below, lc, stride;
+    int m;                       // capacity: steps / basis columns this run was set up for
+    int reorth;
+    bool sharded, fold, overlap;
+    double *u_prev, *u_cur, *w;  // rotating work vectors (unnormalised q_{j-1}, q_j, scratch)
+    LzCgs g;
+    double *alpha, *beta, *invb; // device scalar series in the context's bank: alpha[m], beta[m+1], invb[m+1]
+    double *q;                   // optional receiver-row series (device, m)
+    double *om[3];               // selective reorthogonalisation: omega rows (old, current, new)
+    int j;                       // next step
+    int first_next;              // the next step has no q_{j-1} term (start of a run / first step after a thick restart)
+};
 
 #define LZ_PROF_CAP 32768
 // kernel classes for the profiler
@@ -140,6 +161,12 @@ struct LzPeerDesc {
     int *err;                                             // set to 1 when a wait gave up (peer lost): results are garbage, no hang
 };
 #define LZ_PEER_SPIN_LIMIT (1u << 27)
+
+// single-vector run in pieces (lz_vector.cu), used by the checkpoint / thick-restart code in lz_eigs.cu
+int lz_vec_setup(lz_ctx *ctx, const lz_matrix *A, int m, int64_t lc, int reorth, double *q);
+int lz_vec_start(lz_ctx *ctx, const double *b);
+int lz_vec_steps(lz_ctx *ctx, int j_end);
+int lz_vec_report(lz_ctx *ctx, double *alpha_host, double *beta_host, int *steps_done);
 
 int lz_ctx_workspace(lz_ctx *ctx, size_t bytes, void **out);   // grow-only scratch
 int lz_ctx_basis(lz_ctx *ctx, int64_t rows, int cols, double **out);            // vector path: row-tiled slab
@@ -191,6 +218,8 @@ struct lz_matrix {
     const double *ell_data;  // ELL4 row-interleaved
     const uint32_t *ell_idx;
     int owns;                // arrays owned by the library (freed on destroy)
+    int owns_csr;            // ELL4 operators: the CSR shadow (rowptr/colidx/vals + schedules) built for the block path
+    int64_t csr_nnz;         // entries of the CSR arrays (== nnz for CSR operators; true non-zeros of an ELL4 shadow)
     int n_chunks;
     int32_t *chunk_row;      // n_chunks + 1
     int32_t *chunk_ptr;      // rowptr[chunk_row[c]], n_chunks + 1

@@ -77,13 +77,15 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
     A->n_virtual = nv;
     LZ_CUDA(cudaMalloc(&A->vrowptr, sizeof(int32_t) * ((size_t)nv + 8)));
     LZ_CUDA(cudaMalloc(&A->ybar, sizeof(double) * ((size_t)nv + 8)));
-    k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->nnz, A->rowptr, A->vstart, A->vrowptr);
+    k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->csr_nnz, A->rowptr, A->vstart, A->vrowptr);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
 
 static int build_schedule(lz_ctx *ctx, lz_matrix *A)
 {
+    if (A->format == LZ_FMT_CSR) A->csr_nnz = A->nnz;
+    const int64_t nnz = A->csr_nnz;
     A->tile = LZ_SPMV_TILE;
     A->cap = 1024;                       // shared-memory slots per ring stage of the fine-schedule kernel
     int *d_max = ctx->flags + 8;
@@ -95,22 +97,22 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     if (A->max_row_nnz > A->cap - A->tile && !ctx->knobs.no_split) LZ_TRY(build_split(ctx, A));   // a long row would push chunks off the streaming path
     const int32_t *rp = A->vrowptr ? A->vrowptr : A->rowptr;
     const int64_t rows = A->vrowptr ? A->n_virtual : A->n_rows;
-    int64_t nch = (A->nnz + A->tile - 1) / A->tile;
+    int64_t nch = (nnz + A->tile - 1) / A->tile;
     if (nch < 1) nch = 1;
     LZ_CHECK(nch * 2 <= LZ_PARTIALS_CAP, LZ_ERR_UNSUPPORTED, "matrix too large for the reduction scratch (%lld chunks)", (long long)nch);
     A->n_chunks = (int)nch;
     LZ_CUDA(cudaMalloc(&A->chunk_row, sizeof(int32_t) * (nch + 1)));
     LZ_CUDA(cudaMalloc(&A->chunk_ptr, sizeof(int32_t) * (nch + 1)));
     A->tma_ok = ((uintptr_t)A->vals % 16 == 0) && ((uintptr_t)A->colidx % 16 == 0);
-    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, A->nnz, rp, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
+    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
     // the SpMM kernel amortises its per-chunk cost over wider rows: its own, coarser schedule
-    int64_t mch = (A->nnz + LZ_SPMM_TILE - 1) / LZ_SPMM_TILE;
+    int64_t mch = (nnz + LZ_SPMM_TILE - 1) / LZ_SPMM_TILE;
     if (mch < 1) mch = 1;
     A->mm_n_chunks = (int)mch;
     LZ_CUDA(cudaMalloc(&A->mm_chunk_row, sizeof(int32_t) * (mch + 1)));
     LZ_CUDA(cudaMalloc(&A->mm_chunk_ptr, sizeof(int32_t) * (mch + 1)));
-    k_chunk_rows<<<(unsigned)((mch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, A->nnz, rp, (int)mch, LZ_SPMM_TILE, A->mm_chunk_row, A->mm_chunk_ptr);
+    k_chunk_rows<<<(unsigned)((mch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)mch, LZ_SPMM_TILE, A->mm_chunk_row, A->mm_chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     return LZ_OK;
@@ -401,6 +403,36 @@ int lz_ell_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int width, int la
             }
         }
         A->max_row_nnz = 4;
+        // CSR shadow (explicit zeros dropped, ELL column order kept) with the chunk schedules: the block path
+        // runs the staged SpMM on it instead of a width-4 ELL kernel; the vector path keeps k_ell4_spmv
+        {
+            int32_t *cnt, *rp;
+            LZ_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * (n_rows + 1)));
+            LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n_rows + 1)));
+            LZ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (n_rows + 1), ctx->stream));
+            k_ell_count<<<grid, 256, 0, ctx->stream>>>(n_rows, 4, 1, A->ell_data, cnt);
+            LZ_LAUNCH_CHECK(ctx);
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
+            void *tmp;
+            LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
+            cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
+            ctx->launches++;
+            int32_t nnz32 = 0;
+            LZ_CUDA(cudaMemcpyAsync(&nnz32, rp + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+            LZ_CUDA(cudaFree(tmp));
+            LZ_CUDA(cudaFree(cnt));
+            int32_t *ci; double *va;
+            LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * ((size_t)nnz32 + 8)));
+            LZ_CUDA(cudaMalloc(&va, sizeof(double) * ((size_t)nnz32 + 8)));
+            A->rowptr = rp; A->colidx = ci; A->vals = va;
+            A->owns_csr = 1; A->csr_nnz = nnz32;
+            k_ell_fill<<<grid, 256, 0, ctx->stream>>>(n_rows, 4, 1, A->ell_data, A->ell_idx, rp, ci, va);
+            LZ_LAUNCH_CHECK(ctx);
+            int st = build_schedule(ctx, A);
+            if (st != LZ_OK) { lz_matrix_destroy(A); return st; }
+        }
         *out = A;
         return LZ_OK;
     }
@@ -444,10 +476,12 @@ int lz_matrix_destroy(lz_matrix *A)
         if (A->prev) A->prev->next = A->next; else A->ctx->matrices = A->next;
         if (A->next) A->next->prev = A->prev;
     }                                        // orphaned (context destroyed first): cudaFree synchronises by itself
-    if (A->owns) {
+    if (A->owns || A->owns_csr) {
         cudaFree((void *)A->rowptr);
         cudaFree((void *)A->colidx);
         cudaFree((void *)A->vals);
+    }
+    if (A->owns) {
         cudaFree((void *)A->ell_data);
         cudaFree((void *)A->ell_idx);
     }
@@ -474,9 +508,10 @@ int lz_matrix_info(const lz_matrix *A, int64_t *n_rows, int64_t *n_cols, int64_t
 int lz_matrix_csr_view(const lz_matrix *A, const int32_t **rowptr, const int32_t **colidx, const double **vals)
 {
     LZ_CHECK(A, LZ_ERR_INVALID, "lz_matrix_csr_view: A is NULL");
-    if (rowptr) *rowptr = A->rowptr;
-    if (colidx) *colidx = A->colidx;
-    if (vals) *vals = A->vals;
+    const bool csr = A->format == LZ_FMT_CSR;       // (an ELL4 operator's internal CSR shadow is not part of the interface)
+    if (rowptr) *rowptr = csr ? A->rowptr : nullptr;
+    if (colidx) *colidx = csr ? A->colidx : nullptr;
+    if (vals) *vals = csr ? A->vals : nullptr;
     return LZ_OK;
 }
 

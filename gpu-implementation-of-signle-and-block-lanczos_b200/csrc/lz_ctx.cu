@@ -56,7 +56,7 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     auto env_set = [](const char *name) { return getenv(name) ? 1 : 0; };
     LzKnobs &k = c->knobs;
     k.spmv_hint = env_set("LZ_SPMV_HINT");
-    k.spmm_hint = env_set("LZ_SPMM_HINT");
+    k.spmm_hint = env_int("LZ_SPMM_HINT", -1);
     k.spmm_run = env_int("LZ_SPMM_RUN", 1);
     k.no_split = env_set("LZ_NO_SPLIT");
     k.cgs_shape_order = env_int("LZ_CGS_SHAPE_ORDER", 1);
@@ -97,6 +97,8 @@ int lz_ctx_destroy(lz_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm) lz_comm_destroy(ctx);
+    delete ctx->vrun;
+    ctx->vrun = nullptr;
     // orphan the operators still alive: they keep their device arrays and can be destroyed later
     for (lz_matrix *A = ctx->matrices; A;) {
         lz_matrix *nx = A->next;

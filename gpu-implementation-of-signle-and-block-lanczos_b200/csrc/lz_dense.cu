@@ -116,9 +116,9 @@ int lz_gram2(lz_ctx *ctx, int64_t n, int bw, const double *X, const double *Y1, 
     void *w;
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * 2 * bw * bw, &w));
     lz_prof_begin(ctx, LZ_K_GRAM, 8.0 * (double)n * bw * 3.0);
-    if (bw == 8) k_gram2_dmma<8><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
-    else if (bw == 16) k_gram2_dmma<16><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
-    else k_gram2_dmma<32><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
+    if (bw == 8) k_gram2_dmma<8, false><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
+    else if (bw == 16) k_gram2_dmma<16, false><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
+    else k_gram2_dmma<32, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, X, Y1, Y2, (double *)w);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     k_gram_reduce<<<(bw * bw + 7) / 8, 256, 0, ctx->stream>>>(bw, grid, (const double *)w, 2 * bw * bw, G1, 0);

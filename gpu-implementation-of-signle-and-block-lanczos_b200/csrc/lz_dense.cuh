@@ -164,56 +164,62 @@ k_gram_reduce(int bw, int n_parts, const double *__restrict__ gpart, int gstride
 // two Gram matrices from one read of X:  G1_partial = X^T Y1,  G2_partial = X^T Y2   (row-major panels).
 // Used for the reference order of the block recurrence when the SpMM cannot subtract Q_{j-1} beta_j itself:
 // alpha_j = sym(Q_j^T (A Q_j - Q_{j-1} beta_j)) = sym(G1 - G2 beta_j) with G1 = Q_j^T (A Q_j), G2 = Q_j^T Q_{j-1}.
-template <int BW>
+template <int BW, bool SPLIT>
 __global__ void __launch_bounds__(LZ_DENSE_THREADS)
 k_gram2_dmma(int64_t n, const double *__restrict__ X, const double *__restrict__ Y1, const double *__restrict__ Y2,
              double *__restrict__ gpart /* [cta][2][BW*BW] */)
 {
-    constexpr int T = BW / 8;
+    // SPLIT (BW = 32, 32 accumulator doubles per product): warps 0-3 form X^T Y1 and warps 4-7 X^T Y2 over the SAME
+    // slabs (X is fetched by both halves, the second time from L1); otherwise every warp forms both products.
+    constexpr int T = BW / 8, NP = SPLIT ? 1 : 2, WPP = SPLIT ? LZ_DENSE_WARPS / 2 : LZ_DENSE_WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kk = lane & 3, mm = lane >> 2;
-    double acc[2][T][T][2];
+    const int half = SPLIT ? warp / WPP : 0, wsub = SPLIT ? warp % WPP : warp;
+    double acc[NP][T][T][2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < NP; ++h)
 #pragma unroll
         for (int a = 0; a < T; ++a)
 #pragma unroll
             for (int b = 0; b < T; ++b) acc[h][a][b][0] = acc[h][a][b][1] = 0.0;
+    const double *Ya = SPLIT ? (half ? Y2 : Y1) : Y1;
     const int64_t n_slabs = (n + 31) / 32;
-    const int64_t wglobal = (int64_t)blockIdx.x * LZ_DENSE_WARPS + warp, wtotal = (int64_t)gridDim.x * LZ_DENSE_WARPS;
+    const int64_t wglobal = (int64_t)blockIdx.x * WPP + wsub, wtotal = (int64_t)gridDim.x * WPP;
     for (int64_t slab = wglobal; slab < n_slabs; slab += wtotal) {
 #pragma unroll 2
         for (int g = 0; g < 8; ++g) {
             const int64_t i = slab * 32 + g * 4 + kk;
             const bool ok = i < n;
-            double xa[T], y1[T], y2[T];
+            double xa[T], y1[T], y2[SPLIT ? 1 : T];
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 xa[t] = ok ? __ldg(X + i * BW + t * 8 + mm) : 0.0;
-                y1[t] = ok ? __ldg(Y1 + i * BW + t * 8 + mm) : 0.0;
-                y2[t] = ok ? __ldg(Y2 + i * BW + t * 8 + mm) : 0.0;
+                y1[t] = ok ? __ldg(Ya + i * BW + t * 8 + mm) : 0.0;
+                if (!SPLIT) y2[t] = ok ? __ldg(Y2 + i * BW + t * 8 + mm) : 0.0;
             }
 #pragma unroll
             for (int a = 0; a < T; ++a)
 #pragma unroll
                 for (int b = 0; b < T; ++b) {
                     lz_dmma(acc[0][a][b][0], acc[0][a][b][1], xa[a], y1[b]);
-                    lz_dmma(acc[1][a][b][0], acc[1][a][b][1], xa[a], y2[b]);
+                    if (!SPLIT) lz_dmma(acc[NP - 1][a][b][0], acc[NP - 1][a][b][1], xa[a], y2[b]);
                 }
         }
     }
     __shared__ double sm[BW * BW];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        for (int w = 0; w < LZ_DENSE_WARPS; ++w) {
-            if (warp == w) {
+        for (int w = 0; w < WPP; ++w) {
+            const int wv = SPLIT ? h * WPP + w : w;        // the warp whose accumulators are added in this turn
+            if (warp == wv) {
 #pragma unroll
                 for (int a = 0; a < T; ++a)
 #pragma unroll
                     for (int b = 0; b < T; ++b) {
                         const int p = a * 8 + mm, q = b * 8 + 2 * kk;
-                        if (w == 0) { sm[p + q * BW] = acc[h][a][b][0]; sm[p + (q + 1) * BW] = acc[h][a][b][1]; }
-                        else { sm[p + q * BW] += acc[h][a][b][0]; sm[p + (q + 1) * BW] += acc[h][a][b][1]; }
+                        const double v0 = acc[SPLIT ? 0 : h][a][b][0], v1 = acc[SPLIT ? 0 : h][a][b][1];
+                        if (w == 0) { sm[p + q * BW] = v0; sm[p + (q + 1) * BW] = v1; }
+                        else { sm[p + q * BW] += v0; sm[p + (q + 1) * BW] += v1; }
                     }
             }
             __syncthreads();

@@ -185,7 +185,7 @@ extern "C" int lz_ritz(int m, int bw, const double *alpha, const double *beta, c
 // Same construction here, on the host: Householder tridiagonalisation, implicit QL with the full
 // eigenvector matrix, then the triple product.  Only the lower triangle of T is read (uplo = LOWER).
 // ---------------------------------------------------------------------------------------------
-static int sym_eig_full(int N, std::vector<double> &A /* col-major, destroyed */, std::vector<double> &d, std::vector<double> &Zt)
+int lz_sym_eig_full(int N, std::vector<double> &A /* col-major, destroyed */, std::vector<double> &d, std::vector<double> &Zt)
 {
     for (int j = 0; j < N; ++j)
         for (int i = j + 1; i < N; ++i) A[j + (size_t)i * N] = A[i + (size_t)j * N];
@@ -209,7 +209,7 @@ extern "C" int lz_expm_sym(int n, double *T_host)
     LZ_CHECK(n >= 1 && T_host, LZ_ERR_INVALID, "lz_expm_sym: bad arguments");
     LZ_CHECK(n <= 2048, LZ_ERR_UNSUPPORTED, "lz_expm_sym: dimension %d is too large for the host eigensolver", n);
     std::vector<double> A(T_host, T_host + (size_t)n * n), d, Zt;
-    LZ_TRY(sym_eig_full(n, A, d, Zt));
+    LZ_TRY(lz_sym_eig_full(n, A, d, Zt));
     std::vector<double> ex(n);
     for (int i = 0; i < n; ++i) ex[i] = exp(d[i]);
     for (int c = 0; c < n; ++c)

@@ -16,7 +16,8 @@
 // indices into ctx->scalars used by the drivers
 enum { S_NRM2 = 0, S_NRM2_BEFORE = 1, S_ALPHA_LOCAL = 2, S_TMP = 3, S_BETA_LAST = 4 };
 // indices into ctx->flags
-enum { F_BREAKDOWN = 0, F_SECOND_SWEEP = 1 };
+enum { F_BREAKDOWN = 0, F_SECOND_SWEEP = 1, F_FORCE = 4, F_REORTH_COUNT = 5 };
+#define SB_VECTOR_LIMIT 4096   // the vector drivers' share of the context's scalar bank (the block driver owns the rest)
 // tickets
 enum { T_SPMV = 0, T_DOT = 1, T_UPD = 2, T_PROJ = 3 };
 
@@ -365,11 +366,20 @@ k_cgs_reduce(int K, int n_parts, const double *__restrict__ cpart, double *__res
 __global__ void __launch_bounds__(VT)
 k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t cs, double *__restrict__ w,
              const double *__restrict__ c, double *partials, unsigned int *ticket, const LzFinal fin,
-             int *flags, int need_flag, int dgks_test, const double *nrm2_before)
+             int *flags, int need_flag, int dgks_test, const double *nrm2_before, int skip_share)
 {
     extern __shared__ double csm[];           // c[K]
     __shared__ double red[32];
-    if (need_flag && flags[F_SECOND_SWEEP] == 0) return;
+    if (need_flag && flags[F_SECOND_SWEEP] == 0) {
+        // skipped sweep (selective reorthogonalisation).  Sharded runs issue their collectives unconditionally, so
+        // the skipping kernel still takes part: peer mode adds a zero, NCCL mode re-publishes the norm pass B left
+        // (rank 0 contributes it, the others zero) so that the all-reduce + finalisation that follows changes nothing
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (fin.pd) { double z = 0.0; lz_peer_sum_thread<1>(fin.pd, fin.seq, &z); }
+            else if (skip_share >= 0) *fin.nrm2_out = skip_share ? *nrm2_before : 0.0;
+        }
+        return;
+    }
     for (int k = threadIdx.x; k < K; k += VT) csm[k] = c[k];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -443,10 +453,6 @@ __global__ void k_finalize_first(const double *nrm2, double *beta, double *invb,
 // ---------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-struct LzCgs {
-    double *V; int64_t ts, cs; double *cpart; double *c; unsigned grid;      // basis element (i,k): V[(i>>5)*ts + k*cs + (i&31)]
-};
-
 // Sharded runs: a kernel whose last CTA finalises a norm either all-reduces it in place over peer memory (the
 // sequence number is drawn HERE, immediately before the launch, so every rank issues its collectives in the same
 // order) or -- NCCL mode -- only publishes the local total, and finish_norm() adds the all-reduce + finalisation.
@@ -481,7 +487,8 @@ static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, doub
     const LzFinal f = arm_final(ctx, fin, sharded, want_norm);
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
     k_cgs_update<<<want < cap ? want : cap, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
-        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, f, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE);
+        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, f, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE,
+        (sharded && want_norm && !f.pd) ? (lz_comm_rank(ctx) == 0 ? 1 : 0) : -1);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     return finish_norm(ctx, f, sharded, want_norm);
@@ -547,6 +554,81 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
 
 __global__ void k_copy_scalar(const double *src, double *dst) { *dst = *src; }
 
+// ---------------------------------------------------------------------------------------------
+// Selective (partial) reorthogonalisation: Simon's omega recurrence estimates  omega_{j+1,k} ~ q_{j+1} . q_k  from the
+// scalars alone; w is reorthogonalised against the stored basis only when an estimate passes sqrt(eps), and once more
+// on the following step.  The recurrence runs in one CTA on the device and leaves its decision in a flag the (then
+// conditional) CGS kernels read, so the iteration still never synchronises with the host.
+//   beta_{j+1} omega_{j+1,k} = beta_{k+1} omega_{j,k+1} + (alpha_k - alpha_j) omega_{j,k} + beta_k omega_{j,k-1}
+//                              - beta_j omega_{j-1,k} + theta,   |theta| = eps (beta_{k+1} + beta_{j+1})
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_omega_step(int j, double psi, const double *__restrict__ alpha, const double *__restrict__ beta,
+             const double *__restrict__ om_old, const double *__restrict__ om_cur, double *__restrict__ om_new, int *flags)
+{
+    __shared__ double red[32];
+    __shared__ int need_s;
+    const double eps = 2.220446049250313e-16;
+    const double bj1 = beta[j + 1], aj = alpha[j], bj = beta[j];
+    double mx = 0.0;
+    for (int k = threadIdx.x; k < j; k += 256) {
+        // om_cur[k] = omega_{j,k} (om_cur[j] = 1), om_old[k] = omega_{j-1,k} (om_old[j-1] = 1)
+        double t = beta[k + 1] * om_cur[k + 1] + (alpha[k] - aj) * om_cur[k] - bj * om_old[k];
+        if (k > 0) t += beta[k] * om_cur[k - 1];
+        const double th = eps * (beta[k + 1] + bj1);
+        t = (t + (t >= 0.0 ? th : -th)) / bj1;
+        om_new[k] = t;
+        mx = fmax(mx, fabs(t));
+    }
+    // block max through the sum helper's shared array
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m2 = 0.0;
+        for (int wv = 0; wv < 8; ++wv) m2 = fmax(m2, red[wv]);
+        const int forced = flags[F_FORCE];
+        const int need = (m2 > 1.4901161193847656e-08 /* sqrt(eps) */ || forced || !isfinite(m2)) ? 1 : 0;
+        flags[F_SECOND_SWEEP] = need;
+        flags[F_FORCE] = (need && !forced) ? 1 : 0;          // a triggered step is followed by exactly one forced step
+        if (need) flags[F_REORTH_COUNT] += 1;
+        need_s = need;
+        om_new[j] = psi;
+        om_new[j + 1] = 1.0;
+    }
+    __syncthreads();
+    if (need_s)
+        for (int k = threadIdx.x; k <= j; k += 256) om_new[k] = eps;     // q_{j+1} is about to be made orthogonal to working precision
+}
+
+__global__ void k_omega_init(int len, double *om_old, double *om_cur, double *om_new, int *flags)
+{
+    for (int k = threadIdx.x; k < len; k += blockDim.x) { om_old[k] = 0.0; om_cur[k] = 0.0; om_new[k] = 0.0; }
+    __syncthreads();
+    if (threadIdx.x == 0) { om_cur[0] = 1.0; flags[F_FORCE] = 0; flags[F_REORTH_COUNT] = 0; flags[F_SECOND_SWEEP] = 0; }
+}
+
+// omega rows live behind alpha in the scalar bank: three arrays of m + 2
+static inline double *omega_row(const LzVecRun &R, int which) { return R.alpha + R.m + (size_t)which * (R.m + 2); }
+
+static int omega_init(lz_ctx *ctx, LzVecRun &R)
+{
+    R.om[0] = omega_row(R, 0); R.om[1] = omega_row(R, 1); R.om[2] = omega_row(R, 2);
+    k_omega_init<<<1, 256, 0, ctx->stream>>>(R.m + 2, R.om[0], R.om[1], R.om[2], ctx->flags);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+static int omega_step(lz_ctx *ctx, LzVecRun &R, int j)
+{
+    const double n_glob = (double)(R.A->global_rows > 0 ? R.A->global_rows : R.n);
+    const double psi = 2.220446049250313e-16 * sqrt(n_glob);       // q_{j+1} . q_j right after the three-term step
+    k_omega_step<<<1, 256, 0, ctx->stream>>>(j, psi, R.alpha, R.beta, R.om[0], R.om[1], R.om[2], ctx->flags);
+    LZ_LAUNCH_CHECK(ctx);
+    double *t = R.om[0]; R.om[0] = R.om[1]; R.om[1] = R.om[2]; R.om[2] = t;      // (old, cur, new) <- (cur, new, old)
+    return LZ_OK;
+}
+
 // The single-vector driver.  Device arrays: alpha[m], beta[m+1], invb[m+1].
 // With a communicator attached to the context (lz_comm_init) the operator is this rank's row slab,
 // b holds the local rows, every gather source carries [lower halo | local | upper halo] and every
@@ -560,8 +642,10 @@ __global__ void k_copy_scalar(const double *src, double *dst) { *dst = *src; }
 // Sharded, overlapped: the boundary planes of q_{j+1} leave for the neighbours on a side stream as soon as the last
 // update of step j retires, the interior chunks of the next pass A (no halo column) run meanwhile, the two
 // boundary chunk ranges follow once the halo has landed.
-static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
-                               double *alpha, double *beta, double *invb, double *q)
+//
+// The run is a persistent object of the context (LzVecRun): vec_begin sets it up, vec_steps advances it, so a solve
+// can be continued, checkpointed (lz_vector_checkpoint_*) and thick-restarted (lz_eigs_thick_restart).
+int lz_vec_setup(lz_ctx *ctx, const lz_matrix *A, int m, int64_t lc, int reorth, double *q)
 {
     const int64_t n = A->n_rows;
     const bool sharded = ctx->comm != nullptr && lz_comm_world(ctx) > 1;
@@ -570,8 +654,10 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
     LZ_CHECK(A->n_cols == n + hlo + hhi, LZ_ERR_INVALID, "lz_vector_lanczos: operator must be square (%lld x %lld)", (long long)n, (long long)A->n_cols);
     LZ_CHECK(sharded || (hlo == 0 && hhi == 0), LZ_ERR_INVALID, "lz_vector_lanczos: a sharded operator needs lz_comm_init");
     LZ_CHECK(lc >= -1 && lc < n, LZ_ERR_INVALID, "lz_vector_lanczos: lc %lld out of range", (long long)lc);
-    LZ_CHECK(reorth >= LZ_REORTH_NONE && reorth <= LZ_REORTH_FULL_DGKS, LZ_ERR_INVALID, "lz_vector_lanczos: reorth mode %d", reorth);
+    LZ_CHECK(reorth >= LZ_REORTH_NONE && reorth <= LZ_REORTH_SELECTIVE, LZ_ERR_INVALID, "lz_vector_lanczos: reorth mode %d", reorth);
     LZ_CHECK(!(sharded && reorth == LZ_REORTH_FULL_DGKS), LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: DGKS reorthogonalisation is single-GPU only");
+    LZ_CHECK(3 * m + 3 + 16 + (reorth == LZ_REORTH_SELECTIVE ? 3 * (m + 2) : 0) <= SB_VECTOR_LIMIT, LZ_ERR_UNSUPPORTED,
+             "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
     // three rotating work vectors (the reference's q0, q1, w: test_lanczos.cu:57-59), each laid out
     // [pad | lower halo | local rows | upper halo] with the local part 32-byte aligned.  Sharded: the layout is
     // made IDENTICAL on every rank (largest halo / span), so a neighbour's halo region is found by offset.
@@ -599,7 +685,6 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
     void *work;
     if (sharded) LZ_TRY(lz_comm_arena(ctx, work_bytes, (size_t)m + 8, &work));
     else LZ_TRY(lz_ctx_workspace(ctx, work_bytes, &work));
-    double *u_prev = (double *)work + off, *u_cur = u_prev + stride, *w = u_cur + stride;
     if (reorth) {
         LZ_CHECK(sizeof(double) * (VT / 32) * (size_t)m <= 200 * 1024, LZ_ERR_UNSUPPORTED,
                  "lz_vector_lanczos: m = %d too large for the projection kernel's shared memory", m);
@@ -610,29 +695,61 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
         g.ts = ctx->basis_ts; g.cs = ctx->basis_cs;
         LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_cgs_project, 200 * 1024));
     }
-    double *sc = ctx->scalars;
-    const bool peer = sharded && lz_comm_peer(ctx);
-    const bool fold = reorth == LZ_REORTH_FULL && !ctx->knobs.no_fold;
+    if (!ctx->vrun) ctx->vrun = new LzVecRun();
+    LzVecRun &R = *ctx->vrun;
+    memset(&R, 0, sizeof(R));
+    R.A = A; R.n = n; R.hlo = hlo; R.hhi = hhi; R.n_below = n_below; R.lc = lc; R.stride = stride;
+    R.m = m; R.reorth = reorth; R.sharded = sharded;
+    R.fold = reorth == LZ_REORTH_FULL && !ctx->knobs.no_fold;
     // interior chunks exist and the operator knows them: overlap the halo exchange with them
-    const bool overlap = sharded && !ctx->knobs.no_overlap && A->has_split && A->bnd_hi > A->bnd_lo && A->format == LZ_FMT_CSR && A->tma_ok && !A->vrowptr;
-    LZ_CUDA(cudaMemcpyAsync(u_cur, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-    // beta[0] = ||b||  (vector_lanczos.hpp:21)
-    LZ_TRY(dot_async(ctx, n, b, b, sc + S_NRM2));
-    if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_NRM2, 1));
-    k_finalize_first<<<1, 1, 0, ctx->stream>>>(sc + S_NRM2, beta, invb, ctx->flags);
-    LZ_LAUNCH_CHECK(ctx);
+    R.overlap = sharded && !ctx->knobs.no_overlap && A->has_split && A->bnd_hi > A->bnd_lo && A->format == LZ_FMT_CSR && A->tma_ok && !A->vrowptr;
+    R.u_prev = (double *)work + off; R.u_cur = R.u_prev + stride; R.w = R.u_cur + stride;
+    R.g = g;
+    R.beta = ctx->scalars + 16; R.invb = R.beta + (m + 1); R.alpha = R.invb + (m + 1);
+    R.q = q;
+    R.j = 0; R.first_next = 1;
+    return LZ_OK;
+}
 
-    for (int j = 0; j < m; ++j) {
+// u_cur <- b ; beta[0] = ||b||  (vector_lanczos.hpp:21)
+int lz_vec_start(lz_ctx *ctx, const double *b)
+{
+    LzVecRun &R = *ctx->vrun;
+    double *sc = ctx->scalars;
+    LZ_CUDA(cudaMemcpyAsync(R.u_cur, b, sizeof(double) * R.n, cudaMemcpyDeviceToDevice, ctx->stream));
+    LZ_TRY(dot_async(ctx, R.n, b, b, sc + S_NRM2));
+    if (R.sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, sc + S_NRM2, 1));
+    k_finalize_first<<<1, 1, 0, ctx->stream>>>(sc + S_NRM2, R.beta, R.invb, ctx->flags);
+    LZ_LAUNCH_CHECK(ctx);
+    if (R.reorth == LZ_REORTH_SELECTIVE) LZ_TRY(omega_init(ctx, R));
+    R.j = 0; R.first_next = 1;
+    return LZ_OK;
+}
+
+// steps [R.j, j_end)
+int lz_vec_steps(lz_ctx *ctx, int j_end)
+{
+    LzVecRun &R = *ctx->vrun;
+    LZ_CHECK(j_end <= R.m, LZ_ERR_INVALID, "lz_vector_lanczos: step %d beyond the capacity %d of this run", j_end, R.m);
+    const lz_matrix *A = R.A;
+    const int64_t n = R.n, hlo = R.hlo, hhi = R.hhi;
+    const bool sharded = R.sharded, fold = R.fold, overlap = R.overlap;
+    const bool peer = sharded && lz_comm_peer(ctx);
+    const int reorth = R.reorth;
+    const LzCgs &g = R.g;
+    double *alpha = R.alpha, *beta = R.beta, *invb = R.invb, *sc = ctx->scalars;
+    for (int j = R.j; j < j_end; ++j) {
+        double *u_prev = R.u_prev, *u_cur = R.u_cur, *w = R.w;
         // neighbours' boundary planes of q_j (unnormalised, like everything in the rotating buffers)
-        if (sharded) LZ_TRY(lz_comm_halo_exchange(ctx, u_cur, n, hlo, hhi, n_below, overlap));
+        if (sharded) LZ_TRY(lz_comm_halo_exchange(ctx, u_cur, n, hlo, hhi, R.n_below, overlap));
         LzPassA pa;
         memset(&pa, 0, sizeof(pa));
         pa.x_own = u_cur; pa.u_prev = u_prev; pa.invb = invb; pa.beta = beta;
         pa.alpha_out = (sharded || fold) ? nullptr : alpha + j; pa.alpha_partial = sc + S_ALPHA_LOCAL;
         pa.vcol = reorth ? g.V + (size_t)j * g.cs : nullptr;
         pa.vts = g.ts;
-        pa.qout = (q && lc >= 0) ? q + j : nullptr;
-        pa.lc = lc; pa.j = j; pa.first = (j == 0);
+        pa.qout = (R.q && R.lc >= 0) ? R.q + j : nullptr;
+        pa.lc = R.lc; pa.j = j; pa.first = R.first_next;
         pa.partials = ctx->partials; pa.ticket = ctx->tickets + T_SPMV;
         lz_prof_begin(ctx, LZ_K_SPMV, 12.0 * (double)A->nnz + 28.0 * (double)n + (reorth ? 8.0 * (double)n : 0.0));
         if (overlap) {
@@ -665,17 +782,31 @@ static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b,
             const LzFinal f2 = {beta, invb, sc + S_NRM2, ctx->flags, j + 1, 1, nullptr, 0};
             if (reorth == LZ_REORTH_FULL) {
                 LZ_TRY(cgs2_fused(ctx, g, n, j + 1, w, f2, sharded, fold ? alpha + j : nullptr));
-            } else {
+            } else if (reorth == LZ_REORTH_FULL_DGKS) {
                 LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 0, 1, sharded, true, nullptr));
+                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 1, 0, sharded, true, nullptr));
+            } else {
+                // selective: the omega recurrence decides on the device whether this step reorthogonalises; both
+                // sweeps are then conditional on the flag it leaves (sharded runs keep their collectives unconditional)
+                LZ_TRY(omega_step(ctx, R, j));
+                LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 1, 0, sharded, false, nullptr));
                 LZ_TRY(cgs_sweep(ctx, g, n, j + 1, w, f2, 1, 0, sharded, true, nullptr));
             }
         }
-        double *t = u_prev; u_prev = u_cur; u_cur = w; w = t;                  // :62 (pointer rotation, no copy)
+        R.u_prev = u_cur; R.u_cur = w; R.w = u_prev;                                  // :62 (pointer rotation, no copy)
+        R.j = j + 1; R.first_next = 0;
     }
-    k_copy_scalar<<<1, 1, 0, ctx->stream>>>(beta + m, sc + S_BETA_LAST);
+    k_copy_scalar<<<1, 1, 0, ctx->stream>>>(beta + R.j, sc + S_BETA_LAST);
     LZ_LAUNCH_CHECK(ctx);
     ctx->last_coupling_slot = S_BETA_LAST;
     return LZ_OK;
+}
+
+static int vector_lanczos_core(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth, double *q)
+{
+    LZ_TRY(lz_vec_setup(ctx, A, m, lc, reorth, q));
+    LZ_TRY(lz_vec_start(ctx, b));
+    return lz_vec_steps(ctx, m);
 }
 
 // columns j0 .. j0+ncols-1 of the stored basis -> column-major dst (leading dimension ldd)
@@ -694,6 +825,7 @@ int lz_spmv(lz_ctx *ctx, const lz_matrix *A, const double *x, double *y)
 {
     LZ_CHECK(ctx && A && x && y, LZ_ERR_INVALID, "lz_spmv: NULL argument");
     LZ_CHECK(x != y, LZ_ERR_INVALID, "lz_spmv: x and y must not alias");
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_spmv: the operator belongs to another (or a destroyed) context");
     LzPassA none;
     memset(&none, 0, sizeof(none));
     return lz_spmv_any<LZ_EPI_PLAIN>(ctx, A, x, y, none);
@@ -707,6 +839,7 @@ int lz_fdtd_vector(lz_ctx *ctx, const lz_matrix *A, const double *u0, int64_t ns
 {
     LZ_CHECK(ctx && A && u0 && nsteps >= 1, LZ_ERR_INVALID, "lz_fdtd_vector: bad arguments");
     const int64_t n = A->n_rows;
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_fdtd_vector: the operator belongs to another (or a destroyed) context");
     LZ_CHECK(A->n_cols == n && A->halo_lo == 0 && A->halo_hi == 0, LZ_ERR_INVALID, "lz_fdtd_vector: operator must be square and unsharded");
     LZ_CHECK(lc >= -1 && lc < n && (lc >= 0) == (result_host != nullptr), LZ_ERR_INVALID, "lz_fdtd_vector: lc / result mismatch");
     LZ_CUDA(cudaSetDevice(ctx->device));
@@ -762,36 +895,66 @@ int lz_vector_lanczos_async(lz_ctx *ctx, const lz_matrix *A, const double *b, in
                             double *alpha_dev, double *beta_dev, double *q)
 {
     LZ_CHECK(ctx && A && b && alpha_dev && beta_dev && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos_async: bad arguments");
-    LZ_CHECK(2 * m + 2 + 16 <= 4096, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
     LZ_CUDA(cudaSetDevice(ctx->device));
-    // beta needs m+1 slots and invb m+1 slots: keep them in the context's scalar bank
-    double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1);
-    LZ_TRY(vector_lanczos_core(ctx, A, b, m, lc, reorth, alpha_dev, beta_i, invb, q));
-    LZ_CUDA(cudaMemcpyAsync(beta_dev, beta_i, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    LZ_TRY(vector_lanczos_core(ctx, A, b, m, lc, reorth, q));
+    const LzVecRun &R = *ctx->vrun;
+    LZ_CUDA(cudaMemcpyAsync(alpha_dev, R.alpha, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(beta_dev, R.beta, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
     return LZ_OK;
 }
+
+}  // extern "C"
+
+// coefficients of the steps done so far to the host + the breakdown report (synchronises)
+int lz_vec_report(lz_ctx *ctx, double *alpha_host, double *beta_host, int *steps_done)
+{
+    const LzVecRun &R = *ctx->vrun;
+    int flag = 0;
+    if (alpha_host && R.j) LZ_CUDA(cudaMemcpyAsync(alpha_host, R.alpha, sizeof(double) * R.j, cudaMemcpyDeviceToHost, ctx->stream));
+    if (beta_host && R.j) LZ_CUDA(cudaMemcpyAsync(beta_host, R.beta, sizeof(double) * R.j, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(&flag, ctx->flags + F_BREAKDOWN, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    // flag = first j whose beta_j is zero / non-finite: coefficients alpha[0..j-1], beta[0..j-1] are valid
+    const int done = (flag < R.j) ? flag : R.j;
+    if (steps_done) *steps_done = done;
+    if (done < R.j) {
+        lz_set_error("lz_vector_lanczos: breakdown, beta[%d] is zero or not finite", done);
+        return LZ_ERR_BREAKDOWN;
+    }
+    return LZ_OK;
+}
+
+extern "C" {
 
 int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc, int reorth,
                       double *alpha_host, double *beta_host, double *q, int *steps_done)
 {
     LZ_CHECK(ctx && A && b && alpha_host && beta_host && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos: bad arguments");
-    LZ_CHECK(3 * m + 3 + 16 <= 4096, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
     LZ_CUDA(cudaSetDevice(ctx->device));
-    double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1), *alpha_i = invb + (m + 1);
-    LZ_TRY(vector_lanczos_core(ctx, A, b, m, lc, reorth, alpha_i, beta_i, invb, q));
-    int flag = 0;
-    LZ_CUDA(cudaMemcpyAsync(alpha_host, alpha_i, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    LZ_CUDA(cudaMemcpyAsync(beta_host, beta_i, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    LZ_CUDA(cudaMemcpyAsync(&flag, ctx->flags + F_BREAKDOWN, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
-    // flag = first j whose beta_j is zero / non-finite: coefficients alpha[0..j-1], beta[0..j-1] are valid
-    int done = (flag < m) ? flag : m;
-    if (steps_done) *steps_done = done;
-    if (done < m) {
-        lz_set_error("lz_vector_lanczos: breakdown, beta[%d] is zero or not finite", done);
-        return LZ_ERR_BREAKDOWN;
-    }
-    return LZ_OK;
+    LZ_TRY(vector_lanczos_core(ctx, A, b, m, lc, reorth, q));
+    return lz_vec_report(ctx, alpha_host, beta_host, steps_done);
+}
+
+// The same run in pieces: begin sets up a run of at most m_capacity steps (basis slab, work vectors, beta_0), advance
+// performs `steps` more and reports all coefficients so far.  Between two advances the state can be saved
+// (lz_vector_checkpoint_save) and, in another process / on another context, restored (lz_vector_checkpoint_load).
+int lz_vector_lanczos_begin(lz_ctx *ctx, const lz_matrix *A, const double *b, int m_capacity, int64_t lc, int reorth, double *q)
+{
+    LZ_CHECK(ctx && A && b && m_capacity >= 1, LZ_ERR_INVALID, "lz_vector_lanczos_begin: bad arguments");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    LZ_TRY(lz_vec_setup(ctx, A, m_capacity, lc, reorth, q));
+    return lz_vec_start(ctx, b);
+}
+
+int lz_vector_lanczos_advance(lz_ctx *ctx, int steps, double *alpha_host, double *beta_host, int *steps_done)
+{
+    LZ_CHECK(ctx && ctx->vrun && ctx->vrun->A, LZ_ERR_INVALID, "lz_vector_lanczos_advance: no run has been begun on this context");
+    LZ_CHECK(steps >= 0 && ctx->vrun->j + steps <= ctx->vrun->m, LZ_ERR_INVALID, "lz_vector_lanczos_advance: %d more steps exceed the capacity %d",
+             steps, ctx->vrun->m);
+    LZ_CHECK(ctx->vrun->A->ctx == ctx, LZ_ERR_INVALID, "lz_vector_lanczos_advance: the run's operator has been orphaned");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    LZ_TRY(lz_vec_steps(ctx, ctx->vrun->j + steps));
+    return lz_vec_report(ctx, alpha_host, beta_host, steps_done);
 }
 
 int lz_vector_lanczos_sharded(lz_ctx *ctx, const lz_matrix *A_local, const double *b_local, int m, int reorth,
@@ -799,11 +962,11 @@ int lz_vector_lanczos_sharded(lz_ctx *ctx, const lz_matrix *A_local, const doubl
 {
     LZ_CHECK(ctx && A_local && b_local && alpha_dev && beta_dev && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos_sharded: bad arguments");
     LZ_CHECK(ctx->comm, LZ_ERR_COMM, "lz_vector_lanczos_sharded: call lz_comm_init first");
-    LZ_CHECK(2 * m + 2 + 16 <= 4096, LZ_ERR_UNSUPPORTED, "lz_vector_lanczos_sharded: m = %d exceeds the scalar bank", m);
     LZ_CUDA(cudaSetDevice(ctx->device));
-    double *beta_i = ctx->scalars + 16, *invb = beta_i + (m + 1);
-    LZ_TRY(vector_lanczos_core(ctx, A_local, b_local, m, -1, reorth, alpha_dev, beta_i, invb, nullptr));
-    LZ_CUDA(cudaMemcpyAsync(beta_dev, beta_i, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    LZ_TRY(vector_lanczos_core(ctx, A_local, b_local, m, -1, reorth, nullptr));
+    const LzVecRun &R = *ctx->vrun;
+    LZ_CUDA(cudaMemcpyAsync(alpha_dev, R.alpha, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(beta_dev, R.beta, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
     return LZ_OK;
 }
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "liblanczos_b200.so")
 _LIB = None
 
 LZ_OK = 0
-REORTH_NONE, REORTH_FULL, REORTH_FULL_DGKS = 0, 1, 2
+REORTH_NONE, REORTH_FULL, REORTH_FULL_DGKS, REORTH_SELECTIVE = 0, 1, 2, 3
 H2D, D2H, D2D = 1, 2, 3
 
 
@@ -73,6 +73,13 @@ def lib():
         "lz_assemble_T": (i32, [vp, i32, i32, vp, vp, vp]),
         "lz_vector_lanczos": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp, P(i32)]),
         "lz_vector_lanczos_async": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp]),
+        "lz_vector_lanczos_begin": (i32, [vp, vp, vp, i32, i64, i32, vp]),
+        "lz_vector_lanczos_advance": (i32, [vp, i32, vp, vp, P(i32)]),
+        "lz_vector_checkpoint_save": (i32, [vp, C.c_char_p]),
+        "lz_vector_checkpoint_load": (i32, [vp, vp, C.c_char_p, vp]),
+        "lz_vector_ritz_vectors": (i32, [vp, i32, vp, vp, i64]),
+        "lz_vector_reorth_count": (i32, [vp, P(i32)]),
+        "lz_eigs_thick_restart": (i32, [vp, vp, vp, i32, i32, i32, dbl, i32, vp, vp, vp, i64, vp]),
         "lz_vector_basis_info": (i32, [vp, P(i64), P(i32)]),
         "lz_vector_basis_copy": (i32, [vp, i32, i32, vp, i64]),
         "lz_block_lanczos": (i32, [vp, vp, vp, i64, i32, i32, i64, i32, vp, vp, vp]),
@@ -318,6 +325,50 @@ def vector_lanczos(ctx, A, b, m, lc=0, reorth=REORTH_NONE, q=None):
 
 def vector_lanczos_async(ctx, A, b, m, alpha_dev, beta_dev, lc=0, reorth=REORTH_NONE, q=None):
     check(lib().lz_vector_lanczos_async(ctx.h, A.h, _ptr(b), m, lc, reorth, _ptr(alpha_dev), _ptr(beta_dev), _ptr(q)))
+
+
+def vector_lanczos_begin(ctx, A, b, m_capacity, lc=0, reorth=REORTH_NONE, q=None):
+    check(lib().lz_vector_lanczos_begin(ctx.h, A.h, _ptr(b), m_capacity, lc, reorth, _ptr(q)))
+
+
+def vector_lanczos_advance(ctx, steps, m_capacity):
+    """`steps` more steps of the run begun on ctx; returns (alpha, beta, steps_done) with all coefficients so far."""
+    alpha, beta = np.zeros(m_capacity), np.zeros(m_capacity)
+    done = C.c_int(0)
+    st = lib().lz_vector_lanczos_advance(ctx.h, steps, alpha.ctypes.data, beta.ctypes.data, C.byref(done))
+    if st != LZ_OK and st != -4:
+        check(st)
+    return alpha[:done.value], beta[:done.value], done.value
+
+
+def checkpoint_save(ctx, path):
+    check(lib().lz_vector_checkpoint_save(ctx.h, str(path).encode()))
+
+
+def checkpoint_load(ctx, A, path, q=None):
+    check(lib().lz_vector_checkpoint_load(ctx.h, A.h, str(path).encode(), _ptr(q)))
+
+
+def ritz_vectors(ctx, Y, X, ldx):
+    """X[:, :k] = V_j Y for the run on ctx; Y: (j, k) numpy array, X: device buffer (column-major, ld = ldx)."""
+    Yc = np.asfortranarray(Y, dtype=np.float64)
+    check(lib().lz_vector_ritz_vectors(ctx.h, Yc.shape[1], Yc.ctypes.data, _ptr(X), ldx))
+
+
+def reorth_count(ctx):
+    c = C.c_int(0)
+    check(lib().lz_vector_reorth_count(ctx.h, C.byref(c)))
+    return c.value
+
+
+def eigs_thick_restart(ctx, A, b, k, which=0, m_max=None, tol=1e-10, max_restarts=200, X=None, ldx=0):
+    """k extremal eigenpairs by thick-restart Lanczos; returns (theta, resid_estimates, info dict)."""
+    m_max = m_max or max(2 * k + 8, 32)
+    theta, resid = np.zeros(k), np.zeros(k)
+    info = (C.c_int * 4)()
+    check(lib().lz_eigs_thick_restart(ctx.h, A.h, _ptr(b), k, which, m_max, float(tol), max_restarts, theta.ctypes.data,
+                                      resid.ctypes.data, _ptr(X), ldx, info))
+    return theta, resid, dict(converged=info[0], restarts=info[1], matvecs=info[2], basis=info[3])
 
 
 def block_lanczos(ctx, A, B, ldb, bw, m, alpha, beta, q, lc=0, reorth=REORTH_NONE):

@@ -42,6 +42,9 @@ extern "C" {
 #define LZ_REORTH_NONE 0
 #define LZ_REORTH_FULL 1      /* classical Gram-Schmidt, always two sweeps (CGS2)             */
 #define LZ_REORTH_FULL_DGKS 2 /* second sweep only when the first one removed > 1 - 1/sqrt2   */
+#define LZ_REORTH_SELECTIVE 3 /* partial reorthogonalisation: the omega recurrence (device-side) decides per step
+                                whether w is reorthogonalised against the stored basis (CGS2) -- semi-orthogonal
+                                basis, Ritz values to working precision, a fraction of the basis traffic           */
 
 /* lz_memcpy kinds */
 #define LZ_H2D 1
@@ -159,6 +162,31 @@ int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, i
 /* same, but coefficients stay in DEVICE arrays and nothing synchronises (bench / graph use) */
 int lz_vector_lanczos_async(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc,
                             int reorth, double *alpha_dev, double *beta_dev, double *q);
+/* The same run in pieces (extension).  begin: sets up a run of at most m_capacity steps (work vectors,
+ * basis slab for the reorthogonalising modes, beta_0 = ||b||).  advance: `steps` more Lanczos steps, then ALL
+ * coefficients so far to the host (alpha_host / beta_host: m_capacity entries, or NULL) and the number of valid steps
+ * (LZ_ERR_BREAKDOWN as in lz_vector_lanczos).  lz_vector_lanczos = begin + advance(m). */
+int lz_vector_lanczos_begin(lz_ctx *ctx, const lz_matrix *A, const double *b, int m_capacity, int64_t lc, int reorth,
+                            double *q);
+int lz_vector_lanczos_advance(lz_ctx *ctx, int steps, double *alpha_host, double *beta_host, int *steps_done);
+/* Save the current run -- (q_{j-1}, q_j, alpha, beta, 1/beta, j, the basis columns, the omega rows of a selective run)
+ * -- to a file, and recreate it on a context (this or another one, another process) for the same operator; the
+ * continued run reproduces the uninterrupted one bit for bit. */
+int lz_vector_checkpoint_save(lz_ctx *ctx, const char *path);
+int lz_vector_checkpoint_load(lz_ctx *ctx, const lz_matrix *A, const char *path, double *q);
+/* Ritz vectors X[:, 0..k) = V_j Y of the current run (full / selective reorthogonalisation keeps V): Y_host is the
+ * j x k column-major matrix of eigenvectors of T (j = steps done), X device column-major with leading dimension ldx.
+ * A tall-skinny fp64 tensor-core product (mma.m8n8k4) over the row-tiled basis. */
+int lz_vector_ritz_vectors(lz_ctx *ctx, int k, const double *Y_host, double *X, int64_t ldx);
+/* number of steps of the current LZ_REORTH_SELECTIVE run that reorthogonalised (synchronises) */
+int lz_vector_reorth_count(lz_ctx *ctx, int *count);
+/* Thick-restart Lanczos (extension): k extremal eigenpairs inside a basis of m_max vectors.
+ *   which: 0 smallest, 1 largest, 2 both ends (k/2 smallest + k - k/2 largest, as lz_ritz);  tol: a pair is converged
+ *   when its residual estimate |beta_m y_m| <= tol * max|theta|;  at most max_restarts compressions of the basis.
+ *   theta_host[k] ascending, resid_host[k] (or NULL) the estimates, X (or NULL): device n x k column-major Ritz vectors.
+ *   info4 (or NULL): converged pairs, restarts, operator applications, basis size. */
+int lz_eigs_thick_restart(lz_ctx *ctx, const lz_matrix *A, const double *b, int k, int which, int m_max, double tol,
+                          int max_restarts, double *theta_host, double *resid_host, double *X, int64_t ldx, int *info4);
 /* Krylov basis kept by the last full-reorth run (stored row-tiled inside the context):
  * copy columns j0 .. j0+ncols-1 into dst (device, column-major, leading dimension ldd >= rows) */
 int lz_vector_basis_info(lz_ctx *ctx, int64_t *rows, int *cols);

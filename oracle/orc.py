@@ -224,6 +224,60 @@ def ritz(alpha, beta, k, beta_last=None):
     return w[sel], res
 
 
+def thick_restart_lanczos(csr, b, k, which=0, m_max=None, tol=1e-10, max_restarts=200):
+    """numpy restatement of the thick-restart Lanczos in csrc/lz_eigs.cu (Wu & Simon's TRLan with full CGS2
+    reorthogonalisation), same restart rule: keep the k wanted Ritz pairs plus max(1, 2(m-k)/5) of their
+    neighbours, compress V <- V Y, continue from the residual vector.  which: 0 smallest, 1 largest, 2 both ends.
+    TEST INFRASTRUCTURE ONLY.  Returns (theta ascending, residual estimates, X, info)."""
+    n = len(csr[0]) - 1
+    m = m_max or max(2 * k + 8, 32)
+    V = np.zeros((n, m + 1))
+    H = np.zeros((m, m))
+    beta0 = np.linalg.norm(b)
+    V[:, 0] = b / beta0
+    j0, restarts, matvecs = 0, 0, 0
+    beta_prev = 0.0
+    while True:
+        for j in range(j0, m):
+            w = spmv(csr, V[:, j].copy())
+            if j > j0:
+                w -= beta_prev * V[:, j - 1]
+            c1 = V[:, :j + 1].T @ w
+            w -= V[:, :j + 1] @ c1
+            c2 = V[:, :j + 1].T @ w
+            w -= V[:, :j + 1] @ c2
+            H[j, j] = c1[j]
+            if j > j0:
+                H[j - 1, j] = H[j, j - 1] = beta_prev
+            beta_prev = np.linalg.norm(w)
+            V[:, j + 1] = w / beta_prev
+        matvecs += m - j0
+        beta_m = beta_prev
+        d, Z = np.linalg.eigh(H)
+        lo = k if which == 0 else 0 if which == 1 else k // 2
+        hi = k - lo
+        wanted = list(range(lo)) + list(range(m - hi, m))
+        res = np.abs(beta_m * Z[m - 1, :])
+        nconv = int(np.sum(res[wanted] <= tol * np.max(np.abs(d))))
+        if nconv == k or restarts == max_restarts:
+            break
+        extra = min(max(1, (m - k) * 2 // 5), m - k - 3)
+        elo = extra if which == 0 else 0 if which == 1 else extra // 2
+        ehi = extra - elo
+        keep = list(range(lo + elo)) + list(range(m - (hi + ehi), m))
+        kk = len(keep)
+        V[:, :kk] = V[:, :m] @ Z[:, keep]
+        V[:, kk] = V[:, m]
+        H[:] = 0.0
+        for c, i in enumerate(keep):
+            H[c, c] = d[i]
+            H[c, kk] = H[kk, c] = beta_m * Z[m - 1, i]
+        j0 = kk
+        restarts += 1
+    X = V[:, :m] @ Z[:, wanted]
+    return d[wanted], res[wanted], X, dict(converged=nconv, restarts=restarts, matvecs=matvecs, basis=m)
+
+
 def expm_sym(T):
     T = np.array(T, np.float64)
     n = T.shape[0]

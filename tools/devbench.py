@@ -62,6 +62,17 @@ def main():
             out["lap3d_256_block%d" % bw] = dict(ms_per_iter=ms / m, it_per_s=m / ms * 1e3, gbs=byt / (ms / m) / 1e6, frac=byt / (ms / m) / 1e6 / PEAK,
                                                  classes={k: dict(n=v[0], ms=round(v[1] / 2 / m, 4), gbs=round(v[2] / max(v[1], 1e-9) / 1e6, 1)) for k, v in prof.items() if v[0]})
             A.close(); del B
+    if "spmmcm" in which:
+        # the drop-in lz_spmm (column-major, reference layout) on 256^3, b = 16
+        A = lz.Matrix.laplacian3d(ctx, 256, 256, 256); n, nnz = A.n_rows, A.nnz
+        for bw in (4, 16):
+            X = torch.empty(n * bw, dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
+            lz.check(lz.lib().lz_gen_start_block(ctx.h, n, bw, n, 0x5EED, X.data_ptr()))
+            ms = timeit(lambda: lz.spmm(ctx, A, bw, X, n, Y, n), reps=5, warm=2)
+            byt = 12 * nnz + 4 * n + 16 * n * bw
+            out["lap3d_256_lz_spmm_b%d" % bw] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+            del X, Y
+        A.close()
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "devbench.json"), "w"), indent=1)
