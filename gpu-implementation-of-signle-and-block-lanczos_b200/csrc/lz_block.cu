@@ -379,7 +379,7 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
     if (grid > cr.total) grid = cr.total;
     const int per_cta = (cr.total + grid - 1) / grid;
     k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
-        nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->colidx, A->vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
+        nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
         ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : (FSUB ? LZ_SPMM_HINT_FUSED : 0));
     return LZ_OK;
 }
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256) k_cm_to_rm(int64_t n, int bw, const doubl
 // can W = A X - Q0 B run as ONE pass on this operator?  (staged kernel with the DMMA subtraction: 16 columns)
 static bool spmm_can_fuse(const lz_ctx *ctx, const lz_matrix *A, int bw)
 {
-    return bw == 16 && A->rowptr && A->tma_ok && A->mm_chunk_row && !A->vrowptr && ctx->spmv_variant != 9;
+    return bw == 16 && A->rowptr && A->tma_ok && A->mm_chunk_row && !A->vrowptr && ctx->spmv_variant != 9 && !ctx->knobs.no_spmm_fuse;
 }
 
 // part: 0 all rows, 1 interior chunks of a shard, 2 its boundary chunks (staged kernel only)
@@ -561,13 +561,13 @@ static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, 
         }
         LZ_CHECK(part == 0, LZ_ERR_INVALID, "spmm: partial launches need the staged kernel");
 #define CSR_CASE(B)                                                                                                     \
-    if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->colidx, A->vals, X, W, Q0, Bm); \
-    else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->colidx, A->vals, X, W, Q0, Bm)
+    if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm); \
+    else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm)
         if (bw == 4) { CSR_CASE(4); } else if (bw == 8) { CSR_CASE(8); } else if (bw == 16) { CSR_CASE(16); }
         else if (bw == 32) { CSR_CASE(32); }
         else {
-            if (fuse) k_spmm_rm_any<true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->colidx, A->vals, X, W, Q0, Bm);
-            else k_spmm_rm_any<false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->colidx, A->vals, X, W, Q0, Bm);
+            if (fuse) k_spmm_rm_any<true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm);
+            else k_spmm_rm_any<false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm);
         }
 #undef CSR_CASE
     }
@@ -578,15 +578,16 @@ static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, 
 
 // W[r,:] = sum of the partial rows of r's virtual pieces (row-split operators)
 __global__ void __launch_bounds__(256)
-k_split_combine_rows(int64_t n_rows, int bw, const int32_t *__restrict__ vstart, const double *__restrict__ Wbar, double *__restrict__ W)
+k_split_combine_rows(int64_t n_rows, int bw, const int32_t *__restrict__ vstart, const int32_t *__restrict__ vpos,
+                     const double *__restrict__ Wbar, double *__restrict__ W)
 {
     const int64_t total = n_rows * bw, stride = (int64_t)gridDim.x * 256;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) {
         const int64_t r = e / bw;
         const int c = (int)(e - r * bw);
         const int v0 = vstart[r], v1 = vstart[r + 1];
-        double t = Wbar[(int64_t)v0 * bw + c];
-        for (int v = v0 + 1; v < v1; ++v) t += Wbar[(int64_t)v * bw + c];
+        double t = Wbar[(int64_t)(vpos ? vpos[v0] : v0) * bw + c];
+        for (int v = v0 + 1; v < v1; ++v) t += Wbar[(int64_t)(vpos ? vpos[v] : v) * bw + c];
         W[e] = t;
     }
 }
@@ -600,7 +601,7 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
     void *wbar;
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)A->n_virtual * bw + 64, &wbar));
     LZ_TRY(spmm_rm_rows(ctx, A, A->vrowptr, A->n_virtual, bw, X, (double *)wbar, nullptr, nullptr));
-    k_split_combine_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A->n_rows, bw, A->vstart, (const double *)wbar, W);
+    k_split_combine_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A->n_rows, bw, A->vstart, A->vpos, (const double *)wbar, W);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
@@ -697,7 +698,7 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
         for (int r = 0; r < world; ++r) { const int64_t sp = off_rows + all[4 * r + 1] + all[4 * r + 2]; span_rows = sp > span_rows ? sp : span_rows; }
         n_below = rank > 0 ? all[4 * (rank - 1) + 1] * bw : 0;
     }
-    const size_t pstride = ((size_t)span_rows * bw + 15) & ~(size_t)15;      // one panel incl. halo rows, 128-byte multiple
+    const size_t pstride = ((size_t)span_rows * bw + (size_t)(ctx->knobs.panel_pad > 0 ? ctx->knobs.panel_pad : 0) + 15) & ~(size_t)15;   // one panel incl. halo rows, 128-byte multiple
     // Unsharded full reorthogonalisation keeps Q_j only inside the stored basis (block j at V + j*pan): the
     // normalisation writes it there and the SpMM gathers from there -- no per-step device-to-device copy.
     const bool inplace = reorth && !sharded;

@@ -60,6 +60,8 @@ struct LzKnobs {
     int no_fold;            // LZ_NO_FOLD: keep pass B + separate alpha in the full-reorth vector path
     int spmm_kernel;        // LZ_SPMM_KERNEL: 0 default choice, 1 k_spmm_ws (round-robin chunks), 2 k_spmm_win (staged X window)
     int block_cgs_fuse;     // LZ_BLOCK_CGS_FUSE: 1 (default) fused update+project in the block CGS2, 0 four streams
+    int panel_pad;          // LZ_PANEL_PAD: extra doubles between the block driver's panels (they are 2^k bytes apart on 2^k grids)
+    int no_spmm_fuse;       // LZ_NO_SPMM_FUSE: b = 16 runs the plain staged SpMM + two-Gram formulation instead of the fused subtraction
     int rmat_reorder;       // LZ_REORDER: locality reordering at lz_csr_create time for power-law operators
 };
 
@@ -139,7 +141,7 @@ void lz_prof_begin(lz_ctx *ctx, int cls, double bytes);
 void lz_prof_end(lz_ctx *ctx);
 #define LZ_PARTIALS_CAP (1 << 22)
 #define LZ_TICKETS 64
-#define LZ_SCALARS 8192
+#define LZ_SCALARS 16384
 #define LZ_FLAGS 64
 
 // ---- peer-memory communication (lz_multi.cu) ---------------------------------------------------
@@ -234,6 +236,12 @@ struct lz_matrix {
     int32_t *vrowptr;        // n_virtual + 1
     int32_t *vstart;         // n_rows + 1
     double *ybar;            // n_virtual
+    // length-binned order of the virtual rows (power-law operators, lz_csr.cu): vrowptr then indexes the binned copies
+    // bin_colidx / bin_vals, and piece v (in vstart numbering) of a row is found at position vpos[v]
+    int32_t *vpos, *bin_colidx;
+    double *bin_vals;
+    const int32_t *k_colidx; // the arrays the SpMV / SpMM kernels stream (binned copies when present)
+    const double *k_vals;
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
     int64_t halo_lo, halo_hi;        // halo entries below / above the local range
     // chunks [bnd_lo, bnd_hi) of the fine schedule (mm_*: of the coarse one) hold only rows that reference no halo
@@ -241,6 +249,9 @@ struct lz_matrix {
     int has_split, bnd_lo, bnd_hi, mm_bnd_lo, mm_bnd_hi;
     int64_t global_rows, row_begin;  // position in the global operator
 };
+
+int lz_ell4_build_shadow(lz_ctx *ctx, lz_matrix *A);                      // lz_csr.cu
+lz_matrix *lz_new_matrix(lz_ctx *ctx, int fmt, int64_t n_rows, int64_t n_cols, int64_t nnz);
 
 // ---- device helpers -------------------------------------------------------------------
 #ifdef __CUDACC__

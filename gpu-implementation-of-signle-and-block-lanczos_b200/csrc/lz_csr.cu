@@ -1,6 +1,7 @@
 // lz_csr.cu -- sparse operator objects: CSR (new, in the reference's container style), the
 // reference's ELLPACK (objects/ell_matrix.hpp:10-21), the row-block schedule used by the SpMV /
 // SpMM kernels, and the on-device generators of BASELINE.json's synthetic operators.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
@@ -55,6 +56,48 @@ __global__ void k_split_fill(int64_t n_rows, int64_t nnz, const int32_t *__restr
     for (int v = v0; v < v1; ++v) vrowptr[v] = s + (v - v0) * LZ_SPLIT_L;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-length binning for power-law operators.  After the split every virtual row has <= LZ_SPLIT_L entries, but
+// their lengths still range over 1..LZ_SPLIT_L and the SpMV / SpMM kernels give one thread (a 4..8-lane group) a
+// row at a time: a warp is as slow as its longest row (R-MAT scale 24: mean 32, so ~35 % of the lanes work).
+// The virtual rows are therefore re-ordered by DESCENDING LENGTH INSIDE WINDOWS of LZ_BIN_WINDOW rows -- a stable
+// radix sort on (window, 65535 - length) -- and colidx / vals are copied into that order (owned by the library):
+// rows that share a warp trip now have near-equal lengths, chunks stay contiguous slices for the bulk copies, and
+// the partial sums of a window stay within a few KB of each other (locality of the combine).  x / X keep their
+// order: only the ORDER OF THE ROWS changes, and the combine kernels find piece v of a row at ybar[vpos[v]].
+// ---------------------------------------------------------------------------------------------
+#define LZ_BIN_WINDOW 8192
+
+__global__ void k_bin_keys(int64_t nv, const int32_t *__restrict__ vrowptr, uint32_t *__restrict__ keys, int32_t *__restrict__ ids)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int len = vrowptr[v + 1] - vrowptr[v];
+    keys[v] = ((uint32_t)(v / LZ_BIN_WINDOW) << 9) | (uint32_t)(511 - min(len, 511));    // LZ_SPLIT_L <= 256 < 512
+    ids[v] = (int32_t)v;
+}
+__global__ void k_bin_lens(int64_t nv, const int32_t *__restrict__ vrowptr, const int32_t *__restrict__ perm, int32_t *__restrict__ lens,
+                           int32_t *__restrict__ vpos)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nv) return;
+    if (i == nv) { lens[i] = 0; return; }
+    const int v = perm[i];                    // new position i holds old virtual row v
+    lens[i] = vrowptr[v + 1] - vrowptr[v];
+    vpos[v] = (int32_t)i;
+}
+// one warp per new row: copy its entries from the old position
+__global__ void __launch_bounds__(256)
+k_bin_copy(int64_t nv, const int32_t *__restrict__ old_ptr, const int32_t *__restrict__ new_ptr, const int32_t *__restrict__ perm,
+           const int32_t *__restrict__ colidx, const double *__restrict__ vals, int32_t *__restrict__ ncol, double *__restrict__ nval)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= nv) return;
+    const int src = old_ptr[perm[i]], dst = new_ptr[i], len = new_ptr[i + 1] - dst;
+    for (int k = lane; k < len; k += 32) { ncol[dst + k] = colidx[src + k]; nval[dst + k] = vals[src + k]; }
+}
+
 static int build_split(lz_ctx *ctx, lz_matrix *A)
 {
     const int64_t n = A->n_rows;
@@ -79,6 +122,41 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
     LZ_CUDA(cudaMalloc(&A->ybar, sizeof(double) * ((size_t)nv + 8)));
     k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->csr_nnz, A->rowptr, A->vstart, A->vrowptr);
     LZ_LAUNCH_CHECK(ctx);
+    if (!ctx->knobs.rmat_reorder || (int64_t)nv / LZ_BIN_WINDOW >= (1 << 22)) return LZ_OK;
+    // ---- length binning of the virtual rows (see above) ----
+    const unsigned gv = (unsigned)(((int64_t)nv + 1 + 255) / 256);
+    uint32_t *keys, *keys2;
+    int32_t *ids, *perm, *lens, *nptr, *ncol;
+    double *nval;
+    LZ_CUDA(cudaMalloc(&keys, sizeof(uint32_t) * (size_t)nv)); LZ_CUDA(cudaMalloc(&keys2, sizeof(uint32_t) * (size_t)nv));
+    LZ_CUDA(cudaMalloc(&ids, sizeof(int32_t) * (size_t)nv)); LZ_CUDA(cudaMalloc(&perm, sizeof(int32_t) * (size_t)nv));
+    LZ_CUDA(cudaMalloc(&lens, sizeof(int32_t) * ((size_t)nv + 1))); LZ_CUDA(cudaMalloc(&nptr, sizeof(int32_t) * ((size_t)nv + 8)));
+    LZ_CUDA(cudaMalloc(&A->vpos, sizeof(int32_t) * (size_t)nv));
+    k_bin_keys<<<gv, 256, 0, ctx->stream>>>(nv, A->vrowptr, keys, ids);
+    LZ_LAUNCH_CHECK(ctx);
+    tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ids, perm, nv, 0, 32, ctx->stream);
+    LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, perm, nv, 0, 32, ctx->stream);   // stable: pieces of one row stay in order
+    ctx->launches++;
+    k_bin_lens<<<gv, 256, 0, ctx->stream>>>(nv, A->vrowptr, perm, lens, A->vpos);
+    LZ_LAUNCH_CHECK(ctx);
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    LZ_CUDA(cudaFree(tmp));
+    tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens, nptr, nv + 1, ctx->stream);
+    LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lens, nptr, nv + 1, ctx->stream);
+    ctx->launches++;
+    LZ_CUDA(cudaMalloc(&ncol, sizeof(int32_t) * ((size_t)A->csr_nnz + 8)));
+    LZ_CUDA(cudaMalloc(&nval, sizeof(double) * ((size_t)A->csr_nnz + 8)));
+    k_bin_copy<<<(unsigned)(((int64_t)nv * 32 + 255) / 256), 256, 0, ctx->stream>>>(nv, A->vrowptr, nptr, perm, A->colidx, A->vals, ncol, nval);
+    LZ_LAUNCH_CHECK(ctx);
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    LZ_CUDA(cudaFree(tmp)); LZ_CUDA(cudaFree(keys)); LZ_CUDA(cudaFree(keys2)); LZ_CUDA(cudaFree(ids)); LZ_CUDA(cudaFree(perm)); LZ_CUDA(cudaFree(lens));
+    LZ_CUDA(cudaFree(A->vrowptr));
+    A->vrowptr = nptr;              // virtual row pointers in binned order, over the binned copies below
+    A->bin_colidx = ncol; A->bin_vals = nval;
     return LZ_OK;
 }
 
@@ -103,7 +181,9 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     A->n_chunks = (int)nch;
     LZ_CUDA(cudaMalloc(&A->chunk_row, sizeof(int32_t) * (nch + 1)));
     LZ_CUDA(cudaMalloc(&A->chunk_ptr, sizeof(int32_t) * (nch + 1)));
-    A->tma_ok = ((uintptr_t)A->vals % 16 == 0) && ((uintptr_t)A->colidx % 16 == 0);
+    A->k_colidx = A->bin_colidx ? A->bin_colidx : A->colidx;       // what the SpMV / SpMM kernels stream
+    A->k_vals = A->bin_vals ? A->bin_vals : A->vals;
+    A->tma_ok = ((uintptr_t)A->k_vals % 16 == 0) && ((uintptr_t)A->k_colidx % 16 == 0);
     k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
     // the SpMM kernel amortises its per-chunk cost over wider rows: its own, coarser schedule
@@ -341,7 +421,50 @@ int lz_gen_lap2d_rows(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t row0, int64_t
     return finish_csr(ctx, A, out);
 }
 
+// CSR shadow of a row-interleaved width-4 ELL operator (explicit zeros dropped, ELL column order kept) with the chunk
+// schedules: the block path runs the staged SpMM on it instead of a width-4 ELL kernel; the vector path keeps k_ell4_spmv
+int lz_ell4_build_shadow(lz_ctx *ctx, lz_matrix *A)
+{
+    const int64_t n_rows = A->n_rows;
+    const unsigned grid = (unsigned)((n_rows + 255) / 256);
+    int32_t *cnt, *rp;
+    LZ_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * (n_rows + 1)));
+    LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n_rows + 1)));
+    LZ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (n_rows + 1), ctx->stream));
+    k_ell_count<<<grid, 256, 0, ctx->stream>>>(n_rows, 4, 1, A->ell_data, cnt);
+    LZ_LAUNCH_CHECK(ctx);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
+    void *tmp;
+    LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
+    ctx->launches++;
+    int32_t nnz32 = 0;
+    LZ_CUDA(cudaMemcpyAsync(&nnz32, rp + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    LZ_CUDA(cudaFree(tmp));
+    LZ_CUDA(cudaFree(cnt));
+    int32_t *ci; double *va;
+    LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * ((size_t)nnz32 + 8)));
+    LZ_CUDA(cudaMalloc(&va, sizeof(double) * ((size_t)nnz32 + 8)));
+    A->rowptr = rp; A->colidx = ci; A->vals = va;
+    A->owns_csr = 1; A->csr_nnz = nnz32;
+    k_ell_fill<<<grid, 256, 0, ctx->stream>>>(n_rows, 4, 1, A->ell_data, A->ell_idx, rp, ci, va);
+    LZ_LAUNCH_CHECK(ctx);
+    return build_schedule(ctx, A);
+}
+
+lz_matrix *lz_new_matrix(lz_ctx *ctx, int fmt, int64_t n_rows, int64_t n_cols, int64_t nnz) { return new_matrix(ctx, fmt, n_rows, n_cols, nnz); }
+
 extern "C" {
+
+int lz_matrix_ell_view(const lz_matrix *A, const double **data, const uint32_t **idx)
+{
+    LZ_CHECK(A, LZ_ERR_INVALID, "lz_matrix_ell_view: A is NULL");
+    if (data) *data = A->format == LZ_FMT_ELL4 ? A->ell_data : nullptr;
+    if (idx) *idx = A->format == LZ_FMT_ELL4 ? A->ell_idx : nullptr;
+    return LZ_OK;
+}
 
 int lz_csr_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *rowptr,
                   const int32_t *colidx, const double *vals, lz_matrix **out)
@@ -403,34 +526,8 @@ int lz_ell_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int width, int la
             }
         }
         A->max_row_nnz = 4;
-        // CSR shadow (explicit zeros dropped, ELL column order kept) with the chunk schedules: the block path
-        // runs the staged SpMM on it instead of a width-4 ELL kernel; the vector path keeps k_ell4_spmv
         {
-            int32_t *cnt, *rp;
-            LZ_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * (n_rows + 1)));
-            LZ_CUDA(cudaMalloc(&rp, sizeof(int32_t) * (n_rows + 1)));
-            LZ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (n_rows + 1), ctx->stream));
-            k_ell_count<<<grid, 256, 0, ctx->stream>>>(n_rows, 4, 1, A->ell_data, cnt);
-            LZ_LAUNCH_CHECK(ctx);
-            size_t tmp_bytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
-            void *tmp;
-            LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
-            cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, rp, (int)(n_rows + 1), ctx->stream);
-            ctx->launches++;
-            int32_t nnz32 = 0;
-            LZ_CUDA(cudaMemcpyAsync(&nnz32, rp + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            LZ_CUDA(cudaStreamSynchronize(ctx->stream));
-            LZ_CUDA(cudaFree(tmp));
-            LZ_CUDA(cudaFree(cnt));
-            int32_t *ci; double *va;
-            LZ_CUDA(cudaMalloc(&ci, sizeof(int32_t) * ((size_t)nnz32 + 8)));
-            LZ_CUDA(cudaMalloc(&va, sizeof(double) * ((size_t)nnz32 + 8)));
-            A->rowptr = rp; A->colidx = ci; A->vals = va;
-            A->owns_csr = 1; A->csr_nnz = nnz32;
-            k_ell_fill<<<grid, 256, 0, ctx->stream>>>(n_rows, 4, 1, A->ell_data, A->ell_idx, rp, ci, va);
-            LZ_LAUNCH_CHECK(ctx);
-            int st = build_schedule(ctx, A);
+            int st = lz_ell4_build_shadow(ctx, A);
             if (st != LZ_OK) { lz_matrix_destroy(A); return st; }
         }
         *out = A;
@@ -492,6 +589,9 @@ int lz_matrix_destroy(lz_matrix *A)
     cudaFree(A->vrowptr);
     cudaFree(A->vstart);
     cudaFree(A->ybar);
+    cudaFree(A->vpos);
+    cudaFree(A->bin_colidx);
+    cudaFree(A->bin_vals);
     delete A;
     return LZ_OK;
 }

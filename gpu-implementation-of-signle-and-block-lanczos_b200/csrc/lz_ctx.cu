@@ -72,6 +72,8 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     k.spmm_kernel = env_int("LZ_SPMM_KERNEL", 0);
     k.block_cgs_fuse = env_int("LZ_BLOCK_CGS_FUSE", 1);
     k.rmat_reorder = env_int("LZ_REORDER", 1);
+    k.panel_pad = env_int("LZ_PANEL_PAD", 0);
+    k.no_spmm_fuse = env_set("LZ_NO_SPMM_FUSE");
     *out = c;
     return LZ_OK;
 }

@@ -31,11 +31,23 @@ static int gram_launch(lz_ctx *ctx, int64_t n, int bw, const double *X, int64_t 
     return LZ_OK;
 }
 
+enum { SB_S8A = 8192, SB_S8B = 8192 + 64 };      // 8 x 8 block-diagonal copies of 4 x 4 factors (ctx->scalars)
+
 int lz_gram(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *X, int64_t ldx, const double *Y, int64_t ldy,
             double *G, int mode)
 {
     const int grid = dense_grid(ctx, n);
     void *w;
+    if (rm && bw == 4 && n % 2 == 0 && (uintptr_t)X % 16 == 0 && (uintptr_t)Y % 16 == 0) {      // width 4 on the tensor pipe (pairs of rows)
+        LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * 64, &w));
+        lz_prof_begin(ctx, LZ_K_GRAM, 8.0 * (double)n * bw * (X == Y ? 1.0 : 2.0));
+        k_gram_dmma<8, true, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n / 2, X, 0, Y, 0, (double *)w);
+        LZ_LAUNCH_CHECK(ctx);
+        lz_prof_end(ctx);
+        k_gram_reduce_fold4<<<2, 256, 0, ctx->stream>>>(grid, (const double *)w, G, mode);
+        LZ_LAUNCH_CHECK(ctx);
+        return LZ_OK;
+    }
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * bw * bw, &w));
     if (rm) return gram_launch<true, true>(ctx, n, bw, X, ldx, Y, ldy, G, mode, (double *)w, grid);
     return gram_launch<false, false>(ctx, n, bw, X, ldx, Y, ldy, G, mode, (double *)w, grid);
@@ -75,6 +87,22 @@ int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t l
 {
     const int grid = dense_grid(ctx, n);
     void *w = nullptr;
+    if (rm && bw == 4 && n % 2 == 0 && (uintptr_t)T % 16 == 0 && (uintptr_t)R % 16 == 0) {      // width 4 on the tensor pipe (pairs of rows)
+        double *S8 = ctx->scalars + SB_S8A;
+        k_blockdiag2<<<1, 64, 0, ctx->stream>>>(S, S8);
+        LZ_LAUNCH_CHECK(ctx);
+        if (G_opt) LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * 64, &w));
+        lz_prof_begin(ctx, LZ_K_PANEL, 8.0 * (double)n * bw * (beta != 0.0 ? 3.0 : 2.0));
+        if (G_opt) k_panel_dmma<8, true, true, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n / 2, T, 0, S8, beta, alpha, R, 0, (double *)w);
+        else k_panel_dmma<8, true, true, false><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n / 2, T, 0, S8, beta, alpha, R, 0, nullptr);
+        LZ_LAUNCH_CHECK(ctx);
+        lz_prof_end(ctx);
+        if (G_opt) {
+            k_gram_reduce_fold4<<<2, 256, 0, ctx->stream>>>(grid, (const double *)w, G_opt, 0);
+            LZ_LAUNCH_CHECK(ctx);
+        }
+        return LZ_OK;
+    }
     if (G_opt) LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * bw * bw, &w));
     if (rm) return panel_launch<true>(ctx, n, bw, T, ldt, S, beta, alpha, R, ldr, G_opt, (double *)w, grid);
     return panel_launch<false>(ctx, n, bw, T, ldt, S, beta, alpha, R, ldr, G_opt, (double *)w, grid);
@@ -83,12 +111,30 @@ int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t l
 // W -= T1 S1 + T2 S2 (row-major), G_opt receives W_new^T W_new
 int lz_panel2(lz_ctx *ctx, int64_t n, int bw, const double *T1, const double *S1, const double *T2, const double *S2, double *W, double *G_opt)
 {
+    const int grid = dense_grid(ctx, n);
+    void *w = nullptr;
+    if (bw == 4 && n % 2 == 0 && (uintptr_t)T1 % 16 == 0 && (uintptr_t)T2 % 16 == 0 && (uintptr_t)W % 16 == 0) {   // width 4: pairs of rows
+        double *S8a = ctx->scalars + SB_S8A, *S8b = ctx->scalars + SB_S8B;
+        k_blockdiag2<<<1, 64, 0, ctx->stream>>>(S1, S8a);
+        LZ_LAUNCH_CHECK(ctx);
+        k_blockdiag2<<<1, 64, 0, ctx->stream>>>(S2, S8b);
+        LZ_LAUNCH_CHECK(ctx);
+        if (G_opt) LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * 64, &w));
+        lz_prof_begin(ctx, LZ_K_PANEL, 8.0 * (double)n * bw * 4.0);
+        if (G_opt) k_panel2_dmma<8, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n / 2, T1, S8a, T2, S8b, W, (double *)w);
+        else k_panel2_dmma<8, false><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n / 2, T1, S8a, T2, S8b, W, nullptr);
+        LZ_LAUNCH_CHECK(ctx);
+        lz_prof_end(ctx);
+        if (G_opt) {
+            k_gram_reduce_fold4<<<2, 256, 0, ctx->stream>>>(grid, (const double *)w, G_opt, 0);
+            LZ_LAUNCH_CHECK(ctx);
+        }
+        return LZ_OK;
+    }
     if (!(bw == 8 || bw == 16 || bw == 32)) {
         LZ_TRY(lz_panel(ctx, n, bw, true, T1, 0, S1, 1.0, -1.0, W, 0, nullptr));
         return lz_panel(ctx, n, bw, true, T2, 0, S2, 1.0, -1.0, W, 0, G_opt);
     }
-    const int grid = dense_grid(ctx, n);
-    void *w = nullptr;
     if (G_opt) LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * bw * bw, &w));
     lz_prof_begin(ctx, LZ_K_PANEL, 8.0 * (double)n * bw * 4.0);
 #define LZ_P2(B)                                                                                                        \

@@ -161,6 +161,31 @@ k_gram_reduce(int bw, int n_parts, const double *__restrict__ gpart, int gstride
     if (lane == 0) G[e] = mode == 0 ? s : 0.5 * s + 0.5 * st;
 }
 
+// Width-4 panels on the tensor pipe.  mma.m8n8k4 wants 8 columns, so a row-major n x 4 panel (n even) is read as an
+// (n/2) x 8 panel whose row i is [row 2i | row 2i+1]:  X8^T Y8 = [[Xe^T Ye, Xe^T Yo], [Xo^T Ye, Xo^T Yo]] and the 4 x 4
+// Gram matrix is the sum of the two diagonal blocks;  T8 blockdiag(S, S) = [Te S | To S] is the panel product itself.
+static __global__ void k_blockdiag2(const double *__restrict__ S, double *__restrict__ S8)
+{
+    const int e = threadIdx.x;
+    if (e < 64) { const int r = e % 8, c = e / 8; S8[e] = (r / 4 == c / 4) ? S[(r % 4) + (c % 4) * 4] : 0.0; }
+}
+static __global__ void __launch_bounds__(256)
+k_gram_reduce_fold4(int n_parts, const double *__restrict__ gpart /* [parts][64] */, double *__restrict__ G, int mode)
+{
+    const int lane = threadIdx.x & 31, e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= 16) return;
+    const int p = e % 4, q = e / 4;
+    double s = 0.0, st = 0.0;
+    for (int i = lane; i < n_parts; i += 32) {
+        const double *g = gpart + (size_t)i * 64;
+        s += g[p + q * 8] + g[(p + 4) + (q + 4) * 8];
+        if (mode == 1) st += g[q + p * 8] + g[(q + 4) + (p + 4) * 8];
+    }
+    s = lz_warp_sum(s);
+    if (mode == 1) st = lz_warp_sum(st);
+    if (lane == 0) G[e] = mode == 0 ? s : 0.5 * s + 0.5 * st;
+}
+
 // two Gram matrices from one read of X:  G1_partial = X^T Y1,  G2_partial = X^T Y2   (row-major panels).
 // Used for the reference order of the block recurrence when the SpMM cannot subtract Q_{j-1} beta_j itself:
 // alpha_j = sym(Q_j^T (A Q_j - Q_{j-1} beta_j)) = sym(G1 - G2 beta_j) with G1 = Q_j^T (A Q_j), G2 = Q_j^T Q_{j-1}.

@@ -451,7 +451,7 @@ static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const do
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > cr.total) grid = cr.total;
     k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
-        cr, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args, blocked,
+        cr, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->k_colidx, A->k_vals, x, y, args, blocked,
         ctx->knobs.spmv_hint);      // evict-first on the matrix streams measured 4-5 % slower: off
     return LZ_OK;
 }
@@ -500,7 +500,7 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
         if (coarse) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, 0, true, part)));
         else LZ_TRY((lz_launch_ws_variant<MODE, 3, 5, 3, 1024, 5>(ctx, A, x, y, args, 5, 0, false, part)));
     } else {
-        k_csr_spmv<MODE><<<A->n_chunks, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->chunk_row, A->vrowptr ? A->vrowptr : A->rowptr, A->colidx, A->vals, x, y, args);
+        k_csr_spmv<MODE><<<A->n_chunks, LZ_SPMV_THREADS, 0, ctx->stream>>>(A->chunk_row, A->vrowptr ? A->vrowptr : A->rowptr, A->k_colidx, A->k_vals, x, y, args);
     }
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
@@ -516,17 +516,17 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_split_combine(int64_t n_rows, const int32_t *__restrict__ vstart, const double *__restrict__ ybar, double *__restrict__ y,
-                const LzPassA args)
+k_split_combine(int64_t n_rows, const int32_t *__restrict__ vstart, const int32_t *__restrict__ vpos, const double *__restrict__ ybar,
+                double *__restrict__ y, const LzPassA args)
 {
     __shared__ double red[32];
     const LzRowEpi<MODE> epi(args);
     double acc = 0.0;
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n_rows; r += stride) {
-        const int v0 = vstart[r], v1 = vstart[r + 1];
-        double t = ybar[v0];
-        for (int v = v0 + 1; v < v1; ++v) t += ybar[v];
+        const int v0 = vstart[r], v1 = vstart[r + 1];       // piece v of the row sits at ybar[vpos[v]] in the binned order
+        double t = ybar[vpos ? vpos[v0] : v0];
+        for (int v = v0 + 1; v < v1; ++v) t += ybar[vpos ? vpos[v] : v];
         acc += epi.finish(r, t, y);
     }
     if (MODE == LZ_EPI_LANCZOS) {
@@ -546,7 +546,7 @@ static inline int lz_spmv_any(lz_ctx *ctx, const lz_matrix *A, const double *x, 
     if (MODE == LZ_EPI_LANCZOS) LZ_TRY(lz_launch_spmv<LZ_EPI_SCALED>(ctx, A, x, A->ybar, args));
     else LZ_TRY(lz_launch_spmv<LZ_EPI_PLAIN>(ctx, A, x, A->ybar, args));
     int64_t want = (A->n_rows + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
-    k_split_combine<MODE><<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(A->n_rows, A->vstart, A->ybar, y, args);
+    k_split_combine<MODE><<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(A->n_rows, A->vstart, A->vpos, A->ybar, y, args);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }

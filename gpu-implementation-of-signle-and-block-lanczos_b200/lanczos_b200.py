@@ -55,6 +55,8 @@ def lib():
         "lz_matrix_destroy": (i32, [vp]),
         "lz_matrix_info": (i32, [vp, P(i64), P(i64), P(i64)]),
         "lz_matrix_csr_view": (i32, [vp, P(vp), P(vp), P(vp)]),
+        "lz_gen_maxwell": (i32, [vp, i32, i32, i32, P(vp)]),
+        "lz_matrix_ell_view": (i32, [vp, P(vp), P(vp)]),
         "lz_gen_laplacian2d": (i32, [vp, i64, i64, P(vp)]),
         "lz_gen_laplacian3d": (i32, [vp, i64, i64, i64, P(vp)]),
         "lz_gen_rmat_edges": (i32, [vp, i32, i64, u64, vp, vp]),
@@ -201,6 +203,22 @@ class Matrix:
         h = C.c_void_p()
         check(lib().lz_ell_create(ctx.h, n_rows, n_cols, width, layout, _ptr(data), _ptr(idx), C.byref(h)))
         return cls(ctx, h, (data, idx))
+
+    @classmethod
+    def maxwell(cls, ctx, nx, ny=None, nz=None):
+        """The reference's Matrix_A(Nx, Ny, Nz) (A = D W), assembled on the device."""
+        h = C.c_void_p()
+        check(lib().lz_gen_maxwell(ctx.h, nx, ny or nx, nz or nx, C.byref(h)))
+        return cls(ctx, h)
+
+    def ell_to_host(self):
+        """(data, idx) numpy copies of a width-4 ELL operator, shape (n_rows, 4) (row-interleaved device format)."""
+        d, i = C.c_void_p(), C.c_void_p()
+        check(lib().lz_matrix_ell_view(self.h, C.byref(d), C.byref(i)))
+        data, idx = np.empty((self.n_rows, 4), np.float64), np.empty((self.n_rows, 4), np.uint32)
+        check(lib().lz_memcpy(self.ctx.h, data.ctypes.data, d, data.nbytes, D2H))
+        check(lib().lz_memcpy(self.ctx.h, idx.ctypes.data, i, idx.nbytes, D2H))
+        return data, idx
 
     @classmethod
     def laplacian2d(cls, ctx, nx, ny):

@@ -106,6 +106,14 @@ int lz_matrix_csr_view(const lz_matrix *A, const int32_t **rowptr, const int32_t
 /* synthetic operators generated on the device (BASELINE.json configs 2-5) */
 int lz_gen_laplacian2d(lz_ctx *ctx, int64_t nx, int64_t ny, lz_matrix **out);
 int lz_gen_laplacian3d(lz_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, lz_matrix **out);
+/* The reference's own test operator, assembled on the device: A = D W of Matrix_A(Nx, Ny, Nz)
+ * (matrix_a/build_A_ell.hpp:8-255 followed by Ell_matrix::mult_diagonal, test_lanczos.cu:29-49) -- the 3-D Maxwell curl
+ * operator on a staggered grid, n = 3 N (N+1)(2N+1) rows for Nx = Ny = Nz = N, width-4 ELL.  Every entry comes from
+ * the closed form of the Kronecker products in the reference's operation order: the arrays are bit-identical to the
+ * host builder's.  The result is a native row-interleaved ELL4 operator (lz_matrix_ell_view shows its arrays). */
+int lz_gen_maxwell(lz_ctx *ctx, int Nx, int Ny, int Nz, lz_matrix **out);
+/* borrowed views of the row-interleaved ELL arrays of a width-4 ELL operator (NULL for CSR operators) */
+int lz_matrix_ell_view(const lz_matrix *A, const double **data, const uint32_t **idx);
 /* directed R-MAT edge list, (a,b,c,d) = (0.57,0.19,0.19,0.05), counter-based RNG (config 4); the caller
  * symmetrises / de-duplicates / adds the Laplacian diagonal (tools/rmat.py) and hands the CSR to lz_csr_create */
 int lz_gen_rmat_edges(lz_ctx *ctx, int scale, int64_t n_edges, uint64_t seed, int32_t *src, int32_t *dst);

@@ -278,6 +278,71 @@ def thick_restart_lanczos(csr, b, k, which=0, m_max=None, tol=1e-10, max_restart
     return d[wanted], res[wanted], X, dict(converged=nconv, restarts=restarts, matvecs=matvecs, basis=m)
 
 
+def _mx_axis(N):
+    Np = N + 2
+    h = (1.0 - 0.0) / (Np - 1)
+    p = np.array([0.0 + i * h for i in range(Np)])
+    h2 = ((1.0 - h) - 0.0) / (Np - 2)
+    d = np.array([0.0 + i * h2 for i in range(Np - 1)]) + h / 2
+    dp, dd = p[1:] - p[:-1], d[1:] - d[:-1]
+    F = dict(rows=N + 1, cols=N, w=2, val=np.zeros((N + 1, 2)), col=np.zeros((N + 1, 2), np.int64))
+    for r in range(N + 1):
+        inv = 1.0 / dp[r]; s = 0
+        if r >= 1: F["val"][r, s] = inv * -1.0; F["col"][r, s] = r - 1; s += 1
+        if r < N: F["val"][r, s] = inv * 1.0; F["col"][r, s] = r
+    B = dict(rows=N, cols=N + 1, w=2, val=np.zeros((N, 2)), col=np.zeros((N, 2), np.int64))
+    for r in range(N):
+        inv = 1.0 / dd[r]
+        B["val"][r, 0] = -(inv * 1.0); B["col"][r, 0] = r
+        B["val"][r, 1] = -(inv * -1.0); B["col"][r, 1] = r + 1
+    ident = lambda n: dict(rows=n, cols=n, w=1, val=np.ones((n, 1)), col=np.arange(n).reshape(n, 1))
+    diagv = lambda v: dict(rows=len(v), cols=len(v), w=1, val=v.reshape(-1, 1).copy(), col=np.arange(len(v)).reshape(-1, 1))
+    return dict(F=F, B=B, I=ident(N), Ip=ident(N + 1), W=diagv(dp), Wh=diagv(dd))
+
+def _mx_k3(a, b, c, sign=1.0):
+    rows = a["rows"] * b["rows"] * c["rows"]; w = a["w"] * b["w"] * c["w"]
+    R = np.arange(rows)
+    rz, rem = R // (b["rows"] * c["rows"]), R % (b["rows"] * c["rows"])
+    ry, rx = rem // c["rows"], rem % c["rows"]
+    val = np.zeros((rows, w)); col = np.zeros((rows, w), np.int64)
+    for s in range(w):
+        ka, kb, kc = s // (b["w"] * c["w"]), (s // c["w"]) % b["w"], s % c["w"]
+        val[:, s] = a["val"][rz, ka] * (b["val"][ry, kb] * c["val"][rx, kc])
+        col[:, s] = a["col"][rz, ka] * (b["cols"] * c["cols"]) + (b["col"][ry, kb] * c["cols"] + c["col"][rx, kc])
+    if sign != 1.0: val = val * sign
+    return dict(rows=rows, cols=a["cols"] * b["cols"] * c["cols"], w=w, val=val, col=col)
+
+def maxwell_closed_form(Nx, Ny=None, Nz=None):
+    """Closed form of the reference's Matrix_A(Nx, Ny, Nz) followed by mult_diagonal (matrix_a/build_A_ell.hpp:8-255,
+    objects/ell_matrix.hpp:340-361): numpy restatement of what csrc/lz_maxwell.cu evaluates per row.  Returns
+    (D values (n,4), column ids (n,4), W diagonal (n,), A = D W values (n,4)).  TEST INFRASTRUCTURE ONLY."""
+    x, y, z = _mx_axis(Nx), _mx_axis(Ny or Nx), _mx_axis(Nz or Nx)
+    De12, De13 = _mx_k3(z["F"], y["Ip"], x["I"], -1.0), _mx_k3(z["Ip"], y["F"], x["I"])
+    De21, De23 = _mx_k3(z["F"], y["I"], x["Ip"]), _mx_k3(z["Ip"], y["I"], x["F"], -1.0)
+    De31, De32 = _mx_k3(z["I"], y["F"], x["Ip"], -1.0), _mx_k3(z["I"], y["Ip"], x["F"])
+    Dh12, Dh13 = _mx_k3(z["B"], y["I"], x["Ip"]), _mx_k3(z["I"], y["B"], x["Ip"], -1.0)
+    Dh21, Dh23 = _mx_k3(z["B"], y["Ip"], x["I"], -1.0), _mx_k3(z["I"], y["Ip"], x["B"])
+    Dh31, Dh32 = _mx_k3(z["Ip"], y["B"], x["I"]), _mx_k3(z["Ip"], y["I"], x["B"], -1.0)
+    def curl(b12, b13, b21, b23, b31, b32, c1, c2):
+        rows = b12["rows"] + b21["rows"] + b31["rows"]
+        val = np.zeros((rows, 4)); col = np.zeros((rows, 4), np.int64)
+        r2, r3 = b12["rows"], b12["rows"] + b21["rows"]
+        def ins(blk, r0, s0, shift):
+            val[r0:r0 + blk["rows"], s0:s0 + 2] = blk["val"]; col[r0:r0 + blk["rows"], s0:s0 + 2] = blk["col"] + shift
+        ins(b12, 0, 0, c1); ins(b13, 0, 2, c1 + c2)
+        ins(b21, r2, 0, 0); ins(b23, r2, 2, c1 + c2)
+        ins(b31, r3, 0, 0); ins(b32, r3, 2, c1)
+        return val, col
+    De_rows = De12["rows"] + De21["rows"] + De31["rows"]; Dh_rows = Dh12["rows"] + Dh21["rows"] + Dh31["rows"]
+    Dev, Dec = curl(De12, De13, De21, De23, De31, De32, Dh12["rows"], Dh21["rows"])
+    Dhv, Dhc = curl(Dh12, Dh13, Dh21, Dh23, Dh31, Dh32, De12["rows"], De21["rows"])
+    Dv = np.vstack([Dhv, Dev]); Dc = np.vstack([Dhc + Dh_rows, Dec])
+    Wb = [_mx_k3(z["Wh"], y["Wh"], x["W"]), _mx_k3(z["Wh"], y["W"], x["Wh"]), _mx_k3(z["W"], y["Wh"], x["Wh"]),
+          _mx_k3(z["W"], y["W"], x["Wh"], -1.0), _mx_k3(z["W"], y["Wh"], x["W"], -1.0), _mx_k3(z["Wh"], y["W"], x["W"], -1.0)]
+    Wv = np.concatenate([b["val"][:, 0] for b in Wb])
+    Av = Dv * Wv[Dc]
+    return Dv, Dc, Wv, Av
+
 def expm_sym(T):
     T = np.array(T, np.float64)
     n = T.shape[0]

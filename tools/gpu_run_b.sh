@@ -21,3 +21,11 @@ print("hint $h", {k:(round(v["it_per_s"],1), v["classes"]["spmm"]["ms"], v["clas
 PY
 done 2>&1 | tee gpurun_out/b_spmm_hint_sweep_8_32.log
 timeout 200 python tools/devbench.py spmmcm 2>&1 | tail -5 | tee gpurun_out/b_spmm_cm.log
+for r in 1 0; do
+  LZ_REORDER=$r timeout 400 python tools/run_configs.py cfg4 > /tmp/o.log 2>&1 || tail -5 /tmp/o.log
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/configs.json"))
+print("LZ_REORDER=$r", {k:(round(v.get("it_per_s",0),2), {c:round(x["ms"]/max(x["launches"],1),3) for c,x in v.get("classes",{}).items()}) for k,v in d.items() if "classes" in v})
+PY
+done 2>&1 | tee gpurun_out/b_rmat.log
