@@ -164,7 +164,7 @@ k_spmm_rm(int64_t n_rows, const int32_t *__restrict__ rowptr, const int32_t *__r
 #define SPMM_WS_RCAP 1024      // rowptr entries staged per chunk
 // default L2 policy bits of the fused (A X - Q0 B) kernel: the extra Q0 stream otherwise pushes the gathered panel's
 // reuse window out of L2 (3.2 ms instead of 1.4 ms on 256^3, b = 16: profiles/r02_spmm.md)
-#define LZ_SPMM_HINT_FUSED 15
+#define LZ_SPMM_HINT_FUSED 6
 
 __device__ __forceinline__ void lz_ld256_ro(const double *p, double &a, double &b, double &c, double &d)
 {

@@ -117,6 +117,7 @@ int lz_func_smem_optin(lz_ctx *ctx, const void *func, int bytes, bool carveout_m
 // ---- persistent state of a single-vector run (lz_vector.cu): begin once, advance in pieces, checkpoint, restart
 struct LzCgs {
     double *V; int64_t ts, cs; double *cpart; double *c; unsigned grid;      // basis element (i,k): V[(i>>5)*ts + k*cs + (i&31)]
+    int rpt;                     // rows per thread of the streaming CGS kernels (8, or 4 for small shards)
 };
 struct LzVecRun {
     const lz_matrix *A;

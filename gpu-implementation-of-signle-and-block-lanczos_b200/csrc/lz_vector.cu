@@ -140,70 +140,80 @@ static int launch_pass_b(lz_ctx *ctx, int64_t n, double *w, const double *u_cur,
 // Both stream V exactly once with 256-bit loads; each thread keeps 8 rows of w in registers and
 // walks the K columns, so w itself is read once per sweep.
 // ---------------------------------------------------------------------------------------------
-#define CGS_TILE (VT * V_ROWS_PER_THREAD)   // rows per CTA trip
+#define CGS_TILE (VT * V_ROWS_PER_THREAD)   // rows per CTA trip (8 rows per thread)
 #define CGS_UNROLL 4
+// Work granularity: a CTA takes whole tiles round-robin, so with T tiles on G CTAs the kernel lasts ceil(T / G) tile
+// times -- at 2 M rows per GPU (config 2 on 8 GPUs) that is 1024 tiles on 296 CTAs = 4 rounds for 3.46 rounds of work,
+// the 15 % that capped the round-1 scaling at 8 GPUs.  RPT = 4 (one 256-bit load per column and thread, twice the
+// column unroll to keep the same bytes in flight) halves the tile when there are fewer than ~8 tiles per CTA.
+template <int RPT> struct CgsShape { static constexpr int HALVES = RPT / 4, UNROLL = RPT == 8 ? 4 : 6, TILE = VT * RPT; };
 
+template <int RPT>
 __global__ void __launch_bounds__(VT)
 k_cgs_project(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t cs, const double *__restrict__ w,
               double *__restrict__ cpart /* gridDim.x * K */, const int *__restrict__ flags, int need_flag)
 {
+    constexpr int H = CgsShape<RPT>::HALVES, U = CgsShape<RPT>::UNROLL, TILE = CgsShape<RPT>::TILE;
     extern __shared__ double csm[];           // [VT/32][K] per-warp partial coefficients
     if (need_flag && flags[F_SECOND_SWEEP] == 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *mine = csm + (size_t)warp * K;
     for (int k = lane; k < K; k += 32) mine[k] = 0.0;
     __syncwarp();
-    const int64_t n_tiles = (n + CGS_TILE - 1) / CGS_TILE;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t base = tile * CGS_TILE + (int64_t)warp * (32 * V_ROWS_PER_THREAD) + lane * 4;
-        // rows base..base+3 and base+128..base+131 of this warp's 256-row slice
-        const int64_t ra = base, rb = base + 128;
-        // element (i, k) of the basis lives at V[(i >> 5) * ts + k * cs + (i & 31)]  (see lz_ctx_basis)
-        const double *pa = V + (ra >> 5) * ts + (ra & 31), *pb = V + (rb >> 5) * ts + (rb & 31);
-        double wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
-        const bool fa = ra + 3 < n, fb = rb + 3 < n;
-        if (fa) lz_ld256(w + ra, wa[0], wa[1], wa[2], wa[3]);
-        else for (int t = 0; t < 4; ++t) if (ra + t < n) wa[t] = w[ra + t];
-        if (fb) lz_ld256(w + rb, wb[0], wb[1], wb[2], wb[3]);
-        else for (int t = 0; t < 4; ++t) if (rb + t < n) wb[t] = w[rb + t];
+        const int64_t base = tile * TILE + (int64_t)warp * (32 * RPT) + lane * 4;
+        // rows base..base+3 (and base+128..base+131 when RPT = 8) of this warp's slice
+        int64_t r[H]; const double *p[H]; double wv[H][4]; bool full = true;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            r[h] = base + 128 * h;
+            // element (i, k) of the basis lives at V[(i >> 5) * ts + k * cs + (i & 31)]  (see lz_ctx_basis)
+            p[h] = V + (r[h] >> 5) * ts + (r[h] & 31);
+            const bool f = r[h] + 3 < n;
+            full = full && f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) wv[h][t] = 0.0;
+            if (f) lz_ld256(w + r[h], wv[h][0], wv[h][1], wv[h][2], wv[h][3]);
+            else for (int t = 0; t < 4; ++t) if (r[h] + t < n) wv[h][t] = w[r[h] + t];
+        }
         int k = 0;
-        if (fa && fb) {
-            for (; k + CGS_UNROLL <= K; k += CGS_UNROLL) {
-                double va[CGS_UNROLL][4], vb[CGS_UNROLL][4];
+        if (full) {
+            for (; k + U <= K; k += U) {
+                double v[U][H][4];
 #pragma unroll
-                for (int u = 0; u < CGS_UNROLL; ++u) {
-                    const int64_t ko = (int64_t)(k + u) * cs;
-                    lz_ld256_stream(pa + ko, va[u][0], va[u][1], va[u][2], va[u][3]);
-                    lz_ld256_stream(pb + ko, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
-                }
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int u = 0; u < CGS_UNROLL; ++u) {
-                    double s = va[u][0] * wa[0];
-                    s = fma(va[u][1], wa[1], s); s = fma(va[u][2], wa[2], s); s = fma(va[u][3], wa[3], s);
-                    s = fma(vb[u][0], wb[0], s); s = fma(vb[u][1], wb[1], s);
-                    s = fma(vb[u][2], wb[2], s); s = fma(vb[u][3], wb[3], s);
-                    s = lz_warp_sum(s);
-                    if (lane == 0) mine[k + u] += s;
+                    for (int h = 0; h < H; ++h) lz_ld256_stream(p[h] + (int64_t)(k + u) * cs, v[u][h][0], v[u][h][1], v[u][h][2], v[u][h][3]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double sacc = v[u][0][0] * wv[0][0];
+                    sacc = fma(v[u][0][1], wv[0][1], sacc); sacc = fma(v[u][0][2], wv[0][2], sacc); sacc = fma(v[u][0][3], wv[0][3], sacc);
+#pragma unroll
+                    for (int h = 1; h < H; ++h)
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) sacc = fma(v[u][h][t], wv[h][t], sacc);
+                    sacc = lz_warp_sum(sacc);
+                    if (lane == 0) mine[k + u] += sacc;
                 }
             }
         }
         for (; k < K; ++k) {
             const int64_t ko = (int64_t)k * cs;
-            double s = 0.0;
-            for (int t = 0; t < 4; ++t) {
-                if (ra + t < n) s = fma(pa[ko + t], wa[t], s);
-                if (rb + t < n) s = fma(pb[ko + t], wb[t], s);
-            }
-            s = lz_warp_sum(s);
-            if (lane == 0) mine[k] += s;
+            double sacc = 0.0;
+            for (int h = 0; h < H; ++h)
+                for (int t = 0; t < 4; ++t)
+                    if (r[h] + t < n) sacc = fma(p[h][ko + t], wv[h][t], sacc);
+            sacc = lz_warp_sum(sacc);
+            if (lane == 0) mine[k] += sacc;
         }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += VT) {
-        double s = 0.0;
+        double sacc = 0.0;
 #pragma unroll
-        for (int wv = 0; wv < VT / 32; ++wv) s += csm[(size_t)wv * K + k];
-        cpart[(size_t)blockIdx.x * K + k] = s;
+        for (int wv2 = 0; wv2 < VT / 32; ++wv2) sacc += csm[(size_t)wv2 * K + k];
+        cpart[(size_t)blockIdx.x * K + k] = sacc;
     }
 }
 
@@ -363,11 +373,13 @@ k_cgs_reduce(int K, int n_parts, const double *__restrict__ cpart, double *__res
     }
 }
 
-__global__ void __launch_bounds__(VT)
+template <int RPT>
+__global__ void __launch_bounds__(VT, 3)
 k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t cs, double *__restrict__ w,
              const double *__restrict__ c, double *partials, unsigned int *ticket, const LzFinal fin,
              int *flags, int need_flag, int dgks_test, const double *nrm2_before, int skip_share)
 {
+    constexpr int H = CgsShape<RPT>::HALVES, U = CgsShape<RPT>::UNROLL, TILE = CgsShape<RPT>::TILE;
     extern __shared__ double csm[];           // c[K]
     __shared__ double red[32];
     if (need_flag && flags[F_SECOND_SWEEP] == 0) {
@@ -384,50 +396,54 @@ k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc = 0.0;
-    const int64_t n_tiles = (n + CGS_TILE - 1) / CGS_TILE;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t base = tile * CGS_TILE + (int64_t)warp * (32 * V_ROWS_PER_THREAD) + lane * 4;
-        const int64_t ra = base, rb = base + 128;
-        // element (i, k) of the basis lives at V[(i >> 5) * ts + k * cs + (i & 31)]  (see lz_ctx_basis)
-        const double *pa = V + (ra >> 5) * ts + (ra & 31), *pb = V + (rb >> 5) * ts + (rb & 31);
-        double wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
-        const bool fa = ra + 3 < n, fb = rb + 3 < n;
-        if (fa) lz_ld256(w + ra, wa[0], wa[1], wa[2], wa[3]);
-        else for (int t = 0; t < 4; ++t) if (ra + t < n) wa[t] = w[ra + t];
-        if (fb) lz_ld256(w + rb, wb[0], wb[1], wb[2], wb[3]);
-        else for (int t = 0; t < 4; ++t) if (rb + t < n) wb[t] = w[rb + t];
+        const int64_t base = tile * TILE + (int64_t)warp * (32 * RPT) + lane * 4;
+        int64_t r[H]; const double *p[H]; double wv[H][4]; bool fl[H]; bool full = true;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            r[h] = base + 128 * h;
+            // element (i, k) of the basis lives at V[(i >> 5) * ts + k * cs + (i & 31)]  (see lz_ctx_basis)
+            p[h] = V + (r[h] >> 5) * ts + (r[h] & 31);
+            fl[h] = r[h] + 3 < n;
+            full = full && fl[h];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) wv[h][t] = 0.0;
+            if (fl[h]) lz_ld256(w + r[h], wv[h][0], wv[h][1], wv[h][2], wv[h][3]);
+            else for (int t = 0; t < 4; ++t) if (r[h] + t < n) wv[h][t] = w[r[h] + t];
+        }
         int k = 0;
-        if (fa && fb) {
-            for (; k + CGS_UNROLL <= K; k += CGS_UNROLL) {
-                double va[CGS_UNROLL][4], vb[CGS_UNROLL][4];
+        if (full) {
+            for (; k + U <= K; k += U) {
+                double v[U][H][4];
 #pragma unroll
-                for (int u = 0; u < CGS_UNROLL; ++u) {
-                    const int64_t ko = (int64_t)(k + u) * cs;
-                    lz_ld256_stream(pa + ko, va[u][0], va[u][1], va[u][2], va[u][3]);
-                    lz_ld256_stream(pb + ko, vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
-                }
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int u = 0; u < CGS_UNROLL; ++u) {
+                    for (int h = 0; h < H; ++h) lz_ld256_stream(p[h] + (int64_t)(k + u) * cs, v[u][h][0], v[u][h][1], v[u][h][2], v[u][h][3]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
                     const double ck = -csm[k + u];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) { wa[t] = fma(ck, va[u][t], wa[t]); wb[t] = fma(ck, vb[u][t], wb[t]); }
+                    for (int h = 0; h < H; ++h)
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) wv[h][t] = fma(ck, v[u][h][t], wv[h][t]);
                 }
             }
         }
         for (; k < K; ++k) {
             const int64_t ko = (int64_t)k * cs;
             const double ck = -csm[k];
-            for (int t = 0; t < 4; ++t) {
-                if (ra + t < n) wa[t] = fma(ck, pa[ko + t], wa[t]);
-                if (rb + t < n) wb[t] = fma(ck, pb[ko + t], wb[t]);
-            }
+            for (int h = 0; h < H; ++h)
+                for (int t = 0; t < 4; ++t)
+                    if (r[h] + t < n) wv[h][t] = fma(ck, p[h][ko + t], wv[h][t]);
         }
-        if (fa) lz_st256(w + ra, wa[0], wa[1], wa[2], wa[3]);
-        else for (int t = 0; t < 4; ++t) if (ra + t < n) w[ra + t] = wa[t];
-        if (fb) lz_st256(w + rb, wb[0], wb[1], wb[2], wb[3]);
-        else for (int t = 0; t < 4; ++t) if (rb + t < n) w[rb + t] = wb[t];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { acc = fma(wa[t], wa[t], acc); acc = fma(wb[t], wb[t], acc); }
+        for (int h = 0; h < H; ++h) {
+            if (fl[h]) lz_st256(w + r[h], wv[h][0], wv[h][1], wv[h][2], wv[h][3]);
+            else for (int t = 0; t < 4; ++t) if (r[h] + t < n) w[r[h] + t] = wv[h][t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc = fma(wv[h][t], wv[h][t], acc);
+        }
     }
     acc = lz_block_sum<VT>(acc, red);
     double total;
@@ -477,18 +493,43 @@ static int finish_norm(lz_ctx *ctx, const LzFinal &f, bool sharded, bool want_no
     return lz_comm_allreduce_sum(ctx, f.nrm2_out, 1, &e);
 }
 
+// rows per thread of the streaming CGS kernels: 8, or 4 when that leaves fewer than ~8 tiles per CTA (see CgsShape)
+static inline int cgs_rows_per_thread(int64_t n, unsigned max_grid)
+{
+    const int64_t tiles8 = (n + VT * 8 - 1) / (VT * 8);
+    return tiles8 < (int64_t)max_grid * 8 ? 4 : 8;
+}
+
+static int launch_cgs_project(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, const double *w, int need_flag)
+{
+    const size_t smem = sizeof(double) * (VT / 32) * (size_t)K;
+    lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
+    if (g.rpt == 8) k_cgs_project<8><<<g.grid, VT, smem, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, need_flag);
+    else k_cgs_project<4><<<g.grid, VT, smem, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, need_flag);
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    return LZ_OK;
+}
+
 static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin, int need_flag, int dgks_test,
                              bool sharded, bool want_norm)
 {
     // (a variant that gave each warp one tile and four adjacent columns per load -- fully contiguous 1 KB
     // reads of the tiled slab -- measured 4 % slower than this generic kernel: profiles/r01_cgs_fusion.md)
     const int mult = ctx->knobs.cgs_upd_mult;      // default 3 CTAs/SM: 5.9 -> 6.6 TB/s on the row-tiled basis
-    const unsigned want = stream_grid(ctx, n, CGS_TILE), cap = (unsigned)(ctx->sm_count * mult);
+    const unsigned cap = (unsigned)(ctx->sm_count * mult);
+    const int rpt = cgs_rows_per_thread(n, cap);
+    const unsigned want = stream_grid(ctx, n, VT * rpt);
+    const unsigned grid = want < cap ? want : cap;
     const LzFinal f = arm_final(ctx, fin, sharded, want_norm);
+    const int share = (sharded && want_norm && !f.pd) ? (lz_comm_rank(ctx) == 0 ? 1 : 0) : -1;
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
-    k_cgs_update<<<want < cap ? want : cap, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
-        n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, f, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE,
-        (sharded && want_norm && !f.pd) ? (lz_comm_rank(ctx) == 0 ? 1 : 0) : -1);
+    if (rpt == 8)
+        k_cgs_update<8><<<grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
+            n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, f, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE, share);
+    else
+        k_cgs_update<4><<<grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
+            n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, f, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE, share);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     return finish_norm(ctx, f, sharded, want_norm);
@@ -511,11 +552,7 @@ static int cgs_reduce(lz_ctx *ctx, const LzCgs &g, int K, int n_parts, int need_
 static int cgs_sweep(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, const LzFinal &fin,
                      int need_flag, int dgks_test, bool sharded, bool want_norm, double *alpha_out)
 {
-    const size_t smem_p = sizeof(double) * (VT / 32) * (size_t)K;
-    lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
-    k_cgs_project<<<g.grid, VT, smem_p, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, need_flag);
-    LZ_LAUNCH_CHECK(ctx);
-    lz_prof_end(ctx);
+    LZ_TRY(launch_cgs_project(ctx, g, n, K, w, need_flag));
     LZ_TRY(cgs_reduce(ctx, g, K, (int)g.grid, need_flag, sharded, alpha_out));
     return launch_cgs_update(ctx, g, n, K, w, fin, need_flag, dgks_test, sharded, want_norm);
 }
@@ -535,10 +572,7 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
     }
     LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_cgs_update_project, 220 * 1024, true));
     // sweep 1 projection
-    lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * (K + 1));
-    k_cgs_project<<<g.grid, VT, sizeof(double) * (VT / 32) * (size_t)K, ctx->stream>>>(n, K, g.V, g.ts, g.cs, w, g.cpart, ctx->flags, 0);
-    LZ_LAUNCH_CHECK(ctx);
-    lz_prof_end(ctx);
+    LZ_TRY(launch_cgs_project(ctx, g, n, K, w, 0));
     LZ_TRY(cgs_reduce(ctx, g, K, (int)g.grid, 0, sharded, alpha_out));
     // sweep 1 update + sweep 2 projection, one basis stream
     const unsigned fgrid = (unsigned)(ctx->sm_count * ctas);
@@ -675,9 +709,10 @@ int lz_vec_setup(lz_ctx *ctx, const lz_matrix *A, int m, int64_t lc, int reorth,
         n_below = rank > 0 ? all[4 * (rank - 1) + 1] : 0;
     }
     const int64_t stride = round_up(span, 4);
-    LzCgs g = {nullptr, 0, 0, nullptr, nullptr, 0};
-    const unsigned cgs_grid = stream_grid(ctx, n, CGS_TILE) < (unsigned)(ctx->sm_count * 2)
-                                  ? stream_grid(ctx, n, CGS_TILE) : (unsigned)(ctx->sm_count * 2);
+    LzCgs g = {nullptr, 0, 0, nullptr, nullptr, 0, 8};
+    const int cgs_rpt = cgs_rows_per_thread(n, (unsigned)(ctx->sm_count * 2));
+    const unsigned cgs_grid = stream_grid(ctx, n, VT * cgs_rpt) < (unsigned)(ctx->sm_count * 2)
+                                  ? stream_grid(ctx, n, VT * cgs_rpt) : (unsigned)(ctx->sm_count * 2);
     size_t work_bytes = sizeof(double) * (size_t)stride * 3;
     // projection partials: one row of m per CTA; the fused kernel writes S * K <= CF_THREADS entries per CTA
     const size_t cpart_len = std::max((size_t)ctx->sm_count * 2 * m, (size_t)ctx->sm_count * 4 * CF_THREADS);
@@ -691,9 +726,11 @@ int lz_vec_setup(lz_ctx *ctx, const lz_matrix *A, int m, int64_t lc, int reorth,
         g.cpart = (double *)work + 3 * stride;
         g.c = g.cpart + cpart_len;
         g.grid = cgs_grid;
+        g.rpt = cgs_rpt;
         LZ_TRY(lz_ctx_basis(ctx, n, m, &g.V));
         g.ts = ctx->basis_ts; g.cs = ctx->basis_cs;
-        LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_cgs_project, 200 * 1024));
+        LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_cgs_project<8>, 200 * 1024));
+        LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_cgs_project<4>, 200 * 1024));
     }
     if (!ctx->vrun) ctx->vrun = new LzVecRun();
     LzVecRun &R = *ctx->vrun;

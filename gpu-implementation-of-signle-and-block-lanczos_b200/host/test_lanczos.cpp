@@ -4,7 +4,7 @@
 // Plain C++ linked against liblanczos_b200.so; N_COL and USE_BLAS keep their compile-time meaning,
 // and the new options are real run-time flags:
 //   -N <grid points per dim>   -m <iterations>            (reference flags, :338-345)
-//   --matrix maxwell|lap2d|lap3d|mtx (--file <MatrixMarket file>)   --block <b>|--vector   --reorth none|full|dgks   --k <ritz pairs>
+//   --matrix maxwell|maxwell_dev|lap2d|lap3d|mtx (--file <MatrixMarket file>)   --block <b>|--vector   --reorth none|full|dgks|selective   --k <ritz pairs>
 //   --fdtd <steps> (run the fdtd validator and print the relative error, test_lanczos.cu:115-121, :287-299)   -T <T_end>
 //   --format ell|csr   --dump <file>  (alpha/beta/q in the parity tests' record format, for the parity tests)
 #ifndef N_COL
@@ -243,6 +243,12 @@ void test_Lanczos(const Options &o, unsigned int lc)
     DeviceOperator<type_t> A;
     if (o.matrix == "lap2d") { AssertCuda(lz_gen_laplacian2d(lanczos_context(), o.N, o.N, &A.op)); A.rows = (std::size_t)o.N * o.N; }
     else if (o.matrix == "lap3d") { AssertCuda(lz_gen_laplacian3d(lanczos_context(), o.N, o.N, o.N, &A.op)); A.rows = (std::size_t)o.N * o.N * o.N; }
+    else if (o.matrix == "maxwell_dev") {      // the reference's operator A = D*W assembled on the device (bit-identical to Matrix_A + mult_diagonal)
+        AssertCuda(lz_gen_maxwell(lanczos_context(), (int)o.N, (int)o.N, (int)o.N, &A.op));
+        int64_t nr = 0;
+        AssertCuda(lz_matrix_info(A.op, &nr, nullptr, nullptr));
+        A.rows = (std::size_t)nr;
+    }
     else { std::cout << "unknown --matrix " << o.matrix << std::endl; std::abort(); }
     std::cout << " the size of the problem is " << std::endl;
     print(A.rows);
@@ -283,7 +289,7 @@ int main(int argc, char **argv)
         else if (opt == "--dump") o.dump = next();
         else if (opt == "--reorth") {
             const std::string r = next();
-            lzb::reorth_mode() = r == "full" ? LZ_REORTH_FULL : r == "dgks" ? LZ_REORTH_FULL_DGKS : LZ_REORTH_NONE;
+            lzb::reorth_mode() = r == "full" ? LZ_REORTH_FULL : r == "dgks" ? LZ_REORTH_FULL_DGKS : r == "selective" ? LZ_REORTH_SELECTIVE : LZ_REORTH_NONE;
         } else if (opt == "-blas") next();                               // advertised by the reference, ignored there too
         else { std::cout << "Error, unknown option " << opt << std::endl; std::abort(); }
     }

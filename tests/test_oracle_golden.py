@@ -1,6 +1,7 @@
 """CPU suite: the oracle against the golden vectors minted from the reference's own Host code,
 and the generators against independent scipy constructions."""
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 from conftest import load_gold
@@ -134,3 +135,16 @@ def test_oracle_matches_reference_cuda_run(orc, maxwell10):
         nb = 10 * nc * nc
         assert np.max(np.abs(r["alpha"][:nb] - g["alpha"][:nb])) < 1e-10 * np.abs(g["alpha"]).max()
         assert np.max(np.abs(r["beta"][:nb] - g["beta"][:nb])) < 1e-10 * np.abs(g["beta"][:nb]).max()
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 10])
+def test_maxwell_closed_form_matches_reference_builder(orc, N):
+    """The per-row closed form that csrc/lz_maxwell.cu evaluates on the device (numpy restatement in oracle/orc.py)
+    against the arrays minted from the reference's own host builder: D, its column ids, W and A = D W, exactly."""
+    g = load_gold("maxwell_N%d_matrix.npz" % N)
+    n = int(g["n_rows"])
+    Dv, Dc, Wv, Av = orc.maxwell_closed_form(N)
+    assert Dv.shape == (n, 4) and n == 3 * N * (N + 1) * (2 * N + 1)
+    assert np.array_equal(Dv, g["D_data"].reshape(4, n).T) and np.array_equal(Dc, g["D_idx"].reshape(4, n).T)
+    assert np.array_equal(Wv, g["W_data"])
+    assert np.array_equal(Av, g["ell_data"].reshape(4, n).T) and np.array_equal(Dc, g["ell_idx"].reshape(4, n).T)
