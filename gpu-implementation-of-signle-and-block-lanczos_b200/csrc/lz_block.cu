@@ -208,8 +208,11 @@ __global__ void __launch_bounds__((1 + CW) * 32, MINB)
 k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
           const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
           const double *__restrict__ X, double *__restrict__ W, const double *__restrict__ Q0, const double *__restrict__ Bm,
-          const LzChunkRange cr, const int run, const int hint)
+          const LzChunkRange cr, const int run, const int hint, const int64_t ldx, const int64_t ldw)
 {
+    // ldx / ldw: doubles between consecutive rows of X / W (= BW for a whole panel; a BW-column slice of a wider
+    // row-major panel otherwise: power-law operators run wide panels slice by slice so that the rows gathered again
+    // and again -- the hubs' -- fit in L2)
     static_assert(!FSUB || BW == 16, "the fused subtraction is written for 16-column panels");
     constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -334,8 +337,8 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                     for (int g = 0; g < G; ++g) {
                         x0[g] = x1[g] = x2[g] = x3[g] = 0.0;
                         if (cc[g] >= 0) {
-                            if (hint & 8) lz_ld256_ro_pol(Xl + (int64_t)cc[g] * BW, x0[g], x1[g], x2[g], x3[g], pol_last);
-                            else lz_ld256_ro(Xl + (int64_t)cc[g] * BW, x0[g], x1[g], x2[g], x3[g]);
+                            if (hint & 8) lz_ld256_ro_pol(Xl + (int64_t)cc[g] * ldx, x0[g], x1[g], x2[g], x3[g], pol_last);
+                            else lz_ld256_ro(Xl + (int64_t)cc[g] * ldx, x0[g], x1[g], x2[g], x3[g]);
                         }
                     }
 #pragma unroll
@@ -353,8 +356,8 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                     lz_dmma(acc0, acc1, q3, sbs[(3 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q3, sbs[(3 * 2 + 1) * 32 + lane]);
                 }
                 if (valid) {
-                    if (hint & 2) lz_st256_pol(W + r * BW + 4 * l, acc0, acc1, acc2, acc3, pol_first);
-                    else lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                    if (hint & 2) lz_st256_pol(W + r * ldw + 4 * l, acc0, acc1, acc2, acc3, pol_first);
+                    else lz_st256(W + r * ldw + 4 * l, acc0, acc1, acc2, acc3);
                 }
             }
             __syncwarp();
@@ -365,7 +368,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
 
 template <int BW, int CW, int STAGES, int MINB, bool FSUB>
 static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W,
-                                const double *Q0, const double *Bm, int run, int part)
+                                const double *Q0, const double *Bm, int run, int part, int64_t ldx = BW, int64_t ldw = BW)
 {
     constexpr int CAP = 2048;
     const size_t smem = (size_t)STAGES * (CAP * 12 + SPMM_WS_RCAP * 4) + 16 * STAGES;
@@ -380,7 +383,7 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
     const int per_cta = (cr.total + grid - 1) / grid;
     k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
         nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
-        ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : (FSUB ? LZ_SPMM_HINT_FUSED : 0));
+        ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : (FSUB ? LZ_SPMM_HINT_FUSED : 0), ldx, ldw);
     return LZ_OK;
 }
 
@@ -600,6 +603,20 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
     LZ_CHECK(Q0 == nullptr, LZ_ERR_UNSUPPORTED, "fused subtraction is not available on a row-split operator");
     void *wbar;
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)A->n_virtual * bw + 64, &wbar));
+    // Power-law operator, wide panel: the gathered rows are random, and what decides the time is how many of them
+    // are still in L2.  Eight columns at a time (64-byte row slices) four times as many hub rows stay resident, at
+    // the price of streaming the matrix once per slice (R-MAT scale 24, b = 32: profiles/r02_rmat.md).
+    const int slice = ctx->knobs.spmm_slice > 0 ? ctx->knobs.spmm_slice : 8;
+    if (bw > slice && bw % slice == 0 && slice == 8 && A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 &&
+        ((uintptr_t)X % 32 == 0) && ((uintptr_t)wbar % 32 == 0)) {
+        lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 4.0 * (double)A->n_virtual + 16.0 * (double)A->n_virtual * bw);
+        for (int c0 = 0; c0 < bw; c0 += slice) {
+            LZ_TRY((launch_spmm_ws_shape<8, 12, 2, 2, false>(ctx, A, A->vrowptr, A->n_virtual, X + c0, (double *)wbar + c0, nullptr, nullptr,
+                                                             ctx->knobs.spmm_run, 0, bw, bw)));
+            LZ_LAUNCH_CHECK(ctx);
+        }
+        lz_prof_end(ctx);
+    } else
     LZ_TRY(spmm_rm_rows(ctx, A, A->vrowptr, A->n_virtual, bw, X, (double *)wbar, nullptr, nullptr));
     k_split_combine_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A->n_rows, bw, A->vstart, A->vpos, (const double *)wbar, W);
     LZ_LAUNCH_CHECK(ctx);

@@ -73,6 +73,8 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     k.block_cgs_fuse = env_int("LZ_BLOCK_CGS_FUSE", 1);
     k.rmat_reorder = env_int("LZ_REORDER", 1);
     k.panel_pad = env_int("LZ_PANEL_PAD", 0);
+    k.spmm_slice = env_int("LZ_SPMM_SLICE", 0);
+    k.cgs_fuse_min_k = env_int("LZ_CGS_FUSE_MIN_K", 64);
     k.no_spmm_fuse = env_set("LZ_NO_SPMM_FUSE");
     *out = c;
     return LZ_OK;

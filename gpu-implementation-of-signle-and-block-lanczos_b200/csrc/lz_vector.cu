@@ -565,7 +565,9 @@ static int cgs2_fused(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, double *w, 
     int ctas = 1, NB = 2;
     if (!ctx->knobs.cgs_one_cta) cgs_fused_shape(K, ctx->knobs.cgs_shape_order, &ctas, &NB);
     const size_t smem = cgs_fused_smem(K, NB);
-    const bool ok = smem <= 220 * 1024 && K <= CF_MAXC * CF_THREADS && g.cs == CF_R && ((uintptr_t)w % 16 == 0) && !ctx->knobs.no_cgs_fuse;
+    const bool ok = smem <= 220 * 1024 && K <= CF_MAXC * CF_THREADS && g.cs == CF_R && ((uintptr_t)w % 16 == 0) && !ctx->knobs.no_cgs_fuse &&
+                    K >= ctx->knobs.cgs_fuse_min_k;     // below ~64 columns the fused kernel sits on its per-tile floor (0.79 us per 32 rows,
+                                                        // profiles/r01_cgs_fusion.md) and two plain sweeps stream less time than it takes
     if (!ok) {
         LZ_TRY(cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded, false, alpha_out));
         return cgs_sweep(ctx, g, n, K, w, fin, 0, 0, sharded, true, nullptr);

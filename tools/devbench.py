@@ -62,6 +62,29 @@ def main():
             out["lap3d_256_block%d" % bw] = dict(ms_per_iter=ms / m, it_per_s=m / ms * 1e3, gbs=byt / (ms / m) / 1e6, frac=byt / (ms / m) / 1e6 / PEAK,
                                                  classes={k: dict(n=v[0], ms=round(v[1] / 2 / m, 4), gbs=round(v[2] / max(v[1], 1e-9) / 1e6, 1)) for k, v in prof.items() if v[0]})
             A.close(); del B
+    if "maxwell" in which:
+        # the reference's own operator (Maxwell N = 160, ELL4 + CSR shadow), warm: block b = 4, 8, 16 and the vector path
+        A = lz.Matrix.maxwell(ctx, 160); n = A.n_rows
+        for bw in (4, 8, 16):
+            m = 8
+            B = torch.empty(n * bw, dtype=torch.float64, device="cuda")
+            lz.check(lz.lib().lz_gen_start_block(ctx.h, n, bw, n, 0x5EED, B.data_ptr()))
+            al = torch.zeros(m * bw * bw, dtype=torch.float64, device="cuda"); be = torch.zeros((m + 1) * bw * bw, dtype=torch.float64, device="cuda")
+            run = lambda: lz.block_lanczos(ctx, A, B, n, bw, m, al, be, None, lc=-1)
+            run(); ctx.sync()
+            ctx.profile(True)
+            ms = timeit(run, reps=2, warm=0)
+            prof = ctx.profile_read(); ctx.profile(False)
+            out["maxwell160_block%d" % bw] = dict(ms_per_iter=ms / m, it_per_s=m / ms * 1e3,
+                                                 classes={k: dict(n=v[0], ms=round(v[1] / 2 / m, 4), gbs=round(v[2] / max(v[1], 1e-9) / 1e6, 1)) for k, v in prof.items() if v[0]})
+            del B
+        x = torch.empty(n, dtype=torch.float64, device="cuda")
+        lz.check(lz.lib().lz_gen_start_vector(ctx.h, n, 0x5EED, x.data_ptr()))
+        m = 50
+        al = torch.empty(m, dtype=torch.float64, device="cuda"); be = torch.empty_like(al)
+        ms = timeit(lambda: lz.vector_lanczos_async(ctx, A, x, m, al, be), reps=3, warm=1) / m
+        out["maxwell160_vector"] = dict(ms_per_iter=ms, it_per_s=1e3 / ms)
+        A.close()
     if "spmmcm" in which:
         # the drop-in lz_spmm (column-major, reference layout) on 256^3, b = 16
         A = lz.Matrix.laplacian3d(ctx, 256, 256, 256); n, nnz = A.n_rows, A.nnz
