@@ -63,6 +63,7 @@ struct LzKnobs {
     int cgs_fuse_min_k;     // LZ_CGS_FUSE_MIN_K: smallest number of basis columns for which CGS2 uses the fused update+project kernel
     int spmm_slice;         // LZ_SPMM_SLICE: columns per pass of the SpMM on row-split (power-law) operators (default 8; >= b: one pass)
     int panel_pad;          // LZ_PANEL_PAD: extra doubles between the block driver's panels (they are 2^k bytes apart on 2^k grids)
+    int no_spmm_gram;       // LZ_NO_SPMM_GRAM: the fused b = 16 SpMM leaves Q_j^T W to a separate Gram pass
     int no_spmm_fuse;       // LZ_NO_SPMM_FUSE: b = 16 runs the plain staged SpMM + two-Gram formulation instead of the fused subtraction
     int rmat_reorder;       // LZ_REORDER: locality reordering at lz_csr_create time for power-law operators
 };

@@ -76,6 +76,7 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     k.spmm_slice = env_int("LZ_SPMM_SLICE", 0);
     k.cgs_fuse_min_k = env_int("LZ_CGS_FUSE_MIN_K", 64);
     k.no_spmm_fuse = env_set("LZ_NO_SPMM_FUSE");
+    k.no_spmm_gram = env_set("LZ_NO_SPMM_GRAM");
     *out = c;
     return LZ_OK;
 }

@@ -985,6 +985,17 @@ int lz_vector_lanczos_begin(lz_ctx *ctx, const lz_matrix *A, const double *b, in
     return lz_vec_start(ctx, b);
 }
 
+// everything lz_vector_lanczos would allocate on its first call (work vectors, basis slab, scratch), ahead of a timed call
+int lz_vector_lanczos_workspace(lz_ctx *ctx, const lz_matrix *A, int m, int reorth)
+{
+    LZ_CHECK(ctx && A && m >= 1, LZ_ERR_INVALID, "lz_vector_lanczos_workspace: bad arguments");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    LZ_TRY(lz_vec_setup(ctx, A, m, -1, reorth, nullptr));
+    if (A->vrowptr) { void *p; LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * ((size_t)A->n_virtual + 64), &p)); }
+    ctx->vrun->A = nullptr;       // sizes only: no run has begun
+    return LZ_OK;
+}
+
 int lz_vector_lanczos_advance(lz_ctx *ctx, int steps, double *alpha_host, double *beta_host, int *steps_done)
 {
     LZ_CHECK(ctx && ctx->vrun && ctx->vrun->A, LZ_ERR_INVALID, "lz_vector_lanczos_advance: no run has been begun on this context");

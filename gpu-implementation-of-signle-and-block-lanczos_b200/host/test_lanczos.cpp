@@ -62,6 +62,8 @@ void run_vector(Matrix &A, Vector<type_t> &b, const Options &o, unsigned int lc)
     std::vector<type_t> alpha(m), beta(m);
     cublasHandle_t cublasH;
     CUBLAS_CHECK(cublasCreate(&cublasH));
+    // every buffer exists before the clock starts (the reference preallocates q0, q1, w the same way, :56-63)
+    AssertCuda(lz_vector_lanczos_workspace(lanczos_context(), A.device_operator(), (int)m, lzb::reorth_mode()));
     cudaDeviceSynchronize_();
     time.start();
 #ifdef USE_BLAS
@@ -132,6 +134,9 @@ void run_block(Matrix &A, Dense_matrix<type_t> &B, const Options &o, unsigned in
     cusolver_args<type_t> args = cusolver_args<type_t>();
     Vector<type_t> eigen_val(bw, mem_cuda);
     initiate_cusolver(args, beta[0], eigen_val);
+    // every buffer exists before the clock starts (the reference preallocates Q0, Q1, W and the cusolver workspace, :203-233)
+    AssertCuda(lz_block_lanczos_workspace(lanczos_context(), A.device_operator(), (int)bw, (int)m,
+                                          lzb::reorth_mode() == LZ_REORTH_NONE ? LZ_REORTH_NONE : LZ_REORTH_FULL));
     cudaDeviceSynchronize_();
     time.start();
 #ifdef USE_BLAS

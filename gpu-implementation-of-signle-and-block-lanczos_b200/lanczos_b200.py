@@ -75,6 +75,8 @@ def lib():
         "lz_assemble_T": (i32, [vp, i32, i32, vp, vp, vp]),
         "lz_vector_lanczos": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp, P(i32)]),
         "lz_vector_lanczos_async": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp]),
+        "lz_vector_lanczos_workspace": (i32, [vp, vp, i32, i32]),
+        "lz_block_lanczos_workspace": (i32, [vp, vp, i32, i32, i32]),
         "lz_vector_lanczos_begin": (i32, [vp, vp, vp, i32, i64, i32, vp]),
         "lz_vector_lanczos_advance": (i32, [vp, i32, vp, vp, P(i32)]),
         "lz_vector_checkpoint_save": (i32, [vp, C.c_char_p]),

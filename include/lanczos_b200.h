@@ -170,6 +170,11 @@ int lz_vector_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, i
 /* same, but coefficients stay in DEVICE arrays and nothing synchronises (bench / graph use) */
 int lz_vector_lanczos_async(lz_ctx *ctx, const lz_matrix *A, const double *b, int m, int64_t lc,
                             int reorth, double *alpha_dev, double *beta_dev, double *q);
+/* Pre-size what the drivers would allocate on their first call for this operator and these sizes (work vectors / panels,
+ * basis slab, reduction scratch), so that a timed first call -- the reference harness times exactly one cold call,
+ * test_lanczos.cu:74-91 -- measures the iteration and not cudaMalloc.  Optional; unsharded contexts. */
+int lz_vector_lanczos_workspace(lz_ctx *ctx, const lz_matrix *A, int m, int reorth);
+int lz_block_lanczos_workspace(lz_ctx *ctx, const lz_matrix *A, int bw, int m, int reorth);
 /* The same run in pieces (extension).  begin: sets up a run of at most m_capacity steps (work vectors,
  * basis slab for the reorthogonalising modes, beta_0 = ||b||).  advance: `steps` more Lanczos steps, then ALL
  * coefficients so far to the host (alpha_host / beta_host: m_capacity entries, or NULL) and the number of valid steps

@@ -67,9 +67,10 @@ def test_dgks_mode_matches_cgs2_oracle(lz, ctx, orc, problem):
     A.close()
 
 
-@pytest.mark.parametrize("env", [{}, {"LZ_SPMV_VARIANT": "9"}])
+@pytest.mark.parametrize("env", [{}, {"LZ_NO_SPMM_GRAM": "1"}, {"LZ_NO_SPMM_FUSE": "1"}, {"LZ_SPMV_VARIANT": "9"}])
 def test_block_paths_agree_with_oracle(lz, orc, monkeypatch, env):
-    """b = 16 with the staged SpMM + fused DMMA subtraction (default) and with the LDG SpMM + two-Gram formulation."""
+    """b = 16: the staged SpMM with the fused DMMA subtraction and Gram epilogue (default), the same with a separate
+    Gram pass, the plain staged SpMM + two-Gram formulation, and the LDG SpMM + two-Gram formulation."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     for k, v in env.items():
