@@ -660,10 +660,11 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
     LZ_CHECK(Q0 == nullptr, LZ_ERR_UNSUPPORTED, "fused subtraction is not available on a row-split operator");
     void *wbar;
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)A->n_virtual * bw + 64, &wbar));
-    // Power-law operator, wide panel: the gathered rows are random, and what decides the time is how many of them
-    // are still in L2.  Eight columns at a time (64-byte row slices) four times as many hub rows stay resident, at
-    // the price of streaming the matrix once per slice (R-MAT scale 24, b = 32: profiles/r02_rmat.md).
-    const int slice = ctx->knobs.spmm_slice > 0 ? ctx->knobs.spmm_slice : 8;
+    // Power-law operator, wide panel: the gathered rows are random.  Running the panel in 8-column slices (64-byte row
+    // pieces, four times as many hub rows resident in L2, the matrix streamed once per slice) was measured: every slice
+    // costs as much as the whole 32-column pass (R-MAT scale 24: 4 x 54 ms instead of 55 ms, profiles/r02_rmat.md) -- the
+    // product is bound by the RATE of random row gathers (~10 G/s), not by their bytes.  Off unless LZ_SPMM_SLICE=8.
+    const int slice = ctx->knobs.spmm_slice > 0 ? ctx->knobs.spmm_slice : bw;
     if (bw > slice && bw % slice == 0 && slice == 8 && A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 &&
         ((uintptr_t)X % 32 == 0) && ((uintptr_t)wbar % 32 == 0)) {
         lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 4.0 * (double)A->n_virtual + 16.0 * (double)A->n_virtual * bw);
