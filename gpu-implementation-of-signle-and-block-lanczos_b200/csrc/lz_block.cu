@@ -9,8 +9,13 @@
 // column-major layout; the driver converts once on the way in.
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "lz_dense_host.cuh"
 #include "lz_spmv.cuh"
+
+int lz_sym_eig_full_c(int N, double *A, std::vector<double> &d, std::vector<double> &Zt);   // lz_ritz.cu
 
 #define SPMM_THREADS 256
 #define SPMM_U 2            // independent rows per lane group in flight
@@ -937,6 +942,200 @@ int lz_last_coupling(lz_ctx *ctx, int bw, double *beta_last_host)
     const double *src = ctx->scalars + ctx->last_coupling_slot;
     LZ_CUDA(cudaMemcpyAsync(beta_last_host, src, sizeof(double) * bw * bw, cudaMemcpyDeviceToHost, ctx->stream));
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+// row-major (bw) -> column-major (ld), `cols` leading columns only
+__global__ void __launch_bounds__(256) k_rm_to_cm(int64_t n, int bw, int cols, const double *__restrict__ src, double *__restrict__ dst, int64_t ld)
+{
+    __shared__ double t[32][33];
+    const int64_t base = (int64_t)blockIdx.x * 32;
+    for (int e = threadIdx.x; e < 32 * bw; e += 256) {
+        const int r = e / bw, c = e % bw;
+        t[r][c] = (base + r < n) ? src[(base + r) * bw + c] : 0.0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * cols; e += 256) {
+        const int r = e % 32, c = e / 32;
+        if (base + r < n) dst[base + r + (int64_t)c * ld] = t[r][c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block thick-restart Lanczos (BASELINE config 3: block size 16, k = 64): k extremal eigenpairs with
+// a basis of p blocks.  Degenerate / clustered eigenvalues -- the cubic Laplacian has up to six-fold ones -- need a
+// block method: a single Lanczos vector sees one direction per eigenspace.  Every step is the block recurrence with
+// full block CGS2 against ALL stored blocks; after p blocks the projected matrix H (block tridiagonal plus, after a
+// restart, the coupling rows to the kept Ritz vectors) is diagonalised on the host, the basis is compressed to the
+// wanted Ritz vectors plus a share of their neighbours (a whole number of blocks) with DMMA block combinations, and
+// the normalised residual block continues the recurrence.  The reorthogonalisation removes the coupling to the kept
+// vectors, so the restarted step needs no special kernel; H's entries are known in closed form.
+// Unsharded operators, bw in {8, 16, 32}.
+// ---------------------------------------------------------------------------------------------
+int lz_block_eigs_thick_restart(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t ldb, int bw, int k, int which,
+                                int p_blocks, double tol, int max_restarts, double *theta_host, double *resid_host,
+                                double *X, int64_t ldx, int *info4)
+{
+    LZ_CHECK(ctx && A && B && theta_host && k >= 1 && which >= 0 && which <= 2 && tol > 0.0 && max_restarts >= 0, LZ_ERR_INVALID,
+             "lz_block_eigs_thick_restart: bad arguments");
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_block_eigs_thick_restart: the operator belongs to another (or a destroyed) context");
+    LZ_CHECK(bw == 8 || bw == 16 || bw == 32, LZ_ERR_UNSUPPORTED, "lz_block_eigs_thick_restart: block width %d (use 8, 16 or 32)", bw);
+    const int64_t n = A->n_rows;
+    LZ_CHECK(A->n_cols == n && A->halo_lo == 0 && A->halo_hi == 0 && !(ctx->comm && lz_comm_world(ctx) > 1), LZ_ERR_UNSUPPORTED,
+             "lz_block_eigs_thick_restart: unsharded square operators only");
+    const int p = p_blocks, N = p * bw;
+    const int kb = (k + bw - 1) / bw;                                   // blocks needed for the wanted pairs
+    LZ_CHECK(p >= kb + 3 && N <= 2048 && ldb >= n && (!X || ldx >= n), LZ_ERR_INVALID,
+             "lz_block_eigs_thick_restart: need p_blocks >= ceil(k / bw) + 3, p_blocks * bw <= 2048, ldb / ldx >= n");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    const size_t pan = (size_t)n * bw, bb = (size_t)bw * bw;
+    // basis: p blocks + p scratch blocks for the compressed basis (copied back to the front) ; one work panel W
+    double *V;
+    LZ_TRY(lz_ctx_basis_blocks(ctx, (int64_t)pan, 2 * p, &V));
+    void *work;
+    LZ_TRY(lz_ctx_workspace(ctx, sizeof(double) * (pan + 4 * bb * (size_t)(p + 2) + 64), &work));
+    double *W = (double *)work, *C = W + pan;                          // C: CGS coefficients / combination blocks (2 bb p)
+    double *dsm = C + 2 * bb * (size_t)(p + 1);                         // device b x b blocks: alpha, G / beta, beta^{-1}
+    double *d_alpha = dsm, *d_beta = dsm + bb, *d_binv = dsm + 2 * bb;
+    int *flag = ctx->flags + 2;
+    k_flag_init<<<1, 1, 0, ctx->stream>>>(ctx->flags);
+    LZ_LAUNCH_CHECK(ctx);
+    auto block_at = [&](int j) { return V + pan * (size_t)j; };
+    std::vector<double> H((size_t)N * N, 0.0), Hw, d, Zt, hb(bb), beta_p(bb);
+    auto put_block = [&](int bi, int bj, const double *blk /* col-major b x b */, bool transpose) {
+        for (int c = 0; c < bw; ++c)
+            for (int r = 0; r < bw; ++r)
+                H[(size_t)(bi * bw + r) + (size_t)(bj * bw + c) * N] = transpose ? blk[c + r * bw] : blk[r + c * bw];
+    };
+    // Q_0 = B (B^T B)^{-1/2}
+    k_cm_to_rm<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, bw, B, ldb, W);
+    LZ_LAUNCH_CHECK(ctx);
+    LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, d_beta, 0));
+    LZ_TRY(lz_sqrtm_launch(ctx, bw, d_beta, d_binv, flag, 0));
+    LZ_TRY(lz_panel(ctx, n, bw, true, W, 0, d_binv, 0.0, 1.0, block_at(0), 0, nullptr));
+    int j0 = 0, restarts = 0, matvecs = 0, nconv = 0;
+    std::vector<int> order(N), wanted, keep;
+    for (;;) {
+        for (int j = j0; j < p; ++j) {
+            double *Qj = block_at(j);
+            LZ_TRY(spmm_rm(ctx, A, bw, Qj, W, nullptr, nullptr));
+            LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Qj, 0, d_alpha, 1));
+            LZ_CUDA(cudaMemcpyAsync(hb.data(), d_alpha, sizeof(double) * bb, cudaMemcpyDeviceToHost, ctx->stream));
+            LZ_TRY(lz_panel(ctx, n, bw, true, Qj, 0, d_alpha, 1.0, -1.0, W, 0, nullptr));
+            // block CGS2 against every stored block: removes Q_{j-1} beta_j, the coupling to the kept Ritz vectors and
+            // whatever rounding left elsewhere
+            for (int sweep = 0; sweep < 2; ++sweep) LZ_TRY(lz_block_cgs(ctx, n, bw, j + 1, V, (int64_t)pan, W, C, false));
+            LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, d_beta, 0));
+            LZ_TRY(lz_sqrtm_launch(ctx, bw, d_beta, d_binv, flag, j + 1));
+            LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+            put_block(j, j, hb.data(), false);
+            LZ_CUDA(cudaMemcpy(hb.data(), d_beta, sizeof(double) * bb, cudaMemcpyDeviceToHost));
+            if (j + 1 < p) {
+                put_block(j + 1, j, hb.data(), false);
+                put_block(j, j + 1, hb.data(), true);
+                LZ_TRY(lz_panel(ctx, n, bw, true, W, 0, d_binv, 0.0, 1.0, block_at(j + 1), 0, nullptr));
+            } else {
+                beta_p = hb;                                            // coupling to the unbuilt block p
+            }
+        }
+        matvecs += (p - j0) * bw;
+        int fl = 0;
+        LZ_CUDA(cudaMemcpy(&fl, flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (fl <= p) {
+            lz_set_error("lz_block_eigs_thick_restart: breakdown, block %d is rank deficient (invariant subspace or dependent start block)", fl);
+            return LZ_ERR_BREAKDOWN;
+        }
+        Hw = H;
+        LZ_TRY(lz_sym_eig_full_c(N, Hw.data(), d, Zt));                 // Zt[r * N + i] = component r of eigenvector i
+        for (int i = 0; i < N; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return d[x] < d[y]; });
+        double scale = 0.0;
+        for (int i = 0; i < N; ++i) scale = std::max(scale, fabs(d[i]));
+        const int lo = which == 0 ? k : which == 1 ? 0 : k / 2, hi = k - lo;
+        wanted.clear();
+        for (int t = 0; t < lo; ++t) wanted.push_back(order[t]);
+        for (int t = 0; t < hi; ++t) wanted.push_back(order[N - hi + t]);
+        auto resid_of = [&](int idx) {          // || beta_p Y[last block rows, idx] ||
+            double r2 = 0.0;
+            for (int r = 0; r < bw; ++r) {
+                double sacc = 0.0;
+                for (int c = 0; c < bw; ++c) sacc += beta_p[r + c * bw] * Zt[(size_t)(N - bw + c) * N + idx];
+                r2 += sacc * sacc;
+            }
+            return sqrt(r2);
+        };
+        nconv = 0;
+        for (int idx : wanted)
+            if (resid_of(idx) <= tol * scale) ++nconv;
+        if (nconv == k || restarts == max_restarts) break;
+        // keep the wanted pairs plus a share of their neighbours, rounded up to whole blocks
+        int kk = k + std::max(bw, (N - k) * 2 / 5);
+        kk = ((kk + bw - 1) / bw) * bw;
+        kk = std::min(kk, (p - 2) * bw);
+        const int extra = kk - k;
+        const int elo = which == 0 ? extra : which == 1 ? 0 : extra / 2, ehi = extra - elo;
+        keep.clear();
+        for (int t = 0; t < lo + elo; ++t) keep.push_back(order[t]);
+        for (int t = 0; t < hi + ehi; ++t) keep.push_back(order[N - (hi + ehi) + t]);
+        const int kkb = kk / bw;
+        // compressed basis block c = sum_j V_j Y[j-th block rows, kept columns of block c]  -> scratch blocks p .. p+kkb-1
+        std::vector<double> negY((size_t)p * bb);
+        for (int c = 0; c < kkb; ++c) {
+            for (int j = 0; j < p; ++j)
+                for (int s2 = 0; s2 < bw; ++s2)
+                    for (int r = 0; r < bw; ++r)
+                        negY[(size_t)j * bb + r + (size_t)s2 * bw] = -Zt[(size_t)(j * bw + r) * N + keep[c * bw + s2]];
+            LZ_CUDA(cudaMemcpyAsync(C, negY.data(), sizeof(double) * negY.size(), cudaMemcpyHostToDevice, ctx->stream));
+            LZ_TRY(lz_block_combine(ctx, n, bw, p, V, (int64_t)pan, C, block_at(p + c)));
+            LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        LZ_CUDA(cudaMemcpyAsync(block_at(0), block_at(p), sizeof(double) * pan * kkb, cudaMemcpyDeviceToDevice, ctx->stream));
+        // the residual block W beta_p^{-1} becomes block kkb  (d_binv still holds beta_p^{-1})
+        LZ_TRY(lz_panel(ctx, n, bw, true, W, 0, d_binv, 0.0, 1.0, block_at(kkb), 0, nullptr));
+        std::fill(H.begin(), H.end(), 0.0);
+        for (int c = 0; c < kk; ++c) {
+            H[c + (size_t)c * N] = d[keep[c]];
+            for (int r = 0; r < bw; ++r) {              // S = beta_p Y[last block rows, keep]:  H[kk + r, c] = S[r, c]
+                double sacc = 0.0;
+                for (int cc = 0; cc < bw; ++cc) sacc += beta_p[r + cc * bw] * Zt[(size_t)(N - bw + cc) * N + keep[c]];
+                H[(size_t)(kk + r) + (size_t)c * N] = sacc;
+                H[c + (size_t)(kk + r) * N] = sacc;
+            }
+        }
+        j0 = kkb;
+        ++restarts;
+    }
+    std::sort(wanted.begin(), wanted.end(), [&](int x, int y) { return d[x] < d[y]; });
+    for (int t = 0; t < k; ++t) {
+        theta_host[t] = d[wanted[t]];
+        if (resid_host) {
+            double r2 = 0.0;
+            for (int r = 0; r < bw; ++r) {
+                double sacc = 0.0;
+                for (int c = 0; c < bw; ++c) sacc += beta_p[r + c * bw] * Zt[(size_t)(N - bw + c) * N + wanted[t]];
+                r2 += sacc * sacc;
+            }
+            resid_host[t] = sqrt(r2);
+        }
+    }
+    if (X) {
+        std::vector<double> negY((size_t)p * bb);
+        for (int c = 0; c < kb; ++c) {
+            for (int j = 0; j < p; ++j)
+                for (int s2 = 0; s2 < bw; ++s2)
+                    for (int r = 0; r < bw; ++r) {
+                        const int col = c * bw + s2;
+                        negY[(size_t)j * bb + r + (size_t)s2 * bw] = col < k ? -Zt[(size_t)(j * bw + r) * N + wanted[col]] : 0.0;
+                    }
+            LZ_CUDA(cudaMemcpyAsync(C, negY.data(), sizeof(double) * negY.size(), cudaMemcpyHostToDevice, ctx->stream));
+            LZ_TRY(lz_block_combine(ctx, n, bw, p, V, (int64_t)pan, C, block_at(p)));
+            const int cols = std::min(bw, k - c * bw);
+            k_rm_to_cm<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, bw, cols, block_at(p), X + (size_t)c * bw * ldx, ldx);
+            LZ_LAUNCH_CHECK(ctx);
+            LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (info4) { info4[0] = nconv; info4[1] = restarts; info4[2] = matvecs; info4[3] = N; }
     return LZ_OK;
 }
 

@@ -212,6 +212,37 @@ static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int6
     return LZ_OK;
 }
 
+// out = sum_j V_j Yc_j  for J stored row-major blocks and J coefficient blocks Yc (b x b column-major, back to back):
+// the update kernel of the block CGS with W = 0 and C = -Yc (thick restart: one output block of V Y)
+template <int BW>
+static int block_combine_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int64_t pan, double *C /* holds -Yc */, double *out)
+{
+    const size_t bb = (size_t)BW * BW;
+    LZ_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n * BW, ctx->stream));
+    lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * BW * (J + 2));
+    if constexpr (BW >= 16) {
+        void *w;
+        LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)J * bb, &w));
+        k_block_coef_frag<BW><<<J, 256, 0, ctx->stream>>>(J, C, (double *)w);
+        LZ_LAUNCH_CHECK(ctx);
+        k_block_update_w<BW><<<ctx->sm_count * 4, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, (const double *)w, out);
+    } else {
+        k_block_update<BW><<<dense_grid(ctx, n), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, C, out);
+    }
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    return LZ_OK;
+}
+
+int lz_block_combine(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *negY, double *out)
+{
+    if (bw == 8) return block_combine_launch<8>(ctx, n, J, V, pan, negY, out);
+    if (bw == 16) return block_combine_launch<16>(ctx, n, J, V, pan, negY, out);
+    if (bw == 32) return block_combine_launch<32>(ctx, n, J, V, pan, negY, out);
+    lz_set_error("lz_block_combine: block width %d (use 8, 16 or 32)", bw);
+    return LZ_ERR_UNSUPPORTED;
+}
+
 int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C, bool sharded)
 {
     if (bw == 8) return block_cgs_launch<8, 8>(ctx, n, J, V, pan, W, C, sharded);

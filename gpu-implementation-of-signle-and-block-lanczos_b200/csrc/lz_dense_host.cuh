@@ -17,3 +17,5 @@ int lz_panel2(lz_ctx *ctx, int64_t n, int bw, const double *T1, const double *S1
 // G1 = X^T Y1 and G2 = X^T Y2 from one read of X (row-major); alpha = sym(G1 - G2 Bm)
 int lz_gram2(lz_ctx *ctx, int64_t n, int bw, const double *X, const double *Y1, const double *Y2, double *G1, double *G2);
 int lz_alpha_from_grams(lz_ctx *ctx, int bw, const double *G1, const double *G2, const double *Bm, double *alpha);
+// out (row-major n x bw) = sum_j V_j Yc_j ; negY holds the J coefficient blocks negated (b x b column-major each)
+int lz_block_combine(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *negY, double *out);

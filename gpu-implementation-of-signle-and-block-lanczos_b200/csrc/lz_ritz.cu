@@ -204,6 +204,13 @@ int lz_sym_eig_full(int N, std::vector<double> &A /* col-major, destroyed */, st
     return LZ_OK;
 }
 
+// same for a plain array (col-major N x N, destroyed)
+int lz_sym_eig_full_c(int N, double *A, std::vector<double> &d, std::vector<double> &Zt)
+{
+    std::vector<double> a(A, A + (size_t)N * N);
+    return lz_sym_eig_full(N, a, d, Zt);
+}
+
 extern "C" int lz_expm_sym(int n, double *T_host)
 {
     LZ_CHECK(n >= 1 && T_host, LZ_ERR_INVALID, "lz_expm_sym: bad arguments");

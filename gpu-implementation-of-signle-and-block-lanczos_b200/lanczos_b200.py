@@ -84,6 +84,7 @@ def lib():
         "lz_vector_ritz_vectors": (i32, [vp, i32, vp, vp, i64]),
         "lz_vector_reorth_count": (i32, [vp, P(i32)]),
         "lz_eigs_thick_restart": (i32, [vp, vp, vp, i32, i32, i32, dbl, i32, vp, vp, vp, i64, vp]),
+        "lz_block_eigs_thick_restart": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, dbl, i32, vp, vp, vp, i64, vp]),
         "lz_vector_basis_info": (i32, [vp, P(i64), P(i32)]),
         "lz_vector_basis_copy": (i32, [vp, i32, i32, vp, i64]),
         "lz_block_lanczos": (i32, [vp, vp, vp, i64, i32, i32, i64, i32, vp, vp, vp]),
@@ -388,6 +389,16 @@ def eigs_thick_restart(ctx, A, b, k, which=0, m_max=None, tol=1e-10, max_restart
     info = (C.c_int * 4)()
     check(lib().lz_eigs_thick_restart(ctx.h, A.h, _ptr(b), k, which, m_max, float(tol), max_restarts, theta.ctypes.data,
                                       resid.ctypes.data, _ptr(X), ldx, info))
+    return theta, resid, dict(converged=info[0], restarts=info[1], matvecs=info[2], basis=info[3])
+
+
+def block_eigs_thick_restart(ctx, A, B, ldb, bw, k, which=0, p_blocks=None, tol=1e-10, max_restarts=200, X=None, ldx=0):
+    """k extremal eigenpairs by block thick-restart Lanczos; returns (theta, resid_estimates, info dict)."""
+    p_blocks = p_blocks or (2 * ((k + bw - 1) // bw) + 4)
+    theta, resid = np.zeros(k), np.zeros(k)
+    info = (C.c_int * 4)()
+    check(lib().lz_block_eigs_thick_restart(ctx.h, A.h, _ptr(B), ldb, bw, k, which, p_blocks, float(tol), max_restarts,
+                                            theta.ctypes.data, resid.ctypes.data, _ptr(X), ldx, info))
     return theta, resid, dict(converged=info[0], restarts=info[1], matvecs=info[2], basis=info[3])
 
 

@@ -200,6 +200,14 @@ int lz_vector_reorth_count(lz_ctx *ctx, int *count);
  *   info4 (or NULL): converged pairs, restarts, operator applications, basis size. */
 int lz_eigs_thick_restart(lz_ctx *ctx, const lz_matrix *A, const double *b, int k, int which, int m_max, double tol,
                           int max_restarts, double *theta_host, double *resid_host, double *X, int64_t ldx, int *info4);
+/* Block thick-restart Lanczos (BASELINE config 3: block size 16, k = 64): the same for multiple / clustered eigenvalues,
+ * which a single Lanczos vector cannot resolve.  B: n x bw start block (column-major, ldb), bw in {8, 16, 32}; the basis
+ * holds p_blocks blocks (p_blocks >= ceil(k / bw) + 3).  Block recurrence with block CGS2 against all stored blocks
+ * (fp64 tensor-core projection / update), host eigensolve of the (p_blocks bw)^2 projected matrix, DMMA compression of
+ * the basis to the kept Ritz vectors.  Outputs as lz_eigs_thick_restart; residual estimate ||beta_p Y_p||. */
+int lz_block_eigs_thick_restart(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t ldb, int bw, int k, int which,
+                                int p_blocks, double tol, int max_restarts, double *theta_host, double *resid_host,
+                                double *X, int64_t ldx, int *info4);
 /* Krylov basis kept by the last full-reorth run (stored row-tiled inside the context):
  * copy columns j0 .. j0+ncols-1 into dst (device, column-major, leading dimension ldd >= rows) */
 int lz_vector_basis_info(lz_ctx *ctx, int64_t *rows, int *cols);

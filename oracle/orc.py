@@ -278,6 +278,69 @@ def thick_restart_lanczos(csr, b, k, which=0, m_max=None, tol=1e-10, max_restart
     return d[wanted], res[wanted], X, dict(converged=nconv, restarts=restarts, matvecs=matvecs, basis=m)
 
 
+def block_thick_restart_lanczos(csr, B, k, which=0, p_blocks=None, tol=1e-10, max_restarts=200):
+    """numpy restatement of lz_block_eigs_thick_restart (csrc/lz_block.cu): block recurrence with full block CGS2,
+    symmetric square roots for the coupling blocks, the same restart rule (wanted pairs plus max(b, 2(N-k)/5) neighbours,
+    rounded up to whole blocks).  TEST INFRASTRUCTURE ONLY.  Returns (theta ascending, residual estimates, X, info)."""
+    n, b = B.shape
+    p = p_blocks or (2 * ((k + b - 1) // b) + 4)
+    N = p * b
+
+    def sym_sqrt(G):
+        w, U = np.linalg.eigh(0.5 * (G + G.T))
+        w = np.abs(w)
+        return (U * np.sqrt(w)) @ U.T, (U / np.sqrt(w)) @ U.T
+
+    V = np.zeros((n, N + b))
+    H = np.zeros((N, N))
+    _, binv = sym_sqrt(B.T @ B)
+    V[:, :b] = B @ binv
+    j0, restarts, matvecs = 0, 0, 0
+    while True:
+        for j in range(j0, p):
+            Q = V[:, j * b:(j + 1) * b]
+            W = spmm(csr, np.ascontiguousarray(Q))
+            G = Q.T @ W
+            alpha = 0.5 * (G + G.T)
+            W = W - Q @ alpha
+            for _ in range(2):
+                Vj = V[:, :(j + 1) * b]
+                W = W - Vj @ (Vj.T @ W)
+            beta, binv = sym_sqrt(W.T @ W)
+            H[j * b:(j + 1) * b, j * b:(j + 1) * b] = alpha
+            if j + 1 < p:
+                H[(j + 1) * b:(j + 2) * b, j * b:(j + 1) * b] = beta
+                H[j * b:(j + 1) * b, (j + 1) * b:(j + 2) * b] = beta.T
+            V[:, (j + 1) * b:(j + 2) * b] = W @ binv
+        matvecs += (p - j0) * b
+        beta_p = beta
+        d, Z = np.linalg.eigh(H)
+        lo = k if which == 0 else 0 if which == 1 else k // 2
+        hi = k - lo
+        wanted = list(range(lo)) + list(range(N - hi, N))
+        res = np.linalg.norm(beta_p @ Z[N - b:, :], axis=0)
+        nconv = int(np.sum(res[wanted] <= tol * np.max(np.abs(d))))
+        if nconv == k or restarts == max_restarts:
+            break
+        kk = k + max(b, (N - k) * 2 // 5)
+        kk = min(((kk + b - 1) // b) * b, (p - 2) * b)
+        extra = kk - k
+        elo = extra if which == 0 else 0 if which == 1 else extra // 2
+        ehi = extra - elo
+        keep = list(range(lo + elo)) + list(range(N - (hi + ehi), N))
+        V[:, :kk] = V[:, :N] @ Z[:, keep]
+        V[:, kk:kk + b] = V[:, N:N + b]
+        H[:] = 0.0
+        H[np.arange(kk), np.arange(kk)] = d[keep]
+        S = beta_p @ Z[N - b:, keep]
+        H[kk:kk + b, :kk] = S
+        H[:kk, kk:kk + b] = S.T
+        j0 = kk // b
+        restarts += 1
+    X = V[:, :N] @ Z[:, wanted]
+    return d[wanted], res[wanted], X, dict(converged=nconv, restarts=restarts, matvecs=matvecs, basis=N)
+
+
 def _mx_axis(N):
     Np = N + 2
     h = (1.0 - 0.0) / (Np - 1)

@@ -173,3 +173,32 @@ def test_selective_reorthogonalisation(lz, ctx, orc):
     th_n = np.linalg.eigvalsh(T(a_n, b_n))
     assert abs(th_n[-1] - lam[-1]) < 1e-8          # (the extreme Ritz value itself is still fine)
     A.close()
+
+
+@pytest.mark.parametrize("bw,which", [(8, 0), (16, 0), (8, 2)])
+def test_block_thick_restart_degenerate_spectrum(lz, ctx, orc, bw, which):
+    """config-3 style: the CUBIC 7-point Laplacian has three- and six-fold eigenvalues, which a single Lanczos vector
+    cannot resolve.  Block thick restart (block CGS2 on the fp64 tensor pipe, DMMA basis compression) must return every
+    copy: against the analytic spectrum with multiplicities, against the oracle's restarted run, and with true residuals."""
+    nx = 12
+    n, k, p = nx ** 3, 12, (6 if bw == 8 else 5)
+    csr = orc.lap3d(nx, nx, nx)
+    B = orc.start_block(n, bw)
+    A = lz.Matrix.laplacian3d(ctx, nx, nx, nx)
+    X = torch.zeros(n * k, dtype=torch.float64, device="cuda")
+    theta, resid, info = lz.block_eigs_thick_restart(ctx, A, dev(np.ascontiguousarray(B.T).reshape(-1)), n, bw, k, which=which,
+                                                     p_blocks=p, tol=1e-10, max_restarts=400, X=X, ldx=n)
+    ctx.sync()
+    assert info["converged"] == k and info["basis"] == p * bw, info
+    th_o, res_o, X_o, info_o = orc.block_thick_restart_lanczos(csr, B, k, which, p, 1e-10, 400)
+    assert info_o["converged"] == k
+    assert np.max(np.abs(theta - th_o)) < 1e-8
+    c = 2 * np.cos(np.pi * np.arange(1, nx + 1) / (nx + 1))
+    lam = np.sort((6 - c[:, None, None] - c[None, :, None] - c[None, None, :]).reshape(-1))
+    want = lam[:k] if which == 0 else np.r_[lam[:k // 2], lam[-(k - k // 2):]]
+    assert np.max(np.abs(theta - want)) < 1e-8                 # multiplicities included (3-fold levels appear 3 times)
+    Xh = X.cpu().numpy().reshape(k, n)
+    assert np.max(np.abs(Xh @ Xh.T - np.eye(k))) < 1e-10
+    tr = true_residuals(lz, ctx, A, X, theta, n, k)
+    assert np.max(tr) < 1e-8 and np.max(resid) < 1e-8
+    A.close()
