@@ -15,7 +15,8 @@ def launches():
     rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if len(r) > 5]
     hdr = rows[0]; ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
     data = [(re.sub(r"[<(].*", "", r[ik]), float(r[iv].replace(",", ""))) for r in rows[1:] if r[iv]]
-    half = data[-2107:] if len(data) < 3000 else data[len(data) // 2:]   # the timed solve (300 steps x 7 launches + 7)
+    per_solve = int(os.environ.get("LZ_LAUNCHES_PER_SOLVE", "2107" if R == "r01" else "1866"))
+    half = data[-per_solve:]        # the timed solve (r01: 300 steps x 7 launches + 7; r02: 63 x 8 + 237 x 6 + 10 with pass B folded into CGS2)
     tot = sum(v for _, v in half); by = {}
     for k, v in half:
         by.setdefault(k, [0, 0.0]); by[k][0] += 1; by[k][1] += v
@@ -24,9 +25,13 @@ def launches():
 
 def full(kernel):
     rep = os.path.join(GO, "%s_full_%s.ncu-rep" % (R, kernel))
-    if not os.path.exists(rep):
+    pre = os.path.join(GO, "%s_full_%s.raw.csv" % (R, kernel))          # exported on the GPU box (gpurun brings back <= 64 MiB)
+    if os.path.exists(pre):
+        out = open(pre).read()
+    elif os.path.exists(rep):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return None
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     open(os.path.join(PR, "%s_full_%s.raw.csv" % (R, kernel)), "w").write(out)
     rows = list(csv.reader(out.splitlines())); hdr, units, val = rows[0], rows[1], rows[2]
     def get(name):
@@ -65,6 +70,37 @@ def sass(kernel_regex, name):
             return keep
     return None
 
+def block_kernels():
+    """round 2: the block-path captures (256^3, b = 16) -> one table: time, DRAM bytes, hit rates, pipe utilisation"""
+    names = ["k_spmm_ws_plain", "k_spmm_ws_fused", "k_spmm_ws_fused_gram", "k_gram_dmma", "k_gram2_dmma", "k_panel_dmma", "k_panel2_dmma",
+             "k_block_project_w", "k_block_update_w", "k_csr_spmv_ws_3d"]
+    cols = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_read"), ("dram__bytes_write.sum", "dram_write"),
+            ("lts__t_sector_hit_rate.pct", "l2_hit_pct"), ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+            ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1_pct"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_active_pct"),
+            ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_active_pct"),
+            ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_scoreboard"),
+            ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block")]
+    out = {}
+    for nme in names:
+        src = os.path.join(GO, "%s_full_%s.raw.csv" % (R, nme))
+        if not os.path.exists(src):
+            continue
+        shutil.copy(src, os.path.join(PR, "%s_full_%s.raw.csv" % (R, nme)))
+        rows = list(csv.reader(open(src)))
+        if len(rows) < 3:
+            continue
+        hdr, units, val = rows[0], rows[1], rows[2]
+        rec = {"kernel": val[hdr.index("Kernel Name")][:90]}
+        for key, short in cols:
+            if key in hdr:
+                i = hdr.index(key)
+                rec[short] = "%s %s" % (val[i], units[i]) if units[i] not in ("", "%") else float(val[i].replace(",", ""))
+        out[nme] = rec
+    return out
+
+
 def main():
     res = {}
     l = launches()
@@ -79,10 +115,18 @@ def main():
         traffic["_source"] = "ncu --set full captures profiles/%s_full_*.raw.csv (dram__bytes_read.sum + dram__bytes_write.sum), bench.py cfg2, launch 250 of each kernel" % R
         json.dump(traffic, open(os.path.join(PR, "roofline_traffic.json"), "w"), indent=1)
     res["traffic"] = traffic
+    res["block_kernels"] = block_kernels()
     res["sass"] = {n: sass(rx, n) for rx, n in ((r"_Z20k_cgs_update_project", "k_cgs_update_project"), (r"_Z12k_cgs_update", "k_cgs_update"),
                                                (r"_Z13k_cgs_project", "k_cgs_project"), (r"_Z13k_csr_spmv_wsILi1ELi3ELi5", "k_csr_spmv_ws"),
-                                               (r"_Z9k_spmm_wsILi16ELi12", "k_spmm_ws16"), (r"_Z11k_gram_dmmaILi16", "k_gram_dmma16"),
-                                               (r"_Z14k_block_updateILi16", "k_block_update16"))}
+                                               (r"_Z9k_spmm_wsILi16ELi12ELi2ELi2048ELi2ELb0", "k_spmm_ws16"), (r"_Z9k_spmm_wsILi16ELi11ELi2ELi2048ELi2ELb1ELb1", "k_spmm_ws16_fused_gram"),
+                                               (r"_Z11k_gram_dmmaILi16", "k_gram_dmma16"),
+                                               (r"_Z17k_block_project_wILi16", "k_block_project_w16"), (r"_Z16k_block_update_wILi16", "k_block_update_w16"),
+                                               (r"_Z13k_panel2_dmmaILi16ELb1", "k_panel2_dmma16"), (r"_Z14k_basis_rotateILi8", "k_basis_rotate8"),
+                                               (r"_Z16k_peer_allreduce", "k_peer_allreduce"))}
+    for f in os.listdir(GO):        # source pages of the kept reports, run logs
+        if f.startswith(R + "_full_") and f.endswith(".source.csv"):
+            shutil.copy(os.path.join(GO, f), os.path.join(PR, f))
+    json.dump(res, open(os.path.join(PR, R + "_summary.json"), "w"), indent=1)
     for f in (R + "_bench_plain.log",):
         if os.path.exists(os.path.join(GO, f)):
             shutil.copy(os.path.join(GO, f), os.path.join(PR, f))
