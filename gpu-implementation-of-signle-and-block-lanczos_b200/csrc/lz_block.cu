@@ -778,7 +778,9 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
     LZ_CHECK(A->n_cols == n + hlo + hhi && ldb >= n, LZ_ERR_INVALID, "lz_block_lanczos: operator must be square and ldb >= n");
     LZ_CHECK(sharded || (hlo == 0 && hhi == 0), LZ_ERR_INVALID, "lz_block_lanczos: a sharded operator needs lz_comm_init");
     LZ_CHECK(lc >= -1 && lc < n, LZ_ERR_INVALID, "lz_block_lanczos: lc out of range");
-    LZ_CHECK(reorth == LZ_REORTH_NONE || reorth == LZ_REORTH_FULL, LZ_ERR_INVALID, "lz_block_lanczos: reorth mode %d", reorth);
+    LZ_CHECK(reorth == LZ_REORTH_NONE || reorth == LZ_REORTH_FULL || reorth == LZ_REORTH_FULL_DGKS, LZ_ERR_INVALID, "lz_block_lanczos: reorth mode %d", reorth);
+    const bool dgks = reorth == LZ_REORTH_FULL_DGKS;
+    LZ_CHECK(!dgks || bw == 8 || bw == 16 || bw == 32, LZ_ERR_UNSUPPORTED, "lz_block_lanczos: the DGKS mode needs a block width of 8, 16 or 32");
     LZ_CUDA(cudaSetDevice(ctx->device));
     const size_t pan = (size_t)n * bw, bb = (size_t)bw * bw;
     // panel layout [lower halo | local | upper halo]; sharded: identical offsets on every rank (peer halo pushes)
@@ -815,9 +817,24 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
     auto halo = [&](double *Q) -> int {
         return sharded ? lz_comm_halo_exchange(ctx, Q, (int64_t)pan, hlo * bw, hhi * bw, n_below, false) : LZ_OK;
     };
-    auto cgs2 = [&](int nblocks) -> int {
-        for (int sweep = 0; sweep < 2; ++sweep) LZ_TRY(lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)pan, W, C, sharded));
-        return LZ_OK;
+    int *sweep_flag = ctx->flags + 6;
+    // Full reorthogonalisation of W against the stored blocks and the next W^T W into `gn`.
+    //   FULL: two block CGS sweeps, always (CGS2), then the Gram.
+    //   DGKS: one sweep, the Gram, and a second sweep + Gram only if some column of W lost more than half of its squared
+    //         norm in the first ("twice is enough", decided on the device from the two Gram diagonals; `gb` = W^T W before)
+    auto reorthogonalise = [&](int nblocks, double *gb, double *gn) -> int {
+        LZ_TRY(lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)pan, W, C, sharded));
+        if (!dgks) {
+            LZ_TRY(lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)pan, W, C, sharded));
+            return lz_gram(ctx, n, bw, true, W, 0, W, 0, gn, 0);
+        }
+        double *ga = sharded ? ctx->scalars + SB_G2 : gn;                 // Gram after the first sweep
+        LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, ga, 0));
+        if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, ga, bb));
+        LZ_TRY(lz_block_dgks_test(ctx, bw, gb, ga, sweep_flag));
+        LZ_TRY(lz_block_cgs(ctx, n, bw, nblocks, V, (int64_t)pan, W, C, sharded, sweep_flag));
+        if (sharded) return lz_gram(ctx, n, bw, true, W, 0, W, 0, gn, 0);   // (its all-reduce follows unconditionally)
+        return lz_gram_if(ctx, n, bw, W, gn, sweep_flag);
     };
     auto qslot = [&](int j) -> double * { return inplace ? V + pan * j : ((j & 1) ? Qb : Qa); };
     const bool qrow = q != nullptr && lc >= 0;
@@ -841,10 +858,11 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
     LZ_TRY(spmm_rm(ctx, A, bw, Q0 - hlo * bw, W, nullptr, nullptr));                          // :121
     LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q0, 0, alpha, 1));                                 // :124
     LZ_TRY(reduce_small(alpha));
-    LZ_TRY(lz_panel(ctx, n, bw, true, Q0, 0, alpha, 1.0, -1.0, W, 0, reorth ? nullptr : gslot(1)));  // :128 (+ :137 fused)
+    double *gbefore = sc + SB_G1;                          // DGKS: W^T W before the sweeps (fused into the panel pass)
+    LZ_TRY(lz_panel(ctx, n, bw, true, Q0, 0, alpha, 1.0, -1.0, W, 0, reorth ? (dgks ? gbefore : nullptr) : gslot(1)));  // :128 (+ :137 fused)
     if (reorth) {
-        LZ_TRY(cgs2(1));
-        LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, gslot(1), 0));
+        if (dgks) LZ_TRY(reduce_small(gbefore));
+        LZ_TRY(reorthogonalise(1, gbefore, gslot(1)));
     }
     LZ_TRY(reduce_small(gslot(1)));
     for (int j = 1; j < m; ++j) {                                                             // :132-166
@@ -866,7 +884,7 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
                 LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Q1, 0, aj, 1));
             }
             LZ_TRY(reduce_small(aj));
-            LZ_TRY(lz_panel(ctx, n, bw, true, Q1, 0, aj, 1.0, -1.0, W, 0, reorth ? nullptr : gn));
+            LZ_TRY(lz_panel(ctx, n, bw, true, Q1, 0, aj, 1.0, -1.0, W, 0, reorth ? (dgks ? gbefore : nullptr) : gn));
         } else {
             // same quantities when the SpMM cannot subtract: G1 = Q_j^T (A Q_j) and G2 = Q_j^T Q_{j-1} from one pass,
             // alpha_j = sym(G1 - G2 beta_j), then one pass subtracts both Q_{j-1} beta_j and Q_j alpha_j (+ next W^T W)
@@ -874,12 +892,12 @@ int lz_block_lanczos(lz_ctx *ctx, const lz_matrix *A, const double *B, int64_t l
             LZ_TRY(lz_gram2(ctx, n, bw, Q1, W, Q0, sc + SB_G1, sc + SB_G2));
             if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, sc + SB_G1, 2048));            // G1 and G2 sit back to back
             LZ_TRY(lz_alpha_from_grams(ctx, bw, sc + SB_G1, sc + SB_G2, bj, aj));
-            LZ_TRY(lz_panel2(ctx, n, bw, Q0, bj, Q1, aj, W, reorth ? nullptr : gn));
+            LZ_TRY(lz_panel2(ctx, n, bw, Q0, bj, Q1, aj, W, reorth ? (dgks ? gbefore : nullptr) : gn));
         }
         Q0 = Q1;                                                                              // :162 (no copy)
         if (V) {
-            LZ_TRY(cgs2(j + 1));
-            LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, gn, 0));
+            if (dgks) LZ_TRY(reduce_small(gbefore));
+            LZ_TRY(reorthogonalise(j + 1, gbefore, gn));
         }
         LZ_TRY(reduce_small(gn));
     }
@@ -996,7 +1014,7 @@ int lz_block_eigs_thick_restart(lz_ctx *ctx, const lz_matrix *A, const double *B
     LZ_TRY(lz_ctx_workspace(ctx, sizeof(double) * (pan + 4 * bb * (size_t)(p + 2) + 64), &work));
     double *W = (double *)work, *C = W + pan;                          // C: CGS coefficients / combination blocks (2 bb p)
     double *dsm = C + 2 * bb * (size_t)(p + 1);                         // device b x b blocks: alpha, G / beta, beta^{-1}
-    double *d_alpha = dsm, *d_beta = dsm + bb, *d_binv = dsm + 2 * bb;
+    double *d_alpha = dsm, *d_beta = dsm + bb, *d_binv = dsm + 2 * bb, *d_gb = dsm + 3 * bb;
     int *flag = ctx->flags + 2;
     k_flag_init<<<1, 1, 0, ctx->stream>>>(ctx->flags);
     LZ_LAUNCH_CHECK(ctx);
@@ -1021,11 +1039,15 @@ int lz_block_eigs_thick_restart(lz_ctx *ctx, const lz_matrix *A, const double *B
             LZ_TRY(spmm_rm(ctx, A, bw, Qj, W, nullptr, nullptr));
             LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, Qj, 0, d_alpha, 1));
             LZ_CUDA(cudaMemcpyAsync(hb.data(), d_alpha, sizeof(double) * bb, cudaMemcpyDeviceToHost, ctx->stream));
-            LZ_TRY(lz_panel(ctx, n, bw, true, Qj, 0, d_alpha, 1.0, -1.0, W, 0, nullptr));
-            // block CGS2 against every stored block: removes Q_{j-1} beta_j, the coupling to the kept Ritz vectors and
-            // whatever rounding left elsewhere
-            for (int sweep = 0; sweep < 2; ++sweep) LZ_TRY(lz_block_cgs(ctx, n, bw, j + 1, V, (int64_t)pan, W, C, false));
+            LZ_TRY(lz_panel(ctx, n, bw, true, Qj, 0, d_alpha, 1.0, -1.0, W, 0, d_gb));
+            // block Gram-Schmidt against every stored block: removes Q_{j-1} beta_j, the coupling to the kept Ritz vectors
+            // and whatever rounding left elsewhere; the second sweep runs only when the first removed more than half of
+            // some column (it always does right after a restart, almost never otherwise)
+            LZ_TRY(lz_block_cgs(ctx, n, bw, j + 1, V, (int64_t)pan, W, C, false));
             LZ_TRY(lz_gram(ctx, n, bw, true, W, 0, W, 0, d_beta, 0));
+            LZ_TRY(lz_block_dgks_test(ctx, bw, d_gb, d_beta, ctx->flags + 6));
+            LZ_TRY(lz_block_cgs(ctx, n, bw, j + 1, V, (int64_t)pan, W, C, false, ctx->flags + 6));
+            LZ_TRY(lz_gram_if(ctx, n, bw, W, d_beta, ctx->flags + 6));
             LZ_TRY(lz_sqrtm_launch(ctx, bw, d_beta, d_binv, flag, j + 1));
             LZ_CUDA(cudaStreamSynchronize(ctx->stream));
             put_block(j, j, hb.data(), false);

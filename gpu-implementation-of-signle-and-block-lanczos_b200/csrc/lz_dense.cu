@@ -15,6 +15,24 @@ static inline int dense_grid(const lz_ctx *ctx, int64_t n)
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
+// W^T W of a row-major panel, executed only when *run_flag != 0 (G keeps its value otherwise); bw in {8, 16, 32}
+int lz_gram_if(lz_ctx *ctx, int64_t n, int bw, const double *W, double *G, const int *run_flag)
+{
+    const int grid = dense_grid(ctx, n);
+    void *w;
+    LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)grid * bw * bw, &w));
+    lz_prof_begin(ctx, LZ_K_GRAM, 8.0 * (double)n * bw);
+    if (bw == 8) k_gram_dmma<8, true, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, W, 0, W, 0, (double *)w, run_flag);
+    else if (bw == 16) k_gram_dmma<16, true, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, W, 0, W, 0, (double *)w, run_flag);
+    else if (bw == 32) k_gram_dmma<32, true, true><<<grid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, W, 0, W, 0, (double *)w, run_flag);
+    else { lz_set_error("lz_gram_if: block width %d", bw); return LZ_ERR_UNSUPPORTED; }
+    LZ_LAUNCH_CHECK(ctx);
+    lz_prof_end(ctx);
+    k_gram_reduce<<<(bw * bw + 7) / 8, 256, 0, ctx->stream>>>(bw, grid, (const double *)w, bw * bw, G, 0, run_flag);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
 template <bool RMX, bool RMY>
 static int gram_launch(lz_ctx *ctx, int64_t n, int bw, const double *X, int64_t ldx, const double *Y, int64_t ldy,
                        double *G, int mode, double *gpart, int grid)
@@ -183,7 +201,7 @@ int lz_alpha_from_grams(lz_ctx *ctx, int bw, const double *G1, const double *G2,
 
 // one classical block Gram-Schmidt sweep of W (row-major n x bw) against J stored row-major blocks
 template <int BW, int JB>
-static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int64_t pan, double *W, double *C, bool sharded)
+static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int64_t pan, double *W, double *C, bool sharded, const int *run_flag)
 {
     const int gx = ctx->sm_count * 2, batches = (J + JB - 1) / JB;
     const size_t bb = (size_t)BW * BW;
@@ -192,21 +210,21 @@ static int block_cgs_launch(lz_ctx *ctx, int64_t n, int J, const double *V, int6
     double *gpart = (double *)w, *Cf = gpart + (size_t)batches * gx * JB * bb;
     const int ugrid = ctx->sm_count * 4;
     lz_prof_begin(ctx, LZ_K_PROJECT, 8.0 * (double)n * BW * (J + batches));
-    if constexpr (BW >= 16) k_block_project_w<BW, JB><<<dim3(gx, batches), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, W, gpart);
-    else k_block_project<BW, JB><<<dim3(gx, batches), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, W, gpart);
+    if constexpr (BW >= 16) k_block_project_w<BW, JB><<<dim3(gx, batches), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, W, gpart, run_flag);
+    else k_block_project<BW, JB><<<dim3(gx, batches), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, W, gpart, run_flag);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    if constexpr (BW >= 16) k_block_project_reduce_w<BW, JB><<<J, 1024, 0, ctx->stream>>>(J, gx, gpart, C);
-    else k_block_project_reduce<JB><<<J, 1024, 0, ctx->stream>>>(BW, J, gx, gpart, C);
+    if constexpr (BW >= 16) k_block_project_reduce_w<BW, JB><<<J, 1024, 0, ctx->stream>>>(J, gx, gpart, C, run_flag);
+    else k_block_project_reduce<JB><<<J, 1024, 0, ctx->stream>>>(BW, J, gx, gpart, C, run_flag);
     LZ_LAUNCH_CHECK(ctx);
     if (sharded) LZ_TRY(lz_comm_allreduce_sum(ctx, C, (size_t)J * bb));      // the coefficients of all ranks' row slabs add up
     if constexpr (BW >= 16) {        // fragment-ordered negative for the update kernel (local permutation)
-        k_block_coef_frag<BW><<<J, 256, 0, ctx->stream>>>(J, C, Cf);
+        k_block_coef_frag<BW><<<J, 256, 0, ctx->stream>>>(J, C, Cf, run_flag);
         LZ_LAUNCH_CHECK(ctx);
     }
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * BW * (J + 2));
-    if constexpr (BW >= 16) k_block_update_w<BW><<<ugrid < 1 ? 1 : ugrid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, Cf, W);
-    else k_block_update<BW><<<dense_grid(ctx, n), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, C, W);
+    if constexpr (BW >= 16) k_block_update_w<BW><<<ugrid < 1 ? 1 : ugrid, LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, Cf, W, run_flag);
+    else k_block_update<BW><<<dense_grid(ctx, n), LZ_DENSE_THREADS, 0, ctx->stream>>>(n, J, V, pan, C, W, run_flag);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
     return LZ_OK;
@@ -243,11 +261,19 @@ int lz_block_combine(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int
     return LZ_ERR_UNSUPPORTED;
 }
 
-int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C, bool sharded)
+int lz_block_dgks_test(lz_ctx *ctx, int bw, const double *G_before, const double *G_after, int *flag)
 {
-    if (bw == 8) return block_cgs_launch<8, 8>(ctx, n, J, V, pan, W, C, sharded);
-    if (bw == 16) return block_cgs_launch<16, 4>(ctx, n, J, V, pan, W, C, sharded);
-    if (bw == 32) return block_cgs_launch<32, 2>(ctx, n, J, V, pan, W, C, sharded);
+    k_block_dgks_test<<<1, 32, 0, ctx->stream>>>(bw, G_before, G_after, flag);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
+int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C, bool sharded, const int *run_flag)
+{
+    if (bw == 8) return block_cgs_launch<8, 8>(ctx, n, J, V, pan, W, C, sharded, run_flag);
+    if (bw == 16) return block_cgs_launch<16, 4>(ctx, n, J, V, pan, W, C, sharded, run_flag);
+    if (bw == 32) return block_cgs_launch<32, 2>(ctx, n, J, V, pan, W, C, sharded, run_flag);
+    LZ_CHECK(run_flag == nullptr, LZ_ERR_UNSUPPORTED, "conditional block sweeps need a block width of 8, 16 or 32");
     // generic widths: block-by-block products (SIMT)
     const size_t bb = (size_t)bw * bw;
     for (int j = 0; j < J; ++j) LZ_TRY(lz_gram(ctx, n, bw, true, V + pan * j, 0, W, 0, C + bb * j, 0));

@@ -38,8 +38,9 @@ __device__ __forceinline__ void lz_dmma(double &d0, double &d1, double a, double
 template <int BW, bool RMX, bool RMY>
 __global__ void __launch_bounds__(LZ_DENSE_THREADS)
 k_gram_dmma(int64_t n, const double *__restrict__ X, int64_t ldx, const double *__restrict__ Y, int64_t ldy,
-            double *__restrict__ gpart)
+            double *__restrict__ gpart, const int *__restrict__ run_flag = nullptr)
 {
+    if (run_flag && *run_flag == 0) return;
     constexpr int T = BW / 8;
     const LzLay<RMX> lx{ldx, BW};
     const LzLay<RMY> ly{ldy, BW};
@@ -146,8 +147,10 @@ k_gram_simt(int64_t n, int bw, const double *__restrict__ X, int64_t ldx, const 
 // per-thread walk over ~600 partials this replaces cost more than the Gram kernel's own tail.
 // gstride: doubles between consecutive partials (bw*bw, or 2*bw*bw for the two-Gram kernel).
 static __global__ void __launch_bounds__(256)
-k_gram_reduce(int bw, int n_parts, const double *__restrict__ gpart, int gstride, double *__restrict__ G, int mode)
+k_gram_reduce(int bw, int n_parts, const double *__restrict__ gpart, int gstride, double *__restrict__ G, int mode,
+              const int *__restrict__ run_flag = nullptr)
 {
+    if (run_flag && *run_flag == 0) return;
     const int lane = threadIdx.x & 31, e = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (e >= bw * bw) return;
     const int p = e % bw, q = e / bw, et = q + p * bw;
@@ -252,6 +255,21 @@ k_gram2_dmma(int64_t n, const double *__restrict__ X, const double *__restrict__
         for (int e = threadIdx.x; e < BW * BW; e += LZ_DENSE_THREADS) gpart[((size_t)blockIdx.x * 2 + h) * BW * BW + e] = sm[e];
         __syncthreads();
     }
+}
+
+// block DGKS test: a second Gram-Schmidt sweep is needed iff the first one removed more than half of the squared norm
+// of SOME column of W ("twice is enough", per column: diag(W'^T W') < 0.5 diag(W^T W)).  flag <- 1 / 0.
+static __global__ void k_block_dgks_test(int bw, const double *__restrict__ G_before, const double *__restrict__ G_after, int *flag)
+{
+    __shared__ int need;
+    if (threadIdx.x == 0) need = 0;
+    __syncthreads();
+    if (threadIdx.x < bw) {
+        const double b = G_before[threadIdx.x + threadIdx.x * bw], a = G_after[threadIdx.x + threadIdx.x * bw];
+        if (!(a >= 0.5 * b)) atomicOr(&need, 1);          // also true for NaN: when in doubt, sweep again
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = need;
 }
 
 // alpha = sym(G1 - G2 B): one CTA, b x b column-major matrices
@@ -416,8 +434,9 @@ k_panel_simt(int64_t n, int bw, const double *T_, int64_t ldt, const double *__r
 template <int BW, int JB>
 __global__ void __launch_bounds__(LZ_DENSE_THREADS)
 k_block_project(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ W,
-                double *__restrict__ gpart /* [gridDim.y][gridDim.x][JB][BW*BW] */)
+                double *__restrict__ gpart /* [gridDim.y][gridDim.x][JB][BW*BW] */, const int *__restrict__ run_flag)
 {
+    if (run_flag && *run_flag == 0) return;          // conditional second sweep (block DGKS)
     constexpr int T = BW / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kk = lane & 3, mm = lane >> 2;
@@ -479,8 +498,9 @@ k_block_project(int64_t n, int J, const double *__restrict__ V, int64_t pan, con
 // C[j] = sum over CTAs of the partials of stored block j (fixed order): one warp per entry, lanes stride over the partials
 template <int JB>
 static __global__ void __launch_bounds__(1024)
-k_block_project_reduce(int bw, int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C)
+k_block_project_reduce(int bw, int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C, const int *__restrict__ run_flag)
 {
+    if (run_flag && *run_flag == 0) return;
     const int j = blockIdx.x, batch = j / JB, jb = j % JB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int e = warp; e < bw * bw; e += nw) {
@@ -493,8 +513,10 @@ k_block_project_reduce(int bw, int J, int n_parts, const double *__restrict__ gp
 
 template <int BW>
 __global__ void __launch_bounds__(LZ_DENSE_THREADS)
-k_block_update(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ C, double *__restrict__ W)
+k_block_update(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ C, double *__restrict__ W,
+               const int *__restrict__ run_flag = nullptr)
 {
+    if (run_flag && *run_flag == 0) return;
     constexpr int NT = BW / 8, KT = BW / 4, G = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kk = lane & 3, mm = lane >> 2;
@@ -559,8 +581,9 @@ __device__ __forceinline__ double2 lz_ld128_stream(const double *p)
 template <int BW, int JB>
 __global__ void __launch_bounds__(LZ_DENSE_THREADS)
 k_block_project_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ W,
-                  double *__restrict__ gpart /* [gridDim.y][gridDim.x][JB][BW*BW] */)
+                  double *__restrict__ gpart /* [gridDim.y][gridDim.x][JB][BW*BW] */, const int *__restrict__ run_flag)
 {
+    if (run_flag && *run_flag == 0) return;          // conditional second sweep (block DGKS)
     constexpr int T = BW / 8, NV = BW / 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kk = lane & 3, mm = lane >> 2;
@@ -633,8 +656,9 @@ k_block_project_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, c
 // C[j] = sum of partials (fixed order, one warp per entry)
 template <int BW, int JB>
 static __global__ void __launch_bounds__(1024)
-k_block_project_reduce_w(int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C)
+k_block_project_reduce_w(int J, int n_parts, const double *__restrict__ gpart, double *__restrict__ C, const int *__restrict__ run_flag)
 {
+    if (run_flag && *run_flag == 0) return;
     const int j = blockIdx.x, batch = j / JB, jb = j % JB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int e = warp; e < BW * BW; e += nw) {
@@ -649,8 +673,9 @@ k_block_project_reduce_w(int J, int n_parts, const double *__restrict__ gpart, d
 // step so that sharded runs all-reduce C once and permute afterwards.
 template <int BW>
 static __global__ void __launch_bounds__(256)
-k_block_coef_frag(int J, const double *__restrict__ C, double *__restrict__ Cf)
+k_block_coef_frag(int J, const double *__restrict__ C, double *__restrict__ Cf, const int *__restrict__ run_flag = nullptr)
 {
+    if (run_flag && *run_flag == 0) return;
     constexpr int KT = BW / 4, NT = BW / 8;
     const int j = blockIdx.x;
     for (int e = threadIdx.x; e < KT * NT * 32; e += blockDim.x) {
@@ -662,8 +687,10 @@ k_block_coef_frag(int J, const double *__restrict__ C, double *__restrict__ Cf)
 
 template <int BW>
 __global__ void __launch_bounds__(LZ_DENSE_THREADS)
-k_block_update_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ Cf, double *__restrict__ W)
+k_block_update_w(int64_t n, int J, const double *__restrict__ V, int64_t pan, const double *__restrict__ Cf, double *__restrict__ W,
+                 const int *__restrict__ run_flag = nullptr)
 {
+    if (run_flag && *run_flag == 0) return;
     constexpr int NT = BW / 8, KT = BW / 4, NC = BW / 16, G = BW == 16 ? 4 : 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kk = lane & 3, mm = lane >> 2;

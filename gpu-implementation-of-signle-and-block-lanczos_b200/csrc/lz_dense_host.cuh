@@ -11,7 +11,11 @@ int lz_panel(lz_ctx *ctx, int64_t n, int bw, bool rm, const double *T, int64_t l
 int lz_sqrtm_launch(lz_ctx *ctx, int b, double *S, double *Sinv, int *flag, int jidx = 0);
 int lz_copy_row_launch(lz_ctx *ctx, int64_t lc, int b, bool rm, const double *Q, int64_t ld, double *q, int64_t off);
 // one classical block Gram-Schmidt sweep: C_j = V_j^T W (j < J), W -= sum_j V_j C_j; V_j row-major, `pan` apart
-int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C, bool sharded = false);
+// run_flag (device int, optional): the sweep's kernels return at once when it is 0 (conditional second sweep)
+int lz_block_cgs(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *W, double *C, bool sharded = false,
+                 const int *run_flag = nullptr);
+// flag <- 1 iff some column of W lost more than half of its squared norm (diagonals of W^T W before / after a sweep)
+int lz_block_dgks_test(lz_ctx *ctx, int bw, const double *G_before, const double *G_after, int *flag);
 // W -= T1 S1 + T2 S2 (row-major panels), G_opt (device bw*bw) receives W_new^T W_new
 int lz_panel2(lz_ctx *ctx, int64_t n, int bw, const double *T1, const double *S1, const double *T2, const double *S2, double *W, double *G_opt);
 // G1 = X^T Y1 and G2 = X^T Y2 from one read of X (row-major); alpha = sym(G1 - G2 Bm)
@@ -19,3 +23,5 @@ int lz_gram2(lz_ctx *ctx, int64_t n, int bw, const double *X, const double *Y1, 
 int lz_alpha_from_grams(lz_ctx *ctx, int bw, const double *G1, const double *G2, const double *Bm, double *alpha);
 // out (row-major n x bw) = sum_j V_j Yc_j ; negY holds the J coefficient blocks negated (b x b column-major each)
 int lz_block_combine(lz_ctx *ctx, int64_t n, int bw, int J, const double *V, int64_t pan, double *negY, double *out);
+// G = W^T W only when *run_flag != 0 (row-major W, bw in {8,16,32})
+int lz_gram_if(lz_ctx *ctx, int64_t n, int bw, const double *W, double *G, const int *run_flag);

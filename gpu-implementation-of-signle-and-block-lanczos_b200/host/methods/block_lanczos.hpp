@@ -17,7 +17,8 @@ void block_lanczos_blas(Matrix &A, Dense_matrix<type_t> &B, const unsigned int m
     lzb::require_device_type<type_t>();
     const std::size_t bw = B.n_cols(), bb = bw * bw;
     Dense_matrix<type_t> a(bb, m, MemorySpace::CUDA), bt(bb, m + 1, MemorySpace::CUDA);
-    const int mode = lzb::reorth_mode() == LZ_REORTH_NONE ? LZ_REORTH_NONE : LZ_REORTH_FULL;
+    const int rm = lzb::reorth_mode();     // the block driver knows none / full (CGS2) / DGKS; the vector-only selective mode maps to DGKS
+    const int mode = rm == LZ_REORTH_NONE ? LZ_REORTH_NONE : (rm == LZ_REORTH_FULL || !(bw == 8 || bw == 16 || bw == 32)) ? LZ_REORTH_FULL : LZ_REORTH_FULL_DGKS;
     AssertCuda(lz_block_lanczos(lanczos_context(), A.device_operator(), reinterpret_cast<const double *>(B.data()), (int64_t)B.n_rows(), (int)bw,
                                 (int)m, lc, mode, reinterpret_cast<double *>(a.data()), reinterpret_cast<double *>(bt.data()),
                                 reinterpret_cast<double *>(q.data())));

@@ -246,6 +246,26 @@ def test_full_size_config3_parity(lz, ctx, orc, reorth):
     A.close()
 
 
+@pytest.mark.parametrize("bw", [8, 16])
+def test_block_dgks_mode_matches_cgs2_oracle(lz, ctx, orc, bw):
+    """LZ_REORTH_FULL_DGKS for blocks: one block Gram-Schmidt sweep, a second one only when a column of W lost more than
+    half of its squared norm (decided on the device).  Against the oracle's unconditional CGS2: blocks to 1e-10, and the
+    basis it leaves is orthonormal to working precision."""
+    nx, ny, nz, m = 20, 18, 16, 10
+    csr = orc.lap3d(nx, ny, nz)
+    n = nx * ny * nz
+    B = orc.start_block(n, bw)
+    A = lz.Matrix.laplacian3d(ctx, nx, ny, nz)
+    ref = orc.block_lanczos(csr, B, m, lc=5, reorth=1, want_basis=True)
+    a, b, q = run_block(lz, ctx, A, B, m, 5, reorth=lz.REORTH_FULL_DGKS)
+    assert lz.block_status(ctx, m) == m
+    assert block_err(a, ref["alpha"], m) < 1e-10 and block_err(b, ref["beta"], m) < 1e-10
+    assert np.max(np.abs(q - ref["q"])) < 1e-10
+    V = ref["V"]
+    assert np.max(np.abs(V.T @ V - np.eye(m * bw))) < 1e-12          # (the oracle's basis: what the run must reproduce)
+    A.close()
+
+
 def test_full_size_config3_properties(lz, ctx):
     """BASELINE config 3 shape: 256^3 7-point Laplacian (16.7 M rows), b = 16.  Size-independent checks:
     beta blocks symmetric positive definite, alpha symmetric, Ritz values inside (0, 12), and the
