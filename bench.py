@@ -239,7 +239,9 @@ def extra_legs(ctx, lz, peak, A2=None, b2=None, m2=300):
                "ms_per_step": ms, "it_per_s": 1e3 / ms,
                "classes_ms_per_step": {k: round(v[1] / mb, 4) for k, v in prof.items() if v[0]}}
         if not reorth:
-            byt = 12.0 * nnz + 4.0 * n + 10 * 8.0 * n * bw
+            # shipped formulation: normalise (2 panel passes) + SpMM with fused subtraction and Gram (matrix + gather + Q_{j-1}
+            # + W = 3) + one-term panel update with the next Gram fused (3): 8 panel passes (round 1 moved 10)
+            byt = 12.0 * nnz + 4.0 * n + 8 * 8.0 * n * bw
             rec.update({"algorithmic_bytes": byt, "frac": byt / ms / 1e6 / peak, "spmm_ms": prof["spmm"][1] / max(prof["spmm"][0], 1),
                         "spmm_frac": prof["spmm"][2] / max(prof["spmm"][1], 1e-9) / 1e6 / peak})
             out["cfg3_block_step"] = rec

@@ -503,7 +503,7 @@ k_spmm_rm_ell4(int64_t n_rows, const double *__restrict__ data, const uint32_t *
 // its row of A in registers and walks the b columns FOUR at a time, so 4 x (row length) independent gathers are in
 // flight per thread; for banded operators the gathers of a warp's 32 consecutive rows coalesce into 256-byte
 // segments of each column, and Y is written in full lines.  Products and sums are separate roundings in the
-// row's storage order (the reference Host loop, objects/ell_matrix.hpp:246-251): bit-exact against the oracle.
+// row's storage order (the reference Host loop, objects/ell_matrix.hpp:246-251): bit-identical to that loop.
 template <int CG>
 __global__ void __launch_bounds__(SPMM_THREADS)
 k_spmm_cm(int64_t n_rows, int b, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
