@@ -494,8 +494,9 @@ static int finish_norm(lz_ctx *ctx, const LzFinal &f, bool sharded, bool want_no
 }
 
 // rows per thread of the streaming CGS kernels: 8, or 4 when that leaves fewer than ~8 tiles per CTA (see CgsShape)
-static inline int cgs_rows_per_thread(int64_t n, unsigned max_grid)
+static inline int cgs_rows_per_thread(const lz_ctx *ctx, int64_t n, unsigned max_grid)
 {
+    if (ctx->knobs.cgs_rpt == 4 || ctx->knobs.cgs_rpt == 8) return ctx->knobs.cgs_rpt;
     const int64_t tiles8 = (n + VT * 8 - 1) / (VT * 8);
     return tiles8 < (int64_t)max_grid * 8 ? 4 : 8;
 }
@@ -518,7 +519,7 @@ static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, doub
     // reads of the tiled slab -- measured 4 % slower than this generic kernel: profiles/r01_cgs_fusion.md)
     const int mult = ctx->knobs.cgs_upd_mult;      // default 3 CTAs/SM: 5.9 -> 6.6 TB/s on the row-tiled basis
     const unsigned cap = (unsigned)(ctx->sm_count * mult);
-    const int rpt = cgs_rows_per_thread(n, cap);
+    const int rpt = cgs_rows_per_thread(ctx, n, cap);
     const unsigned want = stream_grid(ctx, n, VT * rpt);
     const unsigned grid = want < cap ? want : cap;
     const LzFinal f = arm_final(ctx, fin, sharded, want_norm);
@@ -712,7 +713,7 @@ int lz_vec_setup(lz_ctx *ctx, const lz_matrix *A, int m, int64_t lc, int reorth,
     }
     const int64_t stride = round_up(span, 4);
     LzCgs g = {nullptr, 0, 0, nullptr, nullptr, 0, 8};
-    const int cgs_rpt = cgs_rows_per_thread(n, (unsigned)(ctx->sm_count * 2));
+    const int cgs_rpt = cgs_rows_per_thread(ctx, n, (unsigned)(ctx->sm_count * 2));
     const unsigned cgs_grid = stream_grid(ctx, n, VT * cgs_rpt) < (unsigned)(ctx->sm_count * 2)
                                   ? stream_grid(ctx, n, VT * cgs_rpt) : (unsigned)(ctx->sm_count * 2);
     size_t work_bytes = sizeof(double) * (size_t)stride * 3;
