@@ -213,7 +213,7 @@ __device__ __forceinline__ uint64_t lz_policy_evict_last()
 // accumulator layout), the A fragments are the trip's own rows of X read straight from global (L1 hits: a stencil row
 // has just gathered its diagonal neighbour), 8 more DMMAs per trip.
 #define SPMM_GST 20            // row stride (doubles) of the per-warp Gram staging tile: conflict-free fragment reads
-template <int BW, int CW, int STAGES, int CAP, int MINB, bool FSUB, bool GRAM = false>
+template <int BW, int CW, int STAGES, int CAP, int MINB, bool FSUB, bool GRAM = false, int GIN = 4>
 __global__ void __launch_bounds__((1 + CW) * 32, MINB)
 k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
           const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
@@ -226,7 +226,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     // row-major panel otherwise: power-law operators run wide panels slice by slice so that the rows gathered again
     // and again -- the hubs' -- fit in L2)
     static_assert(!FSUB || BW == 16, "the fused subtraction is written for 16-column panels");
-    constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
+    constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = GIN;     // G gathered rows in flight per lane
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *vals_s = reinterpret_cast<double *>(smem_raw);
     int *cols_s = reinterpret_cast<int *>(smem_raw + 8 * (size_t)CAP * STAGES);
@@ -423,14 +423,14 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     }
 }
 
-template <int BW, int CW, int STAGES, int MINB, bool FSUB, bool GRAM = false>
+template <int BW, int CW, int STAGES, int MINB, bool FSUB, bool GRAM = false, int GIN = 4>
 static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W,
                                 const double *Q0, const double *Bm, int run, int part, int64_t ldx = BW, int64_t ldw = BW,
                                 const double *Xown = nullptr, double *gpart = nullptr, int *grid_out = nullptr)
 {
     constexpr int CAP = 2048;
     const size_t smem = (size_t)STAGES * (CAP * 12 + SPMM_WS_RCAP * 4) + 16 * STAGES;
-    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM>, (int)smem));
+    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM, GIN>, (int)smem));
     const int nch = A->mm_n_chunks;
     LzChunkRange cr = {0, nch, 0, nch};
     if (part == 1) cr = {A->mm_bnd_lo, A->mm_bnd_hi - A->mm_bnd_lo, 0, A->mm_bnd_hi - A->mm_bnd_lo};
@@ -440,7 +440,7 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
     if (grid > cr.total) grid = cr.total;
     const int per_cta = (cr.total + grid - 1) / grid;
     if (grid_out) *grid_out = grid;
-    k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
+    k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM, GIN><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
         nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
         ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, ldx, ldw, Xown, gpart);   // hint bit 1: evict-first on the matrix streams
     return LZ_OK;
@@ -455,6 +455,18 @@ static int launch_spmm_ws(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr
     // dev-time knob LZ_SPMM_RUN = chunks per run of the chunk map (default 1; 0: one contiguous range per CTA)
     const int run = ctx->knobs.spmm_run;
     if constexpr (BW == 16) {
+        // LZ_SPMM_SHAPE=1 (A/B): 8 gathered rows in flight per lane (a 7-point row in ONE round trip instead of two) at
+        // 7-8 compute warps per CTA, against 4 in flight at 11-12 warps
+        if (ctx->knobs.spmm_shape == 1) {
+            if (Q0 && gpart) return launch_spmm_ws_shape<16, 7, 2, 2, true, true, 8>(ctx, A, rowptr, n_rows, X, W, Q0, Bm, run, part, 16, 16, Xown, gpart, grid_out);
+            if (Q0) return launch_spmm_ws_shape<16, 8, 2, 2, true, false, 8>(ctx, A, rowptr, n_rows, X, W, Q0, Bm, run, part);
+            return launch_spmm_ws_shape<16, 8, 2, 2, false, false, 8>(ctx, A, rowptr, n_rows, X, W, nullptr, nullptr, run, part);
+        }
+        if (ctx->knobs.spmm_shape == 2) {
+            if (Q0 && gpart) return launch_spmm_ws_shape<16, 9, 2, 2, true, true, 6>(ctx, A, rowptr, n_rows, X, W, Q0, Bm, run, part, 16, 16, Xown, gpart, grid_out);
+            if (Q0) return launch_spmm_ws_shape<16, 10, 2, 2, true, false, 6>(ctx, A, rowptr, n_rows, X, W, Q0, Bm, run, part);
+            return launch_spmm_ws_shape<16, 10, 2, 2, false, false, 6>(ctx, A, rowptr, n_rows, X, W, nullptr, nullptr, run, part);
+        }
         if (Q0 && gpart) return launch_spmm_ws_shape<16, LZ_SPMM_GRAM_CW, 2, 2, true, true>(ctx, A, rowptr, n_rows, X, W, Q0, Bm, run, part, 16, 16, Xown, gpart, grid_out);
         if (Q0) return launch_spmm_ws_shape<16, 12, 2, 2, true>(ctx, A, rowptr, n_rows, X, W, Q0, Bm, run, part);
     }

@@ -60,8 +60,10 @@ struct LzKnobs {
     int no_fold;            // LZ_NO_FOLD: keep pass B + separate alpha in the full-reorth vector path
     int spmm_kernel;        // LZ_SPMM_KERNEL: 0 default choice, 1 k_spmm_ws (round-robin chunks), 2 k_spmm_win (staged X window)
     int block_cgs_fuse;     // LZ_BLOCK_CGS_FUSE: 1 (default) fused update+project in the block CGS2, 0 four streams
+    int no_transpose;       // LZ_NO_TRANSPOSE: the SpMV gather warps always walk a chunk in storage order
     int cgs_rpt;            // LZ_CGS_RPT: rows per thread of the streaming CGS kernels (0 auto, 4, 8)
     int cgs_fuse_min_k;     // LZ_CGS_FUSE_MIN_K: smallest number of basis columns for which CGS2 uses the fused update+project kernel
+    int spmm_shape;         // LZ_SPMM_SHAPE: b = 16 SpMM kernel shape (0 shipped; 1: 8 gathers in flight, 7-8 warps; 2: 6 in flight, 9-10 warps)
     int spmm_slice;         // LZ_SPMM_SLICE: columns per pass of the SpMM on row-split (power-law) operators (default 8; >= b: one pass)
     int panel_pad;          // LZ_PANEL_PAD: extra doubles between the block driver's panels (they are 2^k bytes apart on 2^k grids)
     int no_spmm_gram;       // LZ_NO_SPMM_GRAM: the fused b = 16 SpMM leaves Q_j^T W to a separate Gram pass
@@ -233,6 +235,7 @@ struct lz_matrix {
     int tile, cap;           // nnz per chunk (target) and shared-memory product slots per CTA
     int mm_n_chunks;         // second schedule with LZ_SPMM_TILE-sized chunks for the SpMM kernel
     int32_t *mm_chunk_row, *mm_chunk_ptr;
+    int32_t *chunk_ulen, *mm_chunk_ulen;   // per chunk: the common (odd) row length, or 0 (lz_csr.cu: k_chunk_ulen)
     int tma_ok;              // vals / colidx 16-byte aligned: bulk-copy staged kernel usable
     int max_row_nnz;
     // row-split view for operators with long rows (NULL otherwise): virtual row pointers over the same

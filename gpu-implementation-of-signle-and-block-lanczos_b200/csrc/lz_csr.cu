@@ -28,6 +28,25 @@ __global__ void k_chunk_rows(int64_t n_rows, int64_t nnz, const int32_t *__restr
     chunk_ptr[c] = rowptr[lo];
 }
 
+// chunk_ulen[c] = L when every row of chunk c has exactly L entries and L is odd (stencil interiors: 5, 7, 27 ...), else 0.
+// The SpMV gather warps then walk a chunk TRANSPOSED (entry s of 32 consecutive rows per warp load): the gathered x
+// entries of a warp are contiguous instead of L scattered groups (L1 wavefronts per load: ~L -> 2), and the odd stride
+// keeps the shared-memory accesses (nearly) conflict-free.
+__global__ void k_chunk_ulen(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ rowptr, int32_t *__restrict__ ulen)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int r0 = chunk_row[c], r1 = chunk_row[c + 1];
+    int L = 0;
+    if (r1 > r0) {
+        L = rowptr[r0 + 1] - rowptr[r0];
+        for (int r = r0 + 1; r < r1 && L; ++r)
+            if (rowptr[r + 1] - rowptr[r] != L) L = 0;
+        if (!(L & 1) || L > 63) L = 0;
+    }
+    ulen[c] = L;
+}
+
 __global__ void k_max_row(int64_t n_rows, const int32_t *__restrict__ rowptr, int *out)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,6 +200,7 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     A->n_chunks = (int)nch;
     LZ_CUDA(cudaMalloc(&A->chunk_row, sizeof(int32_t) * (nch + 1)));
     LZ_CUDA(cudaMalloc(&A->chunk_ptr, sizeof(int32_t) * (nch + 1)));
+    LZ_CUDA(cudaMalloc(&A->chunk_ulen, sizeof(int32_t) * (nch + 1)));
     A->k_colidx = A->bin_colidx ? A->bin_colidx : A->colidx;       // what the SpMV / SpMM kernels stream
     A->k_vals = A->bin_vals ? A->bin_vals : A->vals;
     A->tma_ok = ((uintptr_t)A->k_vals % 16 == 0) && ((uintptr_t)A->k_colidx % 16 == 0);
@@ -192,7 +212,12 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     A->mm_n_chunks = (int)mch;
     LZ_CUDA(cudaMalloc(&A->mm_chunk_row, sizeof(int32_t) * (mch + 1)));
     LZ_CUDA(cudaMalloc(&A->mm_chunk_ptr, sizeof(int32_t) * (mch + 1)));
+    LZ_CUDA(cudaMalloc(&A->mm_chunk_ulen, sizeof(int32_t) * (mch + 1)));
     k_chunk_rows<<<(unsigned)((mch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)mch, LZ_SPMM_TILE, A->mm_chunk_row, A->mm_chunk_ptr);
+    LZ_LAUNCH_CHECK(ctx);
+    k_chunk_ulen<<<(unsigned)((nch + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->chunk_row, rp, A->chunk_ulen);
+    LZ_LAUNCH_CHECK(ctx);
+    k_chunk_ulen<<<(unsigned)((mch + 255) / 256), 256, 0, ctx->stream>>>((int)mch, A->mm_chunk_row, rp, A->mm_chunk_ulen);
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     return LZ_OK;
@@ -586,6 +611,8 @@ int lz_matrix_destroy(lz_matrix *A)
     cudaFree(A->chunk_ptr);
     cudaFree(A->mm_chunk_row);
     cudaFree(A->mm_chunk_ptr);
+    cudaFree(A->chunk_ulen);
+    cudaFree(A->mm_chunk_ulen);
     cudaFree(A->vrowptr);
     cudaFree(A->vstart);
     cudaFree(A->ybar);

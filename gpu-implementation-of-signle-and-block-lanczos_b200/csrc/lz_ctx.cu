@@ -74,8 +74,10 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     k.rmat_reorder = env_int("LZ_REORDER", 1);
     k.panel_pad = env_int("LZ_PANEL_PAD", 0);
     k.spmm_slice = env_int("LZ_SPMM_SLICE", 0);
+    k.spmm_shape = env_int("LZ_SPMM_SHAPE", 0);
     k.cgs_fuse_min_k = env_int("LZ_CGS_FUSE_MIN_K", 64);
     k.cgs_rpt = env_int("LZ_CGS_RPT", 0);
+    k.no_transpose = env_set("LZ_NO_TRANSPOSE");
     k.no_spmm_fuse = env_set("LZ_NO_SPMM_FUSE");
     k.no_spmm_gram = env_set("LZ_NO_SPMM_GRAM");
     *out = c;

@@ -260,6 +260,7 @@ __device__ __forceinline__ void lz_mbar_arrive(uint64_t *bar)
 template <int MODE, int GW, int RW, int STAGES, int CAP, int MINB = 1>
 __global__ void __launch_bounds__((1 + GW + RW) * 32, MINB)
 k_csr_spmv_ws(const LzChunkRange cr, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
+              const int32_t *__restrict__ chunk_ulen /* NULL: storage order */,
               const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
               const LzPassA args, const int blocked, const int hint)
@@ -319,13 +320,21 @@ k_csr_spmv_ws(const LzChunkRange cr, const int32_t *__restrict__ chunk_row, cons
     } else if (warp <= GW) {
         // ------------------------------------------------------------------ gather warps
         const int gtid = tid - 32;
-        int p0 = 0, p1 = 0;
-        if (first < last) { p0 = chunk_ptr[cmap(first)]; p1 = chunk_ptr[cmap(first) + 1]; }
+        int p0 = 0, p1 = 0, nr0 = 0, nr1 = 0, nul = 0;
+        if (first < last) {
+            const int c0 = cmap(first);
+            p0 = chunk_ptr[c0]; p1 = chunk_ptr[c0 + 1];
+            if (chunk_ulen) { nul = chunk_ulen[c0]; nr0 = chunk_row[c0]; nr1 = chunk_row[c0 + 1]; }
+        }
         int it = 0;
         for (int c = first; c < last; c += step, ++it) {
             const int slot = it % STAGES;
-            const int cp0 = p0, cp1 = p1;
-            if (c + step < last) { p0 = chunk_ptr[cmap(c + step)]; p1 = chunk_ptr[cmap(c + step) + 1]; }
+            const int cp0 = p0, cp1 = p1, L = nul, R = nr1 - nr0;
+            if (c + step < last) {
+                const int cn = cmap(c + step);
+                p0 = chunk_ptr[cn]; p1 = chunk_ptr[cn + 1];
+                if (chunk_ulen) { nul = chunk_ulen[cn]; nr0 = chunk_row[cn]; nr1 = chunk_row[cn + 1]; }
+            }
             const int a0 = cp0 & ~3, cnt = cp1 - a0, cnt4 = cnt & ~3;
             double *vs = vals_s + (size_t)slot * CAP;
             const int *cs = cols_s + (size_t)slot * CAP;
@@ -335,6 +344,30 @@ k_csr_spmv_ws(const LzChunkRange cr, const int32_t *__restrict__ chunk_row, cons
                     const int k = cnt4 + gtid;
                     vs[k] = __dmul_rn(vals[a0 + k], epi.xs(__ldg(x + colidx[a0 + k])));
                 }
+                if (L > 0) {
+                    // uniform chunk: R rows of L entries.  Walk it transposed -- t = s * R + r -> entry (cp0 - a0) + r * L + s --
+                    // so a warp load gathers entry s of 32 consecutive rows (contiguous x for a stencil)
+                    const int head = cp0 - a0, total = R * L;
+                    const unsigned inv = 0xFFFFFFFFu / (unsigned)R + 1u;          // floor(t / R) = umulhi(t, inv) for t * R < 2^32
+                    auto entry = [&](int t) -> int {                              // -1: past the chunk / in the tail
+                        const int s = (int)__umulhi((unsigned)t, inv), r = t - s * R;
+                        const int k = head + r * L + s;
+                        return (t < total && k < cnt4) ? k : -1;
+                    };
+                    for (int base = gtid; base < total; base += 4 * GT) {       // (4 in flight: the kernel is register-tight)
+                        double xv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = entry(base + u * GT);
+                            xv[u] = k >= 0 ? __ldg(x + cs[k]) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = entry(base + u * GT);
+                            if (k >= 0) vs[k] = __dmul_rn(vs[k], epi.xs(xv[u]));
+                        }
+                    }
+                } else
                 for (int base = gtid; base < cnt4; base += 8 * GT) {
                     double xv[8];
 #pragma unroll
@@ -450,8 +483,9 @@ static inline int lz_launch_ws_variant(lz_ctx *ctx, const lz_matrix *A, const do
     if (cr.total <= 0) return LZ_OK;
     int grid = ctx->sm_count * ctas_per_sm;
     if (grid > cr.total) grid = cr.total;
+    const int32_t *ulen = ctx->knobs.no_transpose ? nullptr : (coarse ? A->mm_chunk_ulen : A->chunk_ulen);
     k_csr_spmv_ws<MODE, GW, RW, STAGES, CAP, MINB><<<grid, (1 + GW + RW) * 32, smem, ctx->stream>>>(
-        cr, chunk_row, chunk_ptr, A->vrowptr ? A->vrowptr : A->rowptr, A->k_colidx, A->k_vals, x, y, args, blocked,
+        cr, chunk_row, chunk_ptr, ulen, A->vrowptr ? A->vrowptr : A->rowptr, A->k_colidx, A->k_vals, x, y, args, blocked,
         ctx->knobs.spmv_hint);      // evict-first on the matrix streams measured 4-5 % slower: off
     return LZ_OK;
 }
