@@ -189,6 +189,7 @@ struct LzArEpi {
     double *copy_dst; int copy_idx;     // copy_dst[0] = buf[copy_idx]           (alpha_j = c1[j]); NULL: skip
     double *beta, *invb; int *flags;    // beta[jn] = sqrt(buf[0]), invb[jn] = 1/beta[jn], breakdown flag; beta NULL: skip
     int jn;
+    int *dgks_flag; const double *dgks_before;   // *dgks_flag = buf[0] < 0.5 * *dgks_before (DGKS test on the reduced norm); NULL: skip
 };
 int lz_comm_allreduce_sum(lz_ctx *ctx, double *buf, size_t count, const LzArEpi *epi = nullptr);
 // u points at the local rows; hlo entries are received just below it, hhi entries just above u[n).

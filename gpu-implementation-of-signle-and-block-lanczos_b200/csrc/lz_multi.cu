@@ -109,6 +109,7 @@ __device__ __forceinline__ void lz_ar_epilogue(const LzArEpi &e, const double *b
         e.invb[e.jn] = 1.0 / b;
         if (!isfinite(t) || t == 0.0) atomicMin(e.flags, e.jn);
     }
+    if (e.dgks_flag) *e.dgks_flag = (buf[0] < 0.5 * (*e.dgks_before)) ? 1 : 0;
 }
 
 __global__ void k_ar_epilogue(const LzArEpi e, const double *buf) { lz_ar_epilogue(e, buf); }

@@ -72,15 +72,17 @@ struct LzFinal {
     unsigned long long seq;
 };
 
-__device__ __forceinline__ void lz_finalize_beta(const LzFinal &f, double total)
+// returns the total it finalised with (all-reduced over the ranks in peer mode)
+__device__ __forceinline__ double lz_finalize_beta(const LzFinal &f, double total)
 {
     if (f.pd) lz_peer_sum_thread<1>(f.pd, f.seq, &total);
     *f.nrm2_out = total;
-    if (!f.finalize) return;
+    if (!f.finalize) return total;
     const double b = sqrt(total);
     if (f.beta) f.beta[f.jn] = b;
     f.invb[f.jn] = 1.0 / b;
     if (!(isfinite(total)) || total == 0.0) atomicMin(f.flags + F_BREAKDOWN, f.jn);   // vector.hpp:233-244
+    return total;
 }
 
 template <bool VEC>
@@ -388,7 +390,12 @@ k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t
         // (rank 0 contributes it, the others zero) so that the all-reduce + finalisation that follows changes nothing
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             if (fin.pd) { double z = 0.0; lz_peer_sum_thread<1>(fin.pd, fin.seq, &z); }
-            else if (skip_share >= 0) *fin.nrm2_out = skip_share ? *nrm2_before : 0.0;
+            else if (skip_share >= 0) {
+                // bit 0: this is rank 0 (it carries the value, the others zero); bit 1: the norm to keep is the one the previous
+                // sweep left in nrm2_out (DGKS), otherwise the one pass B left (selective)
+                const double keep = (skip_share & 2) ? *fin.nrm2_out : *nrm2_before;
+                *fin.nrm2_out = (skip_share & 1) ? keep : 0.0;
+            }
         }
         return;
     }
@@ -448,9 +455,10 @@ k_cgs_update(int64_t n, int K, const double *__restrict__ V, int64_t ts, int64_t
     acc = lz_block_sum<VT>(acc, red);
     double total;
     if (lz_grid_sum<VT, 1>(&acc, partials, ticket, red, &total) && threadIdx.x == 0) {
-        lz_finalize_beta(fin, total);
-        // DGKS: a second sweep is needed only if this one removed a large part of w
-        if (dgks_test) flags[F_SECOND_SWEEP] = (total < 0.5 * (*nrm2_before)) ? 1 : 0;
+        total = lz_finalize_beta(fin, total);
+        // DGKS: a second sweep is needed only if this one removed a large part of w.  (NCCL-mode sharded runs hold only
+        // the local share here: their test runs in the epilogue of the all-reduce that follows, k_ar_epilogue.)
+        if (dgks_test && (fin.finalize || !fin.pd)) flags[F_SECOND_SWEEP] = (total < 0.5 * (*nrm2_before)) ? 1 : 0;
     }
 }
 
@@ -484,12 +492,13 @@ static LzFinal arm_final(lz_ctx *ctx, const LzFinal &fin, bool sharded, bool wan
     return f;
 }
 
-static int finish_norm(lz_ctx *ctx, const LzFinal &f, bool sharded, bool want_norm)
+static int finish_norm(lz_ctx *ctx, const LzFinal &f, bool sharded, bool want_norm, int dgks_test = 0)
 {
     if (!sharded || !want_norm || lz_comm_peer(ctx)) return LZ_OK;
     LzArEpi e;
     memset(&e, 0, sizeof(e));
     e.beta = f.beta; e.invb = f.invb; e.flags = f.flags + F_BREAKDOWN; e.jn = f.jn;
+    if (dgks_test) { e.dgks_flag = f.flags + F_SECOND_SWEEP; e.dgks_before = ctx->scalars + S_NRM2_BEFORE; }
     return lz_comm_allreduce_sum(ctx, f.nrm2_out, 1, &e);
 }
 
@@ -523,7 +532,7 @@ static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, doub
     const unsigned want = stream_grid(ctx, n, VT * rpt);
     const unsigned grid = want < cap ? want : cap;
     const LzFinal f = arm_final(ctx, fin, sharded, want_norm);
-    const int share = (sharded && want_norm && !f.pd) ? (lz_comm_rank(ctx) == 0 ? 1 : 0) : -1;
+    const int share = (sharded && want_norm && !f.pd) ? ((lz_comm_rank(ctx) == 0 ? 1 : 0) | (ctx->vrun && ctx->vrun->reorth == LZ_REORTH_FULL_DGKS ? 2 : 0)) : -1;
     lz_prof_begin(ctx, LZ_K_UPDATE, 8.0 * (double)n * (K + 2));
     if (rpt == 8)
         k_cgs_update<8><<<grid, VT, sizeof(double) * (size_t)K, ctx->stream>>>(
@@ -533,7 +542,7 @@ static int launch_cgs_update(lz_ctx *ctx, const LzCgs &g, int64_t n, int K, doub
             n, K, g.V, g.ts, g.cs, w, g.c, ctx->partials, ctx->tickets + T_UPD, f, ctx->flags, need_flag, dgks_test, ctx->scalars + S_NRM2_BEFORE, share);
     LZ_LAUNCH_CHECK(ctx);
     lz_prof_end(ctx);
-    return finish_norm(ctx, f, sharded, want_norm);
+    return finish_norm(ctx, f, sharded, want_norm, dgks_test);
 }
 
 // partial coefficients -> c (fixed order), all-reduced over the ranks when sharded; alpha_out (optional) receives
@@ -692,7 +701,6 @@ int lz_vec_setup(lz_ctx *ctx, const lz_matrix *A, int m, int64_t lc, int reorth,
     LZ_CHECK(sharded || (hlo == 0 && hhi == 0), LZ_ERR_INVALID, "lz_vector_lanczos: a sharded operator needs lz_comm_init");
     LZ_CHECK(lc >= -1 && lc < n, LZ_ERR_INVALID, "lz_vector_lanczos: lc %lld out of range", (long long)lc);
     LZ_CHECK(reorth >= LZ_REORTH_NONE && reorth <= LZ_REORTH_SELECTIVE, LZ_ERR_INVALID, "lz_vector_lanczos: reorth mode %d", reorth);
-    LZ_CHECK(!(sharded && reorth == LZ_REORTH_FULL_DGKS), LZ_ERR_UNSUPPORTED, "lz_vector_lanczos: DGKS reorthogonalisation is single-GPU only");
     LZ_CHECK(3 * m + 3 + 16 + (reorth == LZ_REORTH_SELECTIVE ? 3 * (m + 2) : 0) <= SB_VECTOR_LIMIT, LZ_ERR_UNSUPPORTED,
              "lz_vector_lanczos: m = %d exceeds the scalar bank", m);
     // three rotating work vectors (the reference's q0, q1, w: test_lanczos.cu:57-59), each laid out

@@ -50,12 +50,12 @@ for tag, env in (("peer+overlap", {}), ("nccl+overlap", {"LZ_COMM": "1"}), ("pee
         lz.check(lz.lib().lz_partition_rows(n, gran, world, rank, C.byref(lo), C.byref(hi)))
         bfull = orc.start_vector(n)
         b = torch.from_numpy(bfull[lo.value:hi.value].copy()).cuda()
-        for reorth in (0, 1):
+        for reorth in (0, 1, 2, 3):       # none, CGS2, DGKS, selective (oracle: CGS2 for every reorthogonalising mode)
             al = torch.zeros(m, dtype=torch.float64, device="cuda"); be = torch.zeros(m, dtype=torch.float64, device="cuda")
             for rep in range(2):      # twice: the second solve reuses the arena and continues the sequence numbers
                 lz.check(lz.lib().lz_vector_lanczos_sharded(ctx.h, A.h, b.data_ptr(), m, reorth, al.data_ptr(), be.data_ptr()))
             ctx.sync()
-            ref = orc.vector_lanczos(csr, bfull, m, reorth=reorth)
+            ref = orc.vector_lanczos(csr, bfull, m, reorth=min(reorth, 1))
             a, bb = al.cpu().numpy(), be.cpu().numpy()
             scale = np.maximum(np.abs(ref["alpha"]), np.mean(ref["beta"][1:]))
             k = min(m, 50)
