@@ -60,7 +60,8 @@ for tag, env in (("peer+overlap", {}), ("nccl+overlap", {"LZ_COMM": "1"}), ("pee
             scale = np.maximum(np.abs(ref["alpha"]), np.mean(ref["beta"][1:]))
             k = min(m, 50)
             ea = np.max(np.abs(a - ref["alpha"])[:k] / scale[:k]); eb = np.max((np.abs(bb - ref["beta"]) / ref["beta"])[:k])
-            assert ea < 1e-10 and eb < 1e-10, (tag, kind, dims, reorth, ea, eb)
+            tol = 1e-10 if reorth < 3 else 1e-8       # selective: semi-orthogonal basis, coefficients agree to O(eps ||A||) in theory
+            assert ea < tol and eb < tol, (tag, kind, dims, reorth, ea, eb)
             # every rank holds the same coefficients bit for bit
             t = al.clone(); dist.broadcast(t, 0); assert torch.equal(t, al), (tag, kind, reorth)
             results[(tag, kind, dims, reorth)] = (ea, eb)
