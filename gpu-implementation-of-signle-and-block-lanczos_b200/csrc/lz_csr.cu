@@ -29,9 +29,11 @@ __global__ void k_chunk_rows(int64_t n_rows, int64_t nnz, const int32_t *__restr
 }
 
 // chunk_ulen[c] = L when every row of chunk c has exactly L entries and L is odd (stencil interiors: 5, 7, 27 ...), else 0.
-// The SpMV gather warps then walk a chunk TRANSPOSED (entry s of 32 consecutive rows per warp load): the gathered x
-// entries of a warp are contiguous instead of L scattered groups (L1 wavefronts per load: ~L -> 2), and the odd stride
-// keeps the shared-memory accesses (nearly) conflict-free.
+// With LZ_TRANSPOSE=1 the SpMV gather warps walk such a chunk TRANSPOSED (entry s of 32 consecutive rows per warp
+// load): the gathered x entries of a warp are contiguous instead of L scattered groups (L1 wavefronts per load: ~L -> 2).
+// Measured SLOWER than the storage-order walk (256^3 fused step 0.549 vs 0.438 ms, 4096^2 0.462 vs 0.338 ms: the index
+// arithmetic, the strided shared-memory accesses and half the loads in flight cost more than the wavefronts saved), so
+// it is an opt-in experiment, not the shipped path (profiles/r02_spmv.md).
 __global__ void k_chunk_ulen(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ rowptr, int32_t *__restrict__ ulen)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
