@@ -60,6 +60,7 @@ struct LzKnobs {
     int no_fold;            // LZ_NO_FOLD: keep pass B + separate alpha in the full-reorth vector path
     int spmm_kernel;        // LZ_SPMM_KERNEL: 0 default choice, 1 k_spmm_ws (round-robin chunks), 2 k_spmm_win (staged X window)
     int block_cgs_fuse;     // LZ_BLOCK_CGS_FUSE: 1 (default) fused update+project in the block CGS2, 0 four streams
+    int split_l;            // LZ_SPLIT_L: longest virtual row of a row-split (power-law) operator
     int no_transpose;       // 1 unless LZ_TRANSPOSE is set: the SpMV gather warps walk a chunk in storage order (the transposed walk of uniform chunks measured slower)
     int cgs_rpt;            // LZ_CGS_RPT: rows per thread of the streaming CGS kernels (0 auto, 4, 8)
     int cgs_fuse_min_k;     // LZ_CGS_FUSE_MIN_K: smallest number of basis columns for which CGS2 uses the fused update+project kernel

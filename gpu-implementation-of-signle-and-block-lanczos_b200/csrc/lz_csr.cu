@@ -59,22 +59,22 @@ __global__ void k_max_row(int64_t n_rows, const int32_t *__restrict__ rowptr, in
 }
 
 // pieces per row, then virtual row pointers (row r's k-th piece starts at rowptr[r] + k*LZ_SPLIT_L)
-__global__ void k_split_count(int64_t n_rows, const int32_t *__restrict__ rowptr, int32_t *__restrict__ pieces)
+__global__ void k_split_count(int64_t n_rows, const int32_t *__restrict__ rowptr, int32_t *__restrict__ pieces, int split_l)
 {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rows) return;
     if (r == n_rows) { pieces[r] = 0; return; }
     const int len = rowptr[r + 1] - rowptr[r];
-    pieces[r] = len <= LZ_SPLIT_L ? 1 : (len + LZ_SPLIT_L - 1) / LZ_SPLIT_L;
+    pieces[r] = len <= split_l ? 1 : (len + split_l - 1) / split_l;
 }
 __global__ void k_split_fill(int64_t n_rows, int64_t nnz, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ vstart,
-                             int32_t *__restrict__ vrowptr)
+                             int32_t *__restrict__ vrowptr, int split_l)
 {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rows) return;
     if (r == n_rows) { vrowptr[vstart[n_rows]] = (int32_t)nnz; return; }
     const int v0 = vstart[r], v1 = vstart[r + 1], s = rowptr[r];
-    for (int v = v0; v < v1; ++v) vrowptr[v] = s + (v - v0) * LZ_SPLIT_L;
+    for (int v = v0; v < v1; ++v) vrowptr[v] = s + (v - v0) * split_l;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -125,7 +125,7 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
     int32_t *pieces;
     LZ_CUDA(cudaMalloc(&pieces, sizeof(int32_t) * (n + 1)));
     LZ_CUDA(cudaMalloc(&A->vstart, sizeof(int32_t) * (n + 1)));
-    k_split_count<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->rowptr, pieces);
+    k_split_count<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->rowptr, pieces, ctx->knobs.split_l);
     LZ_LAUNCH_CHECK(ctx);
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pieces, A->vstart, (int)(n + 1), ctx->stream);
@@ -141,7 +141,7 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
     A->n_virtual = nv;
     LZ_CUDA(cudaMalloc(&A->vrowptr, sizeof(int32_t) * ((size_t)nv + 8)));
     LZ_CUDA(cudaMalloc(&A->ybar, sizeof(double) * ((size_t)nv + 8)));
-    k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->csr_nnz, A->rowptr, A->vstart, A->vrowptr);
+    k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->csr_nnz, A->rowptr, A->vstart, A->vrowptr, ctx->knobs.split_l);
     LZ_LAUNCH_CHECK(ctx);
     if (!ctx->knobs.rmat_reorder || (int64_t)nv / LZ_BIN_WINDOW >= (1 << 22)) return LZ_OK;
     // ---- length binning of the virtual rows (see above) ----

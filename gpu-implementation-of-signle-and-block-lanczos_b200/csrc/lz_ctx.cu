@@ -77,6 +77,9 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     k.spmm_shape = env_int("LZ_SPMM_SHAPE", 0);
     k.cgs_fuse_min_k = env_int("LZ_CGS_FUSE_MIN_K", 64);
     k.cgs_rpt = env_int("LZ_CGS_RPT", 0);
+    k.split_l = env_int("LZ_SPLIT_L", LZ_SPLIT_L);
+    if (k.split_l < 8) k.split_l = 8;
+    if (k.split_l > 256) k.split_l = 256;
     k.no_transpose = env_set("LZ_TRANSPOSE") ? 0 : 1;     // measured slower (profiles/r02_spmv.md): opt-in only
     k.no_spmm_fuse = env_set("LZ_NO_SPMM_FUSE");
     k.no_spmm_gram = env_set("LZ_NO_SPMM_GRAM");

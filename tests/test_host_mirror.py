@@ -159,3 +159,39 @@ def test_harness_matrix_market_operator(host_built, orc, tmp_path):
     ref = orc.vector_lanczos((rp, ci, va), orc.start_vector(n), 40, reorth=1)
     assert np.max(np.abs(d["alpha"] - ref["alpha"])) < 1e-10 * np.abs(ref["alpha"]).max()
     assert np.max(np.abs(d["beta"] - ref["beta"]) / ref["beta"]) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["dgks", "selective"])
+def test_harness_reorth_modes_and_residuals(host_built, orc, tmp_path, mode):
+    """--reorth dgks / selective through the mirror's driver signatures, and the residual estimates the harness now prints
+    next to the Ritz values (|beta_m y_m| from lz_last_coupling + lz_ritz)."""
+    stdout, out = run_harness(host_built, ["--matrix", "lap2d", "-N", "120", "-m", "150", "--vector", "--reorth", mode, "--k", "6"], tmp_path)
+    d = orc.read_dump(out)
+    ref = orc.vector_lanczos(orc.lap2d(120, 120), orc.start_vector(120 * 120), 150, reorth=1)
+    tol = 1e-10 if mode == "dgks" else 1e-8
+    assert np.max(np.abs(d["alpha"][:50] - ref["alpha"][:50])) < tol * np.abs(ref["alpha"]).max()
+    T = orc.assemble_T(ref["alpha"], ref["beta"])
+    w, Y = np.linalg.eigh(T)
+    sel = np.r_[np.arange(3), np.arange(147, 150)]
+    assert np.max(np.abs(d["theta"] - w[sel])) < 1e-8 * np.abs(w).max()
+    assert "residual estimates" in stdout and d["resid"].shape == (6,) and np.all(np.isfinite(d["resid"])) and np.all(d["resid"] >= 0)
+    # |beta_m y_m| with beta_m from the oracle's run continued by one step
+    ref2 = orc.vector_lanczos(orc.lap2d(120, 120), orc.start_vector(120 * 120), 151, reorth=1)
+    want = np.abs(ref2["beta"][150] * Y[149, sel])
+    assert np.max(np.abs(d["resid"] - want)) < 1e-8
+
+
+@pytest.mark.gpu
+def test_harness_device_assembled_maxwell_equals_host_assembled(host_built, orc, tmp_path):
+    """--matrix maxwell_dev (lz_gen_maxwell) drives the same run as the host-assembled operator: the operator arrays are
+    bit-identical, so with the same deterministic start vector the coefficients are identical too."""
+    g = load_gold("maxwell_N10_matrix.npz")
+    n, w = int(g["n_rows"]), int(g["width"])
+    csr = orc.ell_to_csr(n, w, g["ell_data"], g["ell_idx"])
+    stdout, out = run_harness(host_built, ["--matrix", "maxwell_dev", "-N", "10", "-m", "60", "--vector"], tmp_path)
+    d = orc.read_dump(out)
+    ref = orc.vector_lanczos(csr, orc.start_vector(n), 60, lc=int(d["lc"]) if "lc" in d else 0)
+    scale = np.maximum(np.abs(ref["alpha"][:50]), np.mean(np.abs(ref["beta"][1:50])))
+    assert np.max(np.abs(d["alpha"][:50] - ref["alpha"][:50]) / scale) < 1e-10
+    assert np.max(np.abs(d["beta"][:50] - ref["beta"][:50]) / np.abs(ref["beta"][:50])) < 1e-10
