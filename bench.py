@@ -177,6 +177,56 @@ def fp64_dgemm_peak():
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def cfg5_leg(ctx, lz, world, rank, dist, barrier):
+    """BASELINE configs[4] (512^3, 100 steps, no reorth) at THIS world size, outside the headline timed region:
+    1 warm-up + 2 timed solves, device-timed, max over ranks."""
+    import torch
+    wl = WORKLOADS["cfg5"]
+    m = wl["m"]
+    n_global = int(np.prod(wl["dims"]))
+    granule = n_global // wl["dims"][-1]
+    A5 = lz.Matrix.laplacian3d_shard(ctx, *wl["dims"], world, rank) if world > 1 else lz.Matrix.laplacian3d(ctx, *wl["dims"])
+    b5 = torch.empty(A5.n_rows, dtype=torch.float64, device="cuda")
+    if world > 1:
+        lo, hi = lz.C.c_int64(), lz.C.c_int64()
+        lz.check(lz.lib().lz_partition_rows(n_global, granule, world, rank, lz.C.byref(lo), lz.C.byref(hi)))
+        full = torch.empty(n_global, dtype=torch.float64, device="cuda")
+        lz.check(lz.lib().lz_gen_start_vector(ctx.h, n_global, 0x5EED, full.data_ptr()))
+        ctx.sync()
+        b5.copy_(full[lo.value:hi.value])
+        del full
+    else:
+        lz.check(lz.lib().lz_gen_start_vector(ctx.h, A5.n_rows, 0x5EED, b5.data_ptr()))
+    al = torch.zeros(m, dtype=torch.float64, device="cuda")
+    be = torch.zeros(m, dtype=torch.float64, device="cuda")
+
+    def solve5():
+        if world > 1:
+            lz.check(lz.lib().lz_vector_lanczos_sharded(ctx.h, A5.h, b5.data_ptr(), m, 0, al.data_ptr(), be.data_ptr()))
+        else:
+            lz.vector_lanczos_async(ctx, A5, b5, m, al, be, reorth=0)
+    solve5()
+    barrier()
+    reps = 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        solve5()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    a5 = al.cpu().numpy()
+    assert np.all(np.isfinite(a5)) and abs(a5[0] - 6.0) < 6.0, "cfg5 leg: bad alpha"
+    A5.close()
+    del b5
+    return {"workload": "cfg5: " + wl["desc"], "n_gpus": world, "iterations_per_s": m * reps / (ms * 1e-3), "ms_per_solve": ms / reps,
+            "alpha_0": float(a5[0]), "beta_last": float(be.cpu().numpy()[m - 1])}
+
+
 def extra_legs(ctx, lz, peak, A2=None, b2=None, m2=300):
     """north_star targets and the reference-CUDA baseline, measured in the same process right after the headline
     (outside its timed region): (a) fused single-vector step on 256^3 as a fraction of HBM peak; (b) block b = 16 step
@@ -462,6 +512,9 @@ def run_gpu(args, wl, rank, world):
     extra = None
     if world == 1 and not args.no_extra and args.workload == "cfg2":
         extra = extra_legs(ctx, lz, peak, A, b, m)
+    if not args.no_extra and args.workload == "cfg2":
+        c5 = cfg5_leg(ctx, lz, world, rank, dist, barrier)          # every rank runs it (sharded solve)
+        extra = dict(extra or {}, cfg5=c5)
 
     def teardown():
         # identical order on every rank: operators, library communicator + context, then torch's

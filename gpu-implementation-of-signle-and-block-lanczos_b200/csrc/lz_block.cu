@@ -300,7 +300,8 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     } else {
         // ------------------------------------------------------------------ compute warps
         const int sub = lane / LW, l = lane % LW;
-        int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0;
+        int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0, trip_base = 0;
+        const bool rotate = !(hint & 16);         // hint bit 16 (LZ_SPMM_HINT=16): A/B switch, restart the deal per chunk
         int v = vchunk(0);
         if (v < n_virtual) { const int c = cmap(v); nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
         for (int it = 0; v < n_virtual; ++it) {
@@ -321,8 +322,14 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
             const int *cs = cols_s + (size_t)slot * CAP;
             const int *rs = rptr_s + (size_t)slot * SPMM_WS_RCAP;
             lz_mbar_wait(&full[slot], (it / STAGES) & 1);
-            // warp-uniform trips over the chunk's rows: RPW rows per trip, row of this lane group = rb + sub
-            for (int64_t rb = (int64_t)r0 + (warp - 1) * RPW; rb < r1; rb += NG) {
+            // warp-uniform trips over the chunk's rows: RPW rows per trip, row of this lane group = rb + sub.  The trips of
+            // ALL chunks of this CTA are dealt round-robin to the warps (trip_base continues across chunks): a chunk has
+            // 27.5 trips on 11-12 warps, and restarting the deal at warp 0 for every chunk gave the same warps the third
+            // trip each time (the ring lets a warp run one chunk ahead, so the rotation evens the load out)
+            const int trips = (int)((r1 - r0 + RPW - 1) / RPW);
+            const int t0 = (((warp - 1) - trip_base) % CW + CW) % CW;
+            trip_base = rotate ? (trip_base + trips) % CW : 0;
+            for (int64_t rb = (int64_t)r0 + (int64_t)t0 * RPW; rb < r1; rb += NG) {
                 const int64_t r = rb + sub;
                 const bool valid = r < r1;
                 int s = 0, e = 0;
@@ -441,7 +448,7 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
     const int per_cta = (cr.total + grid - 1) / grid;
     if (grid_out) *grid_out = grid;
     k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM, GIN><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
-        nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
+        nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->mm_k_colidx, A->mm_k_vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
         ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, ldx, ldw, Xown, gpart);   // hint bit 1: evict-first on the matrix streams
     return LZ_OK;
 }
@@ -638,13 +645,13 @@ static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, 
         }
         LZ_CHECK(part == 0, LZ_ERR_INVALID, "spmm: partial launches need the staged kernel");
 #define CSR_CASE(B)                                                                                                     \
-    if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm); \
-    else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm)
+    if (fuse) k_spmm_rm<B, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->mm_k_colidx, A->mm_k_vals, X, W, Q0, Bm); \
+    else k_spmm_rm<B, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n, rowptr, A->mm_k_colidx, A->mm_k_vals, X, W, Q0, Bm)
         if (bw == 4) { CSR_CASE(4); } else if (bw == 8) { CSR_CASE(8); } else if (bw == 16) { CSR_CASE(16); }
         else if (bw == 32) { CSR_CASE(32); }
         else {
-            if (fuse) k_spmm_rm_any<true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm);
-            else k_spmm_rm_any<false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->k_colidx, A->k_vals, X, W, Q0, Bm);
+            if (fuse) k_spmm_rm_any<true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->mm_k_colidx, A->mm_k_vals, X, W, Q0, Bm);
+            else k_spmm_rm_any<false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(bw, n, rowptr, A->mm_k_colidx, A->mm_k_vals, X, W, Q0, Bm);
         }
 #undef CSR_CASE
     }
@@ -673,10 +680,11 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
 {
     if (!A->vrowptr) return spmm_rm_rows(ctx, A, A->rowptr, A->n_rows, bw, X, W, Q0, Bm, part);
     LZ_CHECK(part == 0, LZ_ERR_INVALID, "row-split operators cannot be launched in parts");
+    LZ_TRY(lz_matrix_prepare_mm(ctx, A));
     // row-split operator: partial rows per virtual row, then an ordered combine
     LZ_CHECK(Q0 == nullptr, LZ_ERR_UNSUPPORTED, "fused subtraction is not available on a row-split operator");
     void *wbar;
-    LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)A->n_virtual * bw + 64, &wbar));
+    LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)A->mm.n_virtual * bw + 64, &wbar));
     // Power-law operator, wide panel: the gathered rows are random.  Running the panel in 8-column slices (64-byte row
     // pieces, four times as many hub rows resident in L2, the matrix streamed once per slice) was measured: every slice
     // costs as much as the whole 32-column pass (R-MAT scale 24: 4 x 54 ms instead of 55 ms, profiles/r02_rmat.md) -- the
@@ -684,16 +692,16 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
     const int slice = ctx->knobs.spmm_slice > 0 ? ctx->knobs.spmm_slice : bw;
     if (bw > slice && bw % slice == 0 && slice == 8 && A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 &&
         ((uintptr_t)X % 32 == 0) && ((uintptr_t)wbar % 32 == 0)) {
-        lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 4.0 * (double)A->n_virtual + 16.0 * (double)A->n_virtual * bw);
+        lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 4.0 * (double)A->mm.n_virtual + 16.0 * (double)A->mm.n_virtual * bw);
         for (int c0 = 0; c0 < bw; c0 += slice) {
-            LZ_TRY((launch_spmm_ws_shape<8, 12, 2, 2, false>(ctx, A, A->vrowptr, A->n_virtual, X + c0, (double *)wbar + c0, nullptr, nullptr,
+            LZ_TRY((launch_spmm_ws_shape<8, 12, 2, 2, false>(ctx, A, A->mm.vrowptr, A->mm.n_virtual, X + c0, (double *)wbar + c0, nullptr, nullptr,
                                                              ctx->knobs.spmm_run, 0, bw, bw)));
             LZ_LAUNCH_CHECK(ctx);
         }
         lz_prof_end(ctx);
     } else
-    LZ_TRY(spmm_rm_rows(ctx, A, A->vrowptr, A->n_virtual, bw, X, (double *)wbar, nullptr, nullptr));
-    k_split_combine_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A->n_rows, bw, A->vstart, A->vpos, (const double *)wbar, W);
+    LZ_TRY(spmm_rm_rows(ctx, A, A->mm.vrowptr, A->mm.n_virtual, bw, X, (double *)wbar, nullptr, nullptr));
+    k_split_combine_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A->n_rows, bw, A->mm.vstart, A->mm.vpos, (const double *)wbar, W);
     LZ_LAUNCH_CHECK(ctx);
     return LZ_OK;
 }
@@ -942,7 +950,10 @@ int lz_block_lanczos_workspace(lz_ctx *ctx, const lz_matrix *A, int bw, int m, i
     // reduction scratch: Gram partials (two products) and, with reorthogonalisation, the projection partials of m blocks
     size_t scratch = (size_t)ctx->sm_count * 4 * 2 * bb;
     if (reorth) scratch = std::max(scratch, (size_t)((m + 1) / 2 + 1) * ctx->sm_count * 2 * 8 * bb + (size_t)m * bb);
-    if (A->vrowptr) scratch = std::max(scratch, (size_t)A->n_virtual * bw + 64);
+    if (A->vrowptr) {
+        LZ_TRY(lz_matrix_prepare_mm(ctx, A));
+        scratch = std::max(scratch, (size_t)A->mm.n_virtual * bw + 64);
+    }
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * scratch, &p));
     return LZ_OK;
 }

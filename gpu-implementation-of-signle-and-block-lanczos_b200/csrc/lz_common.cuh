@@ -60,7 +60,8 @@ struct LzKnobs {
     int no_fold;            // LZ_NO_FOLD: keep pass B + separate alpha in the full-reorth vector path
     int spmm_kernel;        // LZ_SPMM_KERNEL: 0 default choice, 1 k_spmm_ws (round-robin chunks), 2 k_spmm_win (staged X window)
     int block_cgs_fuse;     // LZ_BLOCK_CGS_FUSE: 1 (default) fused update+project in the block CGS2, 0 four streams
-    int split_l;            // LZ_SPLIT_L: longest virtual row of a row-split (power-law) operator
+    int split_l;            // LZ_SPLIT_L: longest virtual row of a row-split (power-law) operator, SpMV
+    int split_l_mm;         // LZ_SPLIT_L_MM: the same for the SpMM's own split (default 32)
     int no_transpose;       // 1 unless LZ_TRANSPOSE is set: the SpMV gather warps walk a chunk in storage order (the transposed walk of uniform chunks measured slower)
     int cgs_rpt;            // LZ_CGS_RPT: rows per thread of the streaming CGS kernels (0 auto, 4, 8)
     int cgs_fuse_min_k;     // LZ_CGS_FUSE_MIN_K: smallest number of basis columns for which CGS2 uses the fused update+project kernel
@@ -217,6 +218,13 @@ enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
 #define LZ_SPLIT_L 256           // rows longer than this are split into virtual rows
 #define LZ_SPMV_CAP 4096         // shared-memory product slots per CTA (32 KB)
 
+// one row split of a power-law operator: virtual rows of <= L entries, length-binned (see lz_csr.cu)
+struct LzSplit {
+    int n_virtual;
+    int32_t *vstart, *vrowptr, *vpos, *bin_colidx;
+    double *bin_vals;
+};
+
 struct lz_matrix {
     lz_ctx *ctx;             // NULL once the owning context has been destroyed (orphaned: only destroy is legal)
     lz_matrix *next, *prev;  // the context's list of live operators
@@ -250,8 +258,15 @@ struct lz_matrix {
     // bin_colidx / bin_vals, and piece v (in vstart numbering) of a row is found at position vpos[v]
     int32_t *vpos, *bin_colidx;
     double *bin_vals;
-    const int32_t *k_colidx; // the arrays the SpMV / SpMM kernels stream (binned copies when present)
+    const int32_t *k_colidx; // the arrays the SpMV kernels stream (binned copies when present)
     const double *k_vals;
+    // The SpMM's own row split (lz_csr.cu, lz_matrix_prepare_mm): the panel product wants SHORT virtual rows (a lane group
+    // gathers one 128..256-byte panel row per entry and a 256-entry row leaves the other groups of its chunk idle), the
+    // SpMV wants long ones (fewer partial sums).  Built on the first panel product unless both lengths agree (then shared).
+    LzSplit mm;
+    int mm_pending, mm_shared;
+    const int32_t *mm_k_colidx;
+    const double *mm_k_vals;
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
     int64_t halo_lo, halo_hi;        // halo entries below / above the local range
     // chunks [bnd_lo, bnd_hi) of the fine schedule (mm_*: of the coarse one) hold only rows that reference no halo
@@ -261,6 +276,7 @@ struct lz_matrix {
 };
 
 int lz_ell4_build_shadow(lz_ctx *ctx, lz_matrix *A);                      // lz_csr.cu
+int lz_matrix_prepare_mm(lz_ctx *ctx, const lz_matrix *A);                // lz_csr.cu: build the SpMM's row split if it is pending
 lz_matrix *lz_new_matrix(lz_ctx *ctx, int fmt, int64_t n_rows, int64_t n_cols, int64_t nnz);
 
 // ---- device helpers -------------------------------------------------------------------

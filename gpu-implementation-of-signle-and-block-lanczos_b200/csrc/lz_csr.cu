@@ -119,29 +119,31 @@ k_bin_copy(int64_t nv, const int32_t *__restrict__ old_ptr, const int32_t *__res
     for (int k = lane; k < len; k += 32) { ncol[dst + k] = colidx[src + k]; nval[dst + k] = vals[src + k]; }
 }
 
-static int build_split(lz_ctx *ctx, lz_matrix *A)
+// One row split of A with virtual rows of <= split_l entries into S (all arrays owned by S; bin_* stay NULL when the
+// length binning is switched off)
+static int build_split(lz_ctx *ctx, const lz_matrix *A, int split_l, LzSplit *S)
 {
     const int64_t n = A->n_rows;
+    memset(S, 0, sizeof(*S));
     int32_t *pieces;
     LZ_CUDA(cudaMalloc(&pieces, sizeof(int32_t) * (n + 1)));
-    LZ_CUDA(cudaMalloc(&A->vstart, sizeof(int32_t) * (n + 1)));
-    k_split_count<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->rowptr, pieces, ctx->knobs.split_l);
+    LZ_CUDA(cudaMalloc(&S->vstart, sizeof(int32_t) * (n + 1)));
+    k_split_count<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->rowptr, pieces, split_l);
     LZ_LAUNCH_CHECK(ctx);
     size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pieces, A->vstart, (int)(n + 1), ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pieces, S->vstart, (int)(n + 1), ctx->stream);
     void *tmp;
     LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pieces, A->vstart, (int)(n + 1), ctx->stream);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pieces, S->vstart, (int)(n + 1), ctx->stream);
     ctx->launches++;
     int32_t nv = 0;
-    LZ_CUDA(cudaMemcpyAsync(&nv, A->vstart + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(&nv, S->vstart + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     LZ_CUDA(cudaFree(tmp));
     LZ_CUDA(cudaFree(pieces));
-    A->n_virtual = nv;
-    LZ_CUDA(cudaMalloc(&A->vrowptr, sizeof(int32_t) * ((size_t)nv + 8)));
-    LZ_CUDA(cudaMalloc(&A->ybar, sizeof(double) * ((size_t)nv + 8)));
-    k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->csr_nnz, A->rowptr, A->vstart, A->vrowptr, ctx->knobs.split_l);
+    S->n_virtual = nv;
+    LZ_CUDA(cudaMalloc(&S->vrowptr, sizeof(int32_t) * ((size_t)nv + 8)));
+    k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->csr_nnz, A->rowptr, S->vstart, S->vrowptr, split_l);
     LZ_LAUNCH_CHECK(ctx);
     if (!ctx->knobs.rmat_reorder || (int64_t)nv / LZ_BIN_WINDOW >= (1 << 22)) return LZ_OK;
     // ---- length binning of the virtual rows (see above) ----
@@ -152,15 +154,15 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
     LZ_CUDA(cudaMalloc(&keys, sizeof(uint32_t) * (size_t)nv)); LZ_CUDA(cudaMalloc(&keys2, sizeof(uint32_t) * (size_t)nv));
     LZ_CUDA(cudaMalloc(&ids, sizeof(int32_t) * (size_t)nv)); LZ_CUDA(cudaMalloc(&perm, sizeof(int32_t) * (size_t)nv));
     LZ_CUDA(cudaMalloc(&lens, sizeof(int32_t) * ((size_t)nv + 1))); LZ_CUDA(cudaMalloc(&nptr, sizeof(int32_t) * ((size_t)nv + 8)));
-    LZ_CUDA(cudaMalloc(&A->vpos, sizeof(int32_t) * (size_t)nv));
-    k_bin_keys<<<gv, 256, 0, ctx->stream>>>(nv, A->vrowptr, keys, ids);
+    LZ_CUDA(cudaMalloc(&S->vpos, sizeof(int32_t) * (size_t)nv));
+    k_bin_keys<<<gv, 256, 0, ctx->stream>>>(nv, S->vrowptr, keys, ids);
     LZ_LAUNCH_CHECK(ctx);
     tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ids, perm, nv, 0, 32, ctx->stream);
     LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
     cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, perm, nv, 0, 32, ctx->stream);   // stable: pieces of one row stay in order
     ctx->launches++;
-    k_bin_lens<<<gv, 256, 0, ctx->stream>>>(nv, A->vrowptr, perm, lens, A->vpos);
+    k_bin_lens<<<gv, 256, 0, ctx->stream>>>(nv, S->vrowptr, perm, lens, S->vpos);
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     LZ_CUDA(cudaFree(tmp));
@@ -171,13 +173,47 @@ static int build_split(lz_ctx *ctx, lz_matrix *A)
     ctx->launches++;
     LZ_CUDA(cudaMalloc(&ncol, sizeof(int32_t) * ((size_t)A->csr_nnz + 8)));
     LZ_CUDA(cudaMalloc(&nval, sizeof(double) * ((size_t)A->csr_nnz + 8)));
-    k_bin_copy<<<(unsigned)(((int64_t)nv * 32 + 255) / 256), 256, 0, ctx->stream>>>(nv, A->vrowptr, nptr, perm, A->colidx, A->vals, ncol, nval);
+    k_bin_copy<<<(unsigned)(((int64_t)nv * 32 + 255) / 256), 256, 0, ctx->stream>>>(nv, S->vrowptr, nptr, perm, A->colidx, A->vals, ncol, nval);
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     LZ_CUDA(cudaFree(tmp)); LZ_CUDA(cudaFree(keys)); LZ_CUDA(cudaFree(keys2)); LZ_CUDA(cudaFree(ids)); LZ_CUDA(cudaFree(perm)); LZ_CUDA(cudaFree(lens));
-    LZ_CUDA(cudaFree(A->vrowptr));
-    A->vrowptr = nptr;              // virtual row pointers in binned order, over the binned copies below
-    A->bin_colidx = ncol; A->bin_vals = nval;
+    LZ_CUDA(cudaFree(S->vrowptr));
+    S->vrowptr = nptr;              // virtual row pointers in binned order, over the binned copies below
+    S->bin_colidx = ncol; S->bin_vals = nval;
+    return LZ_OK;
+}
+
+// the SpMM kernel amortises its per-chunk cost over wider rows: its own, coarser schedule, over the rows of ITS split
+static int build_mm_schedule(lz_ctx *ctx, lz_matrix *A)
+{
+    const int64_t nnz = A->csr_nnz;
+    const int32_t *rp = A->mm.vrowptr ? A->mm.vrowptr : A->rowptr;
+    const int64_t rows = A->mm.vrowptr ? A->mm.n_virtual : A->n_rows;
+    A->mm_k_colidx = A->mm.bin_colidx ? A->mm.bin_colidx : A->colidx;
+    A->mm_k_vals = A->mm.bin_vals ? A->mm.bin_vals : A->vals;
+    int64_t mch = (nnz + LZ_SPMM_TILE - 1) / LZ_SPMM_TILE;
+    if (mch < 1) mch = 1;
+    A->mm_n_chunks = (int)mch;
+    LZ_CUDA(cudaMalloc(&A->mm_chunk_row, sizeof(int32_t) * (mch + 1)));
+    LZ_CUDA(cudaMalloc(&A->mm_chunk_ptr, sizeof(int32_t) * (mch + 1)));
+    LZ_CUDA(cudaMalloc(&A->mm_chunk_ulen, sizeof(int32_t) * (mch + 1)));
+    k_chunk_rows<<<(unsigned)((mch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)mch, LZ_SPMM_TILE, A->mm_chunk_row, A->mm_chunk_ptr);
+    LZ_LAUNCH_CHECK(ctx);
+    k_chunk_ulen<<<(unsigned)((mch + 255) / 256), 256, 0, ctx->stream>>>((int)mch, A->mm_chunk_row, rp, A->mm_chunk_ulen);
+    LZ_LAUNCH_CHECK(ctx);
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+// First panel product on a row-split operator whose SpMM split differs from the SpMV's: build it now (one radix sort and
+// one copy of the entries; the operator handle is logically const, this is its lazily built cache)
+int lz_matrix_prepare_mm(lz_ctx *ctx, const lz_matrix *Ac)
+{
+    if (!Ac->mm_pending) return LZ_OK;
+    lz_matrix *A = const_cast<lz_matrix *>(Ac);
+    LZ_TRY(build_split(ctx, A, ctx->knobs.split_l_mm, &A->mm));
+    LZ_TRY(build_mm_schedule(ctx, A));
+    A->mm_pending = 0;
     return LZ_OK;
 }
 
@@ -193,7 +229,15 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaMemcpyAsync(&A->max_row_nnz, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (A->max_row_nnz > A->cap - A->tile && !ctx->knobs.no_split) LZ_TRY(build_split(ctx, A));   // a long row would push chunks off the streaming path
+    if (A->max_row_nnz > A->cap - A->tile && !ctx->knobs.no_split) {                   // a long row would push chunks off the streaming path
+        LzSplit S;
+        LZ_TRY(build_split(ctx, A, ctx->knobs.split_l, &S));
+        A->n_virtual = S.n_virtual; A->vstart = S.vstart; A->vrowptr = S.vrowptr; A->vpos = S.vpos;
+        A->bin_colidx = S.bin_colidx; A->bin_vals = S.bin_vals;
+        LZ_CUDA(cudaMalloc(&A->ybar, sizeof(double) * ((size_t)S.n_virtual + 8)));
+        if (ctx->knobs.split_l_mm == ctx->knobs.split_l) { A->mm = S; A->mm_shared = 1; }
+        else A->mm_pending = 1;                                                         // built by the first panel product
+    }
     const int32_t *rp = A->vrowptr ? A->vrowptr : A->rowptr;
     const int64_t rows = A->vrowptr ? A->n_virtual : A->n_rows;
     int64_t nch = (nnz + A->tile - 1) / A->tile;
@@ -203,26 +247,16 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     LZ_CUDA(cudaMalloc(&A->chunk_row, sizeof(int32_t) * (nch + 1)));
     LZ_CUDA(cudaMalloc(&A->chunk_ptr, sizeof(int32_t) * (nch + 1)));
     LZ_CUDA(cudaMalloc(&A->chunk_ulen, sizeof(int32_t) * (nch + 1)));
-    A->k_colidx = A->bin_colidx ? A->bin_colidx : A->colidx;       // what the SpMV / SpMM kernels stream
+    A->k_colidx = A->bin_colidx ? A->bin_colidx : A->colidx;       // what the SpMV kernels stream
     A->k_vals = A->bin_vals ? A->bin_vals : A->vals;
     A->tma_ok = ((uintptr_t)A->k_vals % 16 == 0) && ((uintptr_t)A->k_colidx % 16 == 0);
     k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
-    // the SpMM kernel amortises its per-chunk cost over wider rows: its own, coarser schedule
-    int64_t mch = (nnz + LZ_SPMM_TILE - 1) / LZ_SPMM_TILE;
-    if (mch < 1) mch = 1;
-    A->mm_n_chunks = (int)mch;
-    LZ_CUDA(cudaMalloc(&A->mm_chunk_row, sizeof(int32_t) * (mch + 1)));
-    LZ_CUDA(cudaMalloc(&A->mm_chunk_ptr, sizeof(int32_t) * (mch + 1)));
-    LZ_CUDA(cudaMalloc(&A->mm_chunk_ulen, sizeof(int32_t) * (mch + 1)));
-    k_chunk_rows<<<(unsigned)((mch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)mch, LZ_SPMM_TILE, A->mm_chunk_row, A->mm_chunk_ptr);
-    LZ_LAUNCH_CHECK(ctx);
     k_chunk_ulen<<<(unsigned)((nch + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->chunk_row, rp, A->chunk_ulen);
     LZ_LAUNCH_CHECK(ctx);
-    k_chunk_ulen<<<(unsigned)((mch + 255) / 256), 256, 0, ctx->stream>>>((int)mch, A->mm_chunk_row, rp, A->mm_chunk_ulen);
-    LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
-    return LZ_OK;
+    if (A->mm_pending) return LZ_OK;
+    return build_mm_schedule(ctx, A);
 }
 
 static lz_matrix *new_matrix(lz_ctx *ctx, int fmt, int64_t n_rows, int64_t n_cols, int64_t nnz)
@@ -621,6 +655,10 @@ int lz_matrix_destroy(lz_matrix *A)
     cudaFree(A->vpos);
     cudaFree(A->bin_colidx);
     cudaFree(A->bin_vals);
+    if (!A->mm_shared) {
+        cudaFree(A->mm.vstart); cudaFree(A->mm.vrowptr); cudaFree(A->mm.vpos);
+        cudaFree(A->mm.bin_colidx); cudaFree(A->mm.bin_vals);
+    }
     delete A;
     return LZ_OK;
 }

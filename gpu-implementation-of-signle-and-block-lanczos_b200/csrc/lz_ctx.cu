@@ -80,6 +80,9 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     k.split_l = env_int("LZ_SPLIT_L", LZ_SPLIT_L);
     if (k.split_l < 8) k.split_l = 8;
     if (k.split_l > 256) k.split_l = 256;
+    k.split_l_mm = env_int("LZ_SPLIT_L_MM", 32);
+    if (k.split_l_mm < 8) k.split_l_mm = 8;
+    if (k.split_l_mm > 256) k.split_l_mm = 256;
     k.no_transpose = env_set("LZ_TRANSPOSE") ? 0 : 1;     // measured slower (profiles/r02_spmv.md): opt-in only
     k.no_spmm_fuse = env_set("LZ_NO_SPMM_FUSE");
     k.no_spmm_gram = env_set("LZ_NO_SPMM_GRAM");

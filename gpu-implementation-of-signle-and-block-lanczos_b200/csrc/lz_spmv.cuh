@@ -530,7 +530,7 @@ static inline int lz_launch_spmv(lz_ctx *ctx, const lz_matrix *A, const double *
         // 1 + 6 + 9 warps on the coarse (1536-entry) schedule.  LZ_SPMV_VARIANT=3 / 20 force coarse / fine for
         // every mode (profiles/r01_spmv_variants.md).
         const int v = ctx->spmv_variant;
-        const bool coarse = A->mm_chunk_row && (v == 3 || (MODE == LZ_EPI_PLAIN && v != 20));
+        const bool coarse = A->mm_chunk_row && (!A->vrowptr || A->mm_shared) && (v == 3 || (MODE == LZ_EPI_PLAIN && v != 20));   // the coarse schedule of a row-split operator may index the SpMM's own split
         if (coarse) LZ_TRY((lz_launch_ws_variant<MODE, 6, 9, 3, 2048, 3>(ctx, A, x, y, args, 3, 0, true, part)));
         else LZ_TRY((lz_launch_ws_variant<MODE, 3, 5, 3, 1024, 5>(ctx, A, x, y, args, 5, 0, false, part)));
     } else {
