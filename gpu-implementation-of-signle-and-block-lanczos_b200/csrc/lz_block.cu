@@ -604,6 +604,8 @@ __global__ void __launch_bounds__(256) k_cm_to_rm(int64_t n, int bw, const doubl
     }
 }
 
+#include "lz_spmm_xs.cuh"
+
 // can W = A X - Q0 B run as ONE pass on this operator?  (staged kernel with the DMMA subtraction: 16 columns)
 static bool spmm_can_fuse(const lz_ctx *ctx, const lz_matrix *A, int bw)
 {
@@ -633,6 +635,21 @@ static int spmm_rm_rows(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, 
         int64_t want = (n + SPMM_SLAB - 1) / SPMM_SLAB;
         int64_t cap = (int64_t)ctx->sm_count * 8;
         const unsigned grid = (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+        // operators whose chunks reference a few contiguous column ranges (stencils, banded): the rows of X a chunk needs
+        // are bulk-copied into shared memory and gathered from there (lz_spmm_xs.cuh)
+        int xs_st = 0, xs_sb = 0, xs_xw = 0;
+        if (rowptr == A->rowptr && A->rowptr && (bw == 4 || bw == 8 || bw == 16 || bw == 32) && (!fuse || (bw == 16 && !ctx->knobs.no_spmm_fuse)) &&
+            (!fuse || (uintptr_t)Q0 % 32 == 0) && spmm_xs_plan(ctx, A, bw, X, W, part, &xs_st, &xs_sb, &xs_xw)) {
+            if (bw == 4) LZ_TRY((launch_spmm_xs<4, false, false>(ctx, A, X, W, nullptr, nullptr, xs_st, xs_sb, xs_xw)));
+            else if (bw == 8) LZ_TRY((launch_spmm_xs<8, false, false>(ctx, A, X, W, nullptr, nullptr, xs_st, xs_sb, xs_xw)));
+            else if (bw == 32) LZ_TRY((launch_spmm_xs<32, false, false>(ctx, A, X, W, nullptr, nullptr, xs_st, xs_sb, xs_xw)));
+            else if (fuse && gpart) LZ_TRY((launch_spmm_xs<16, true, true>(ctx, A, X, W, Q0, Bm, xs_st, xs_sb, xs_xw, Xown, gpart, grid_out)));
+            else if (fuse) LZ_TRY((launch_spmm_xs<16, true, false>(ctx, A, X, W, Q0, Bm, xs_st, xs_sb, xs_xw)));
+            else LZ_TRY((launch_spmm_xs<16, false, false>(ctx, A, X, W, nullptr, nullptr, xs_st, xs_sb, xs_xw)));
+            LZ_LAUNCH_CHECK(ctx);
+            lz_prof_end(ctx);
+            return LZ_OK;
+        }
         const bool ws = A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 && (!fuse || spmm_can_fuse(ctx, A, bw)) &&
                         ((uintptr_t)X % 32 == 0) && ((uintptr_t)W % 32 == 0) && (!fuse || (uintptr_t)Q0 % 32 == 0);
         if (ws && (bw == 8 || bw == 16 || bw == 32)) {

@@ -61,6 +61,8 @@ struct LzKnobs {
     int spmm_kernel;        // LZ_SPMM_KERNEL: 0 default choice, 1 k_spmm_ws (round-robin chunks), 2 k_spmm_win (staged X window)
     int block_cgs_fuse;     // LZ_BLOCK_CGS_FUSE: 1 (default) fused update+project in the block CGS2, 0 four streams
     int split_l;            // LZ_SPLIT_L: longest virtual row of a row-split (power-law) operator, SpMV
+    int no_xs;              // LZ_NO_XS: never use the operand-staging SpMM
+    int xs_stages;          // LZ_XS_STAGES: ring depth of the operand-staging SpMM (0 = as many as fit, <= 4)
     int split_l_mm;         // LZ_SPLIT_L_MM: the same for the SpMM's own split (default 32)
     int no_transpose;       // 1 unless LZ_TRANSPOSE is set: the SpMV gather warps walk a chunk in storage order (the transposed walk of uniform chunks measured slower)
     int cgs_rpt;            // LZ_CGS_RPT: rows per thread of the streaming CGS kernels (0 auto, 4, 8)
@@ -214,6 +216,10 @@ enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
 // row-aligned nnz chunks: chunk c covers rows [chunk_row[c], chunk_row[c+1])
 #define LZ_SPMV_THREADS 256
 #define LZ_SPMV_TILE 768         // target nnz per SpMV chunk (profiles/r01_spmv_variants.md)
+#define LZ_XS_TILE 512          // target nnz per chunk of the operand-staging SpMM
+#define LZ_XS_SEGCAP 16         // column segments per chunk
+#define LZ_XS_ECAP 768          // entries per chunk the build kernel sorts (tile + longest row must fit)
+#define LZ_XS_MERGE 8           // columns at most this far apart share a segment
 #define LZ_SPMM_TILE 1536        // target nnz per SpMM chunk (k_spmm_ws stages 2048 entries per slot)
 #define LZ_SPLIT_L 256           // rows longer than this are split into virtual rows
 #define LZ_SPMV_CAP 4096         // shared-memory product slots per CTA (32 KB)
@@ -267,6 +273,16 @@ struct lz_matrix {
     int mm_pending, mm_shared;
     const int32_t *mm_k_colidx;
     const double *mm_k_vals;
+    // X-window schedule of the operand-staging SpMM (lz_spmm_xs.cuh; built by lz_matrix_prepare_xs on the first panel
+    // product): chunks of ~LZ_XS_TILE entries; per chunk the distinct columns it references, merged into <= LZ_XS_SEGCAP
+    // contiguous segments (first column, rows) -- the rows of X the chunk gathers, bulk-copied into shared memory -- and
+    // per entry the 16-bit index of its column's row inside that window (streamed instead of the 32-bit column index)
+    int xs_state;                      // 0 not tried yet, 1 usable, -1 this operator does not fit (irregular / long rows)
+    int xs_n_chunks, xs_max_wrows, xs_max_rows, xs_max_entries;
+    int32_t *xs_chunk_row, *xs_chunk_ptr;
+    int2 *xs_meta;                     // per chunk: (segments, window rows)
+    int2 *xs_seg;                      // [chunk][LZ_XS_SEGCAP]: (first column, rows)
+    uint16_t *xs_lidx;                 // per entry
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
     int64_t halo_lo, halo_hi;        // halo entries below / above the local range
     // chunks [bnd_lo, bnd_hi) of the fine schedule (mm_*: of the coarse one) hold only rows that reference no halo
@@ -276,6 +292,7 @@ struct lz_matrix {
 };
 
 int lz_ell4_build_shadow(lz_ctx *ctx, lz_matrix *A);                      // lz_csr.cu
+int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *A);                // lz_csr.cu: build the X-window schedule (sets xs_state)
 int lz_matrix_prepare_mm(lz_ctx *ctx, const lz_matrix *A);                // lz_csr.cu: build the SpMM's row split if it is pending
 lz_matrix *lz_new_matrix(lz_ctx *ctx, int fmt, int64_t n_rows, int64_t n_cols, int64_t nnz);
 

@@ -3,6 +3,9 @@
 // SpMM kernels, and the on-device generators of BASELINE.json's synthetic operators.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+#include <limits.h>
 
 #include <stdlib.h>
 
@@ -202,6 +205,123 @@ static int build_mm_schedule(lz_ctx *ctx, lz_matrix *A)
     k_chunk_ulen<<<(unsigned)((mch + 255) / 256), 256, 0, ctx->stream>>>((int)mch, A->mm_chunk_row, rp, A->mm_chunk_ulen);
     LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// X-window schedule (lz_spmm_xs.cuh).  One CTA per chunk: sort the chunk's column indices, cut the sorted list into
+// segments wherever two neighbours are more than LZ_XS_MERGE apart, lay the segments out back to back (the chunk's
+// window of X rows) and give every entry the window row of its column.  A stencil chunk of 73 rows of a 7-point
+// operator comes out as 5 segments / ~370 rows; an operator whose chunks need more rows than shared memory holds
+// (checked by the caller against xs_max_wrows) keeps the gathering kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_xs_build(const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ colidx, int2 *__restrict__ meta, int2 *__restrict__ seg,
+           uint16_t *__restrict__ lidx, int *__restrict__ stats /* [0] max window rows, [1] failures */)
+{
+    constexpr int IPT = LZ_XS_ECAP / 256;
+    typedef cub::BlockRadixSort<int, 256, IPT> Sort;
+    typedef cub::BlockScan<int, 256> Scan;
+    __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+    __shared__ int sk[LZ_XS_ECAP + 1];
+    __shared__ int sfirst[LZ_XS_SEGCAP], slast[LZ_XS_SEGCAP], soff[LZ_XS_SEGCAP + 1], s_nseg;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int p0 = chunk_ptr[c], p1 = chunk_ptr[c + 1], cnt = p1 - p0;
+    if (cnt > LZ_XS_ECAP) {                       // (uniform) too many entries for the sort: the operator does not qualify
+        if (tid == 0) { atomicAdd(stats + 1, 1); meta[c] = make_int2(0, 0); }
+        return;
+    }
+    int keys[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) { const int e = tid * IPT + i; keys[i] = e < cnt ? colidx[p0 + e] : INT_MAX; }
+    Sort(tmp.sort).Sort(keys);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) sk[tid * IPT + i] = keys[i];
+    if (tid == 0) sk[LZ_XS_ECAP] = INT_MAX;
+    __syncthreads();
+    // segment heads among the valid sorted keys, segment id = (inclusive count of heads) - 1
+    int heads[IPT], ids[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const int e = tid * IPT + i;
+        heads[i] = (e < cnt && (e == 0 || sk[e] - sk[e - 1] > LZ_XS_MERGE)) ? 1 : 0;
+    }
+    int total_heads;
+    Scan(tmp.scan).InclusiveSum(heads, ids, total_heads);
+    if (tid == 0) s_nseg = total_heads;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const int e = tid * IPT + i, id = ids[i] - 1;
+        if (e < cnt && id < LZ_XS_SEGCAP) {
+            if (heads[i]) sfirst[id] = sk[e];
+            if (e == cnt - 1 || sk[e + 1] - sk[e] > LZ_XS_MERGE) slast[id] = sk[e];
+        }
+    }
+    __syncthreads();
+    const int nseg = s_nseg;
+    if (nseg > LZ_XS_SEGCAP) {
+        if (tid == 0) { atomicAdd(stats + 1, 1); meta[c] = make_int2(0, 0); }
+        return;
+    }
+    if (tid == 0) {
+        int off = 0;
+        for (int s2 = 0; s2 < nseg; ++s2) { soff[s2] = off; off += slast[s2] - sfirst[s2] + 1; }
+        soff[nseg] = off;
+        meta[c] = make_int2(nseg, off);
+        atomicMax(stats, off);
+        if (off > 65535) atomicAdd(stats + 1, 1);
+    }
+    __syncthreads();
+    if (tid < LZ_XS_SEGCAP) seg[(size_t)c * LZ_XS_SEGCAP + tid] = tid < nseg ? make_int2(sfirst[tid], slast[tid] - sfirst[tid] + 1) : make_int2(0, 0);
+    if (soff[nseg] > 65535) return;
+    for (int e = tid; e < cnt; e += 256) {
+        const int col = colidx[p0 + e];
+        int s2 = 0;
+        while (s2 + 1 < nseg && col >= sfirst[s2 + 1]) ++s2;
+        lidx[p0 + e] = (uint16_t)(soff[s2] + col - sfirst[s2]);
+    }
+}
+
+__global__ void k_xs_max_rows(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr, int *__restrict__ stats)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    atomicMax(stats + 2, chunk_row[c + 1] - chunk_row[c]);
+    atomicMax(stats + 3, chunk_ptr[c + 1] - chunk_ptr[c]);
+}
+
+// Builds the X-window schedule of an unsplit CSR operator once (first panel product).  Sets xs_state = 1 when every
+// chunk got a window, -1 otherwise; the launch code checks xs_max_wrows against the shared memory of its panel width.
+int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
+{
+    if (Ac->xs_state != 0) return LZ_OK;
+    lz_matrix *A = const_cast<lz_matrix *>(Ac);
+    A->xs_state = -1;
+    if (ctx->knobs.no_xs || !A->rowptr || A->vrowptr || A->csr_nnz <= 0 || A->max_row_nnz > LZ_XS_ECAP - LZ_XS_TILE) return LZ_OK;
+    const int64_t nnz = A->csr_nnz;
+    const int64_t nch = (nnz + LZ_XS_TILE - 1) / LZ_XS_TILE;
+    if (nch >= (int64_t)1 << 30) return LZ_OK;
+    int *stats = ctx->flags + 16;                           // 4 ints of the context's flag bank
+    LZ_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int), ctx->stream));
+    LZ_CUDA(cudaMalloc(&A->xs_chunk_row, sizeof(int32_t) * (nch + 1)));
+    LZ_CUDA(cudaMalloc(&A->xs_chunk_ptr, sizeof(int32_t) * (nch + 1)));
+    LZ_CUDA(cudaMalloc(&A->xs_meta, sizeof(int2) * nch));
+    LZ_CUDA(cudaMalloc(&A->xs_seg, sizeof(int2) * nch * LZ_XS_SEGCAP));
+    LZ_CUDA(cudaMalloc(&A->xs_lidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
+    LZ_CUDA(cudaMemsetAsync(A->xs_lidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), ctx->stream));
+    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, nnz, A->rowptr, (int)nch, LZ_XS_TILE, A->xs_chunk_row, A->xs_chunk_ptr);
+    LZ_LAUNCH_CHECK(ctx);
+    k_xs_max_rows<<<(unsigned)((nch + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->xs_chunk_row, A->xs_chunk_ptr, stats);
+    LZ_LAUNCH_CHECK(ctx);
+    k_xs_build<<<(unsigned)nch, 256, 0, ctx->stream>>>(A->xs_chunk_ptr, A->colidx, A->xs_meta, A->xs_seg, A->xs_lidx, stats);
+    LZ_LAUNCH_CHECK(ctx);
+    int h[4];
+    LZ_CUDA(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    A->xs_n_chunks = (int)nch; A->xs_max_wrows = h[0]; A->xs_max_rows = h[2]; A->xs_max_entries = h[3];
+    if (h[1] == 0 && h[0] > 0) { A->xs_state = 1; return LZ_OK; }
+    cudaFree(A->xs_chunk_row); cudaFree(A->xs_chunk_ptr); cudaFree(A->xs_meta); cudaFree(A->xs_seg); cudaFree(A->xs_lidx);
+    A->xs_chunk_row = A->xs_chunk_ptr = nullptr; A->xs_meta = A->xs_seg = nullptr; A->xs_lidx = nullptr;
     return LZ_OK;
 }
 
@@ -655,6 +775,7 @@ int lz_matrix_destroy(lz_matrix *A)
     cudaFree(A->vpos);
     cudaFree(A->bin_colidx);
     cudaFree(A->bin_vals);
+    cudaFree(A->xs_chunk_row); cudaFree(A->xs_chunk_ptr); cudaFree(A->xs_meta); cudaFree(A->xs_seg); cudaFree(A->xs_lidx);
     if (!A->mm_shared) {
         cudaFree(A->mm.vstart); cudaFree(A->mm.vrowptr); cudaFree(A->mm.vpos);
         cudaFree(A->mm.bin_colidx); cudaFree(A->mm.bin_vals);

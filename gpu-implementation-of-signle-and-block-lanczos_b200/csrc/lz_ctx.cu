@@ -80,6 +80,8 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     k.split_l = env_int("LZ_SPLIT_L", LZ_SPLIT_L);
     if (k.split_l < 8) k.split_l = 8;
     if (k.split_l > 256) k.split_l = 256;
+    k.no_xs = env_set("LZ_NO_XS");
+    k.xs_stages = env_int("LZ_XS_STAGES", 0);
     k.split_l_mm = env_int("LZ_SPLIT_L_MM", 32);
     if (k.split_l_mm < 8) k.split_l_mm = 8;
     if (k.split_l_mm > 256) k.split_l_mm = 256;

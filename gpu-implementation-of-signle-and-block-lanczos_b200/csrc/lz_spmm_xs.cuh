@@ -1,0 +1,302 @@
+// lz_spmm_xs.cuh -- operand-staging SpMM for operators whose chunks reference few contiguous column ranges (stencils,
+// banded operators; the reference's spmm(), kernels/spmv_spmm.hpp:137-199, on such matrices).
+//
+// k_spmm_ws gathers the rows of X with global loads: L1 tag look-ups and ~40 % occupancy bound it (profiles/r02_spmm.md:
+// no unit saturated, the warps wait on L2 hits).  Here the rows a chunk needs -- its X WINDOW, a handful of contiguous
+// row ranges worked out once per operator by k_xs_build (lz_csr.cu) -- are bulk-copied (cp.async.bulk, one copy per
+// segment, issued by the lanes of the producer warp) into the ring slot together with the chunk's values, row pointers
+// and 16-bit window indices, STAGES-1 chunks ahead.  The compute warps then gather from shared memory: no long-latency
+// load is left inside the entry loop, the occupancy needed drops to one 16-warp CTA per SM, and the matrix stream
+// shrinks from 12 to 10 bytes per entry (the 32-bit column index is not read at all).
+//
+// Bank conflicts: a lane owns four adjacent columns (32 bytes) of a row and reads them as two 128-bit loads; a quarter
+// warp (one wavefront) spans two row groups, whose rows sit at arbitrary multiples of 128 bytes.  Lane groups with odd
+// (lane >> 2) read their upper 16 bytes first: the eight lanes of a wavefront then cover all 32 banks.  The accumulators
+// of those lanes are kept in the swapped order and put back once per row.
+//
+// FSUB / GRAM: the fused DMMA subtraction W = A X - Q0 B and the Gram epilogue of k_spmm_ws, unchanged (same fragment
+// labelling, same reduction order inside a CTA); the Q0 and Xown rows of a trip are fetched BEFORE the entry loop (the
+// kernel has registers to spare at one CTA per SM), so their latency overlaps the shared-memory gathers.
+#pragma once
+
+#define LZ_XS_ES 784            // entries staged per ring slot (chunk entries + alignment slack), multiple of 8
+#define LZ_XS_RCAP 640          // row pointers staged per ring slot
+#define LZ_XS_CW 15             // compute warps per CTA (one CTA per SM)
+
+__device__ __forceinline__ void lz_mbar_wait_bounded(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = lz_smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 26)) __trap();          // a lost copy must not hang the GPU
+    }
+}
+
+template <int BW, int CW, bool FSUB, bool GRAM>
+__global__ void __launch_bounds__((1 + CW) * 32, 1)
+k_spmm_xs(const int n_chunks, const int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
+          const int2 *__restrict__ meta, const int2 *__restrict__ seg, const int32_t *__restrict__ rowptr,
+          const uint16_t *__restrict__ lidx, const double *__restrict__ vals, const double *__restrict__ X, double *__restrict__ W,
+          const double *__restrict__ Q0, const double *__restrict__ Bm, const int stages, const int stage_bytes, const int xw_bytes,
+          const int hint, const double *__restrict__ Xown, double *__restrict__ gpart)
+{
+    static_assert(!GRAM || FSUB, "the fused Gram rides on the 8-row trips of the fused subtraction");
+    static_assert(!FSUB || BW == 16, "the fused subtraction is written for 16-column panels");
+    constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // ring slot s: [ X window (xw_bytes) | values (ES*8) | window indices (ES*2) | row pointers (RCAP*4) ]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * stage_bytes);
+    uint64_t *freeb = full + 4;
+    __shared__ double sbs[FSUB ? 8 * 32 : 1];                             // -B in fragment order (see k_spmm_ws)
+    __shared__ __align__(16) double gst[GRAM ? CW * 8 * SPMM_GST : 1];    // per-warp 8 x 16 tile of W for the Gram fragments
+    double gacc[GRAM ? 2 : 1][GRAM ? 2 : 1][2];
+    if (GRAM) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) gacc[a][b][0] = gacc[a][b][1] = 0.0;
+    }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { lz_mbar_init(&full[s], 1); lz_mbar_init(&freeb[s], CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (FSUB) {
+        for (int e = tid; e < 8 * 32; e += (1 + CW) * 32) {
+            const int ln = e & 31, nt = (e >> 5) & 1, kt = e >> 6;
+            const int kk = ln & 3, mm = ln >> 2;
+            const int kphys = 4 * kk + kt, nphys = 4 * (mm >> 1) + 2 * nt + (mm & 1);
+            sbs[e] = -Bm[kphys + nphys * BW];
+        }
+    }
+    __syncthreads();
+    // chunk -> CTA map: round robin, all CTAs sweep a window of gridDim.x chunks together (the far neighbours of a stencil
+    // row were touched one window earlier and are still in L2)
+    auto vchunk = [&](int it) { return it * (int)gridDim.x + (int)blockIdx.x; };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer warp
+        int p0 = 0, p1 = 0, r0 = 0, r1 = 0;
+        int2 mt = make_int2(0, 0), sg = make_int2(0, 0);
+        int c = vchunk(0);
+        if (c < n_chunks) {
+            p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1];
+            mt = meta[c];
+            if (lane < LZ_XS_SEGCAP) sg = seg[(size_t)c * LZ_XS_SEGCAP + lane];
+        }
+        const uint64_t pol = lz_policy_evict_first();
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int it = 0; c < n_chunks; ++it) {
+            const int cp0 = p0, cp1 = p1, cr0 = r0, cr1 = r1;
+            const int2 cmt = mt, csg = sg;
+            c = vchunk(it + 1);
+            if (c < n_chunks) {
+                p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1];
+                mt = meta[c];
+                if (lane < LZ_XS_SEGCAP) sg = seg[(size_t)c * LZ_XS_SEGCAP + lane];
+            }
+            unsigned char *st = smem_raw + (size_t)slot * stage_bytes;
+            lz_mbar_wait_bounded(&freeb[slot], phase ^ 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const int a0 = cp0 & ~7, cnt8 = (cp1 - a0) & ~7;
+            const int ra = cr0 & ~3;
+            const int rcnt = ((cr1 + 1 - ra) + 3) & ~3;
+            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
+            // window offset of this lane's segment: exclusive prefix of the segment sizes
+            const int rows = lane < cmt.x ? csg.y : 0;
+            int incl = rows;
+#pragma unroll
+            for (int o = 1; o < LZ_XS_SEGCAP; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int off = incl - rows;
+            if (lane == 0)
+                lz_mbar_expect_tx(&full[slot], (uint32_t)cnt8 * 10u + (rows_ok ? (uint32_t)rcnt * 4u : 0u) + (uint32_t)cmt.y * (uint32_t)(BW * 8));
+            __syncwarp();
+            if (lane == 0 && cnt8 > 0) {
+                if (hint & 1) {
+                    lz_bulk_g2s_hint(st + xw_bytes, vals + a0, (uint32_t)cnt8 * 8u, &full[slot], pol);
+                    lz_bulk_g2s_hint(st + xw_bytes + LZ_XS_ES * 8, lidx + a0, (uint32_t)cnt8 * 2u, &full[slot], pol);
+                } else {
+                    lz_bulk_g2s(st + xw_bytes, vals + a0, (uint32_t)cnt8 * 8u, &full[slot]);
+                    lz_bulk_g2s(st + xw_bytes + LZ_XS_ES * 8, lidx + a0, (uint32_t)cnt8 * 2u, &full[slot]);
+                }
+            }
+            if (lane == 1 && rows_ok) lz_bulk_g2s(st + xw_bytes + LZ_XS_ES * 10, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot]);
+            if (rows > 0)
+                lz_bulk_g2s(st + (size_t)off * (BW * 8), X + (int64_t)csg.x * BW, (uint32_t)rows * (uint32_t)(BW * 8), &full[slot]);
+            if (++slot == stages) { slot = 0; phase ^= 1; }
+        }
+    } else {
+        // ------------------------------------------------------------------ compute warps
+        const int sub = lane / LW, l = lane % LW;
+        const int p = (lane >> 2) & 1;                      // bank swizzle: odd groups read their upper 16 bytes first
+        const int offA = 4 * l + 2 * p, offB = 4 * l + 2 * (1 - p);
+        int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0, trip_base = 0;
+        int c = vchunk(0);
+        if (c < n_chunks) { nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int it = 0; c < n_chunks; ++it) {
+            const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
+            c = vchunk(it + 1);
+            if (c < n_chunks) { nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
+            const int a0 = cp0 & ~7, cnt8 = (cp1 - a0) & ~7;
+            const int ra = r0 & ~3;
+            const int rcnt = ((r1 + 1 - ra) + 3) & ~3;
+            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
+            const unsigned char *st = smem_raw + (size_t)slot * stage_bytes;
+            const double *xw = reinterpret_cast<const double *>(st);
+            const double *vs = reinterpret_cast<const double *>(st + xw_bytes);
+            const uint16_t *ls = reinterpret_cast<const uint16_t *>(st + xw_bytes + LZ_XS_ES * 8);
+            const int *rs = reinterpret_cast<const int *>(st + xw_bytes + LZ_XS_ES * 10);
+            const int trips = (int)((r1 - r0 + RPW - 1) / RPW);
+            const int t0 = (((warp - 1) - trip_base) % CW + CW) % CW;     // trips of all chunks dealt round-robin to the warps
+            trip_base = (trip_base + trips) % CW;
+            // operands of the first trip that live in global memory: issued before the wait on the ring
+            const int64_t rb0 = (int64_t)r0 + (int64_t)t0 * RPW;
+            lz_mbar_wait_bounded(&full[slot], phase);
+            for (int64_t rb = rb0; rb < r1; rb += NG) {
+                const int64_t r = rb + sub;
+                const bool valid = r < r1;
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+                if (FSUB && valid) lz_ld256_stream_pol(Q0 + r * BW + 4 * l, q0, q1, q2, q3, lz_policy_evict_first());
+                double xa[2][2];
+                if (GRAM) {
+                    const int kk = lane & 3, mm = lane >> 2;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const int64_t rr = rb + 4 * ks + kk;
+#pragma unroll
+                        for (int a = 0; a < 2; ++a) xa[ks][a] = rr < r1 ? __ldg(Xown + rr * BW + 8 * a + mm) : 0.0;
+                    }
+                }
+                int s = 0, e = 0;
+                if (valid) {
+                    if (rows_ok) { s = rs[r - ra]; e = rs[r - ra + 1]; }
+                    else { s = rowptr[r]; e = rowptr[r + 1]; }
+                }
+                double aA0 = 0.0, aA1 = 0.0, aB0 = 0.0, aB1 = 0.0;
+                for (int k0 = s; k0 < e; k0 += G) {
+                    int li[G]; double vv[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const int k = k0 + g, ks = k - a0;
+                        li[g] = -1; vv[g] = 0.0;
+                        if (k < e) {
+                            if (ks < cnt8) { li[g] = ls[ks]; vv[g] = vs[ks]; }
+                            else { li[g] = lidx[k]; vv[g] = __ldcs(vals + k); }       // the (<= 7) entries the 16-byte copies cannot carry
+                        }
+                    }
+                    double2 xA[G], xB[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        xA[g] = xB[g] = make_double2(0.0, 0.0);
+                        if (li[g] >= 0) {
+                            const double *row = xw + (size_t)li[g] * BW;
+                            xA[g] = *reinterpret_cast<const double2 *>(row + offA);
+                            xB[g] = *reinterpret_cast<const double2 *>(row + offB);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        aA0 = fma(vv[g], xA[g].x, aA0); aA1 = fma(vv[g], xA[g].y, aA1);
+                        aB0 = fma(vv[g], xB[g].x, aB0); aB1 = fma(vv[g], xB[g].y, aB1);
+                    }
+                }
+                double acc0 = p ? aB0 : aA0, acc1 = p ? aB1 : aA1, acc2 = p ? aA0 : aB0, acc3 = p ? aA1 : aB1;
+                if (FSUB) {
+                    __syncwarp();     // the entry loop has per-row trip counts: the MMAs need the whole warp
+                    lz_dmma(acc0, acc1, q0, sbs[(0 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q0, sbs[(0 * 2 + 1) * 32 + lane]);
+                    lz_dmma(acc0, acc1, q1, sbs[(1 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q1, sbs[(1 * 2 + 1) * 32 + lane]);
+                    lz_dmma(acc0, acc1, q2, sbs[(2 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q2, sbs[(2 * 2 + 1) * 32 + lane]);
+                    lz_dmma(acc0, acc1, q3, sbs[(3 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q3, sbs[(3 * 2 + 1) * 32 + lane]);
+                }
+                if (valid) {
+                    if (FSUB) lz_st256_pol(W + r * BW + 4 * l, acc0, acc1, acc2, acc3, lz_policy_evict_first());
+                    else lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                }
+                if (GRAM) {
+                    // G += Xown[rb .. rb+8, :]^T W[rb .. rb+8, :]   (rows past the chunk contribute zeros: their acc is 0)
+                    double *gt = gst + (warp - 1) * 8 * SPMM_GST;
+                    *reinterpret_cast<double2 *>(gt + sub * SPMM_GST + 4 * l) = make_double2(acc0, acc1);
+                    *reinterpret_cast<double2 *>(gt + sub * SPMM_GST + 4 * l + 2) = make_double2(acc2, acc3);
+                    const int kk = lane & 3, mm = lane >> 2;
+                    __syncwarp();
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const double wb0 = gt[(4 * ks + kk) * SPMM_GST + mm], wb1 = gt[(4 * ks + kk) * SPMM_GST + 8 + mm];
+#pragma unroll
+                        for (int a = 0; a < 2; ++a) {
+                            lz_dmma(gacc[a][0][0], gacc[a][0][1], xa[ks][a], wb0);
+                            lz_dmma(gacc[a][1][0], gacc[a][1][1], xa[ks][a], wb1);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) lz_mbar_arrive(&freeb[slot]);
+            if (++slot == stages) { slot = 0; phase ^= 1; }
+        }
+    }
+    if (GRAM) {
+        // CTA partial = sum of the compute warps' accumulators in warp order (fixed), through shared memory
+        __shared__ double gsm[16 * 16];
+        const int kk = lane & 3, mm = lane >> 2;
+        for (int w = 1; w <= CW; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const int pp = a * 8 + mm, q = b * 8 + 2 * kk;
+                        if (w == 1) { gsm[pp + q * 16] = gacc[a][b][0]; gsm[pp + (q + 1) * 16] = gacc[a][b][1]; }
+                        else { gsm[pp + q * 16] += gacc[a][b][0]; gsm[pp + (q + 1) * 16] += gacc[a][b][1]; }
+                    }
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < 256; e += (1 + CW) * 32) gpart[(size_t)blockIdx.x * 256 + e] = gsm[e];
+    }
+}
+
+// true when the operand-staging kernel can run this product: whole operator (no interior / boundary parts), contiguous
+// panels, a window schedule that fits at least two ring slots for this panel width
+static bool spmm_xs_plan(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, const double *W, int part, int *stages, int *stage_bytes,
+                         int *xw_bytes)
+{
+    if (part != 0 || ctx->knobs.no_xs || ctx->spmv_variant == 9 || !A->tma_ok) return false;
+    if (lz_matrix_prepare_xs(ctx, A) != LZ_OK || A->xs_state != 1) return false;
+    if (((uintptr_t)X % 16) || ((uintptr_t)W % 32)) return false;
+    if (A->xs_max_entries + 8 > LZ_XS_ES) return false;
+    const int xw = ((A->xs_max_wrows * bw * 8) + 127) & ~127;
+    const int sb = (xw + LZ_XS_ES * 10 + LZ_XS_RCAP * 4 + 127) & ~127;
+    const int budget = 200 * 1024;                    // dynamic shared memory left beside the static Gram / fragment tiles
+    int st = budget / sb;
+    if (st > 4) st = 4;
+    if (ctx->knobs.xs_stages >= 2 && ctx->knobs.xs_stages < st) st = ctx->knobs.xs_stages;
+    if (st < 2) return false;
+    *stages = st; *stage_bytes = sb; *xw_bytes = xw;
+    return true;
+}
+
+template <int BW, bool FSUB, bool GRAM>
+static int launch_spmm_xs(lz_ctx *ctx, const lz_matrix *A, const double *X, double *W, const double *Q0, const double *Bm, int stages,
+                          int stage_bytes, int xw_bytes, const double *Xown = nullptr, double *gpart = nullptr, int *grid_out = nullptr)
+{
+    const size_t smem = (size_t)stages * stage_bytes + 64;
+    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_xs<BW, LZ_XS_CW, FSUB, GRAM>, (int)smem));
+    int grid = ctx->sm_count;
+    if (grid > A->xs_n_chunks) grid = A->xs_n_chunks;
+    if (grid_out) *grid_out = grid;
+    k_spmm_xs<BW, LZ_XS_CW, FSUB, GRAM><<<grid, (1 + LZ_XS_CW) * 32, smem, ctx->stream>>>(
+        A->xs_n_chunks, A->n_rows, A->xs_chunk_row, A->xs_chunk_ptr, A->xs_meta, A->xs_seg, A->rowptr, A->xs_lidx, A->vals, X, W, Q0, Bm,
+        stages, stage_bytes, xw_bytes, ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, Xown, gpart);
+    return LZ_OK;
+}
