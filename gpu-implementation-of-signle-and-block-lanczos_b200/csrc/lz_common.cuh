@@ -62,7 +62,9 @@ struct LzKnobs {
     int block_cgs_fuse;     // LZ_BLOCK_CGS_FUSE: 1 (default) fused update+project in the block CGS2, 0 four streams
     int split_l;            // LZ_SPLIT_L: longest virtual row of a row-split (power-law) operator, SpMV
     int no_xs;              // LZ_NO_XS: never use the operand-staging SpMM
-    int xs_stages;          // LZ_XS_STAGES: ring depth of the operand-staging SpMM (0 = as many as fit, <= 4)
+    int xs_stages;          // LZ_XS_STAGES: ring depth of the operand-staging SpMM (0 = as many as fit, <= 8)
+    int xs_no_tiles;        // LZ_XS_NO_TILES: chunks of consecutive rows even on structured-grid operators
+    int xs_tile;            // LZ_XS_TILE: target entries per chunk of its schedule (128..512, default 512)
     int split_l_mm;         // LZ_SPLIT_L_MM: the same for the SpMM's own split (default 32)
     int no_transpose;       // 1 unless LZ_TRANSPOSE is set: the SpMV gather warps walk a chunk in storage order (the transposed walk of uniform chunks measured slower)
     int cgs_rpt;            // LZ_CGS_RPT: rows per thread of the streaming CGS kernels (0 auto, 4, 8)
@@ -217,8 +219,9 @@ enum { LZ_FMT_CSR = 0, LZ_FMT_ELL4 = 1 };
 #define LZ_SPMV_THREADS 256
 #define LZ_SPMV_TILE 768         // target nnz per SpMV chunk (profiles/r01_spmv_variants.md)
 #define LZ_XS_TILE 512          // target nnz per chunk of the operand-staging SpMM
-#define LZ_XS_SEGCAP 16         // column segments per chunk
-#define LZ_XS_ECAP 768          // entries per chunk the build kernel sorts (tile + longest row must fit)
+#define LZ_XS_SEGCAP 32         // column segments per chunk (one bulk copy per producer lane)
+#define LZ_XS_ECAP 1024         // entries per chunk the build kernel sorts (tile + longest row must fit)
+#define LZ_XS_OGROUPS 16        // 8-row output groups per chunk (chunks hold <= 128 rows)
 #define LZ_XS_MERGE 8           // columns at most this far apart share a segment
 #define LZ_SPMM_TILE 1536        // target nnz per SpMM chunk (k_spmm_ws stages 2048 entries per slot)
 #define LZ_SPLIT_L 256           // rows longer than this are split into virtual rows
@@ -283,6 +286,16 @@ struct lz_matrix {
     int2 *xs_meta;                     // per chunk: (segments, window rows)
     int2 *xs_seg;                      // [chunk][LZ_XS_SEGCAP]: (first column, rows)
     uint16_t *xs_lidx;                 // per entry
+    // On structured-grid operators the chunks are small BOXES of grid points (lx x ty x tz rows: ty*tz short runs of
+    // consecutive rows) instead of runs of consecutive rows, because a box shares far more of its neighbours (7-point
+    // stencil: 2.7 window rows per row instead of 5.1).  The product walks a row-permuted copy of the operator --
+    // xs_rowptr / xs_vals in chunk order, every chunk padded to a multiple of 8 entries; xs_rowmap[i] = original row of
+    // walked row i; column numbering unchanged -- and writes row xs_rowmap[i] of W.
+    int32_t *xs_rowptr, *xs_rowmap;
+    double *xs_vals;
+    int4 *xs_desc;                     // per chunk: (first entry, end entry, first row, end row) of the walked operator
+    int32_t *xs_oseg;                  // [chunk][LZ_XS_OGROUPS]: original row of every 8th walked row (-1 past the chunk): L2 prefetch of Q0
+    int xs_tile_dims[3];               // lx, ty, tz (0: not tiled)
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)
     int64_t halo_lo, halo_hi;        // halo entries below / above the local range
     // chunks [bnd_lo, bnd_hi) of the fine schedule (mm_*: of the coarse one) hold only rows that reference no halo

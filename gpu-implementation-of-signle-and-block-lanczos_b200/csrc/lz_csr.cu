@@ -6,6 +6,8 @@
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 #include <limits.h>
+#include <vector>
+#include <algorithm>
 
 #include <stdlib.h>
 
@@ -290,38 +292,197 @@ __global__ void k_xs_max_rows(int n_chunks, const int32_t *__restrict__ chunk_ro
     atomicMax(stats + 3, chunk_ptr[c + 1] - chunk_ptr[c]);
 }
 
-// Builds the X-window schedule of an unsplit CSR operator once (first panel product).  Sets xs_state = 1 when every
-// chunk got a window, -1 otherwise; the launch code checks xs_max_wrows against the shared memory of its panel width.
+__global__ void k_xs_perm_lens(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ rowmap, int32_t *__restrict__ lens)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { lens[i] = 0; return; }
+    const int r = rowmap[i];
+    lens[i] = rowptr[r + 1] - rowptr[r];
+}
+// the last row of every chunk is padded with zero-valued entries so that the chunk's entry count is a multiple of 8:
+// every chunk then starts on a 16-byte boundary of the value / window-index streams and the bulk copies carry it whole
+__global__ void k_xs_pad_lens(int n_chunks, const int32_t *__restrict__ chunk_row, int32_t *__restrict__ lens)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int r0 = chunk_row[c], r1 = chunk_row[c + 1];
+    if (r1 <= r0) return;
+    int total = 0;
+    for (int r = r0; r < r1; ++r) total += lens[r];
+    lens[r1 - 1] += (8 - (total & 7)) & 7;
+}
+// one warp per row of the walked operator: its entries from the original row, then the padding (value 0, the row's own
+// index as column: always a valid row of X, and 0 * x adds exactly nothing)
+__global__ void __launch_bounds__(256)
+k_xs_copy(int64_t n, const int32_t *__restrict__ old_ptr, const int32_t *__restrict__ new_ptr, const int32_t *__restrict__ rowmap,
+          const int32_t *__restrict__ colidx, const double *__restrict__ vals, int32_t *__restrict__ ncol, double *__restrict__ nval)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int r = rowmap[i];
+    const int src = old_ptr[r], len = old_ptr[r + 1] - src, dst = new_ptr[i], nlen = new_ptr[i + 1] - dst;
+    for (int k = lane; k < nlen; k += 32) {
+        ncol[dst + k] = k < len ? colidx[src + k] : r;
+        nval[dst + k] = k < len ? vals[src + k] : 0.0;
+    }
+}
+__global__ void k_xs_desc(int n_chunks, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ rowmap,
+                          int32_t *__restrict__ chunk_ptr, int4 *__restrict__ desc, int32_t *__restrict__ oseg)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_chunks) return;
+    chunk_ptr[c] = rowptr[chunk_row[c]];
+    if (c == n_chunks) return;
+    const int r0 = chunk_row[c], r1 = chunk_row[c + 1];
+    desc[c] = make_int4(rowptr[r0], rowptr[r1], r0, r1);
+    for (int g = 0; g < LZ_XS_OGROUPS; ++g) oseg[(size_t)c * LZ_XS_OGROUPS + g] = r0 + 8 * g < r1 ? rowmap[r0 + 8 * g] : -1;
+}
+
+// Structured-grid detection on a sample of interior rows: the offsets (column - row) present in at least half of the
+// sampled rows.  A 7-point operator on an nx x ny x nz grid gives {0, +-1, +-nx, +-nx*ny}: strides 1 | nx | nx*ny.
+// Returns the number of nested strides found (1: only the unit stride, i.e. a banded operator).
+static int xs_detect_strides(lz_ctx *ctx, const lz_matrix *A, int64_t stride[3])
+{
+    const int64_t n = A->n_rows;
+    const int64_t S = std::min<int64_t>(4096, n / 2);
+    if (S < 64) return 0;
+    const int64_t r0 = n / 2;
+    std::vector<int32_t> rp(S + 1);
+    if (cudaMemcpy(rp.data(), A->rowptr + r0, sizeof(int32_t) * (S + 1), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    const int64_t cnt = (int64_t)rp[S] - rp[0];
+    if (cnt <= 0 || cnt > S * 64) return 0;
+    std::vector<int32_t> ci(cnt);
+    if (cudaMemcpy(ci.data(), A->colidx + rp[0], sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    std::vector<int64_t> offs;
+    offs.reserve(cnt);
+    for (int64_t r = 0; r < S; ++r)
+        for (int64_t k = rp[r] - rp[0]; k < rp[r + 1] - rp[0]; ++k) offs.push_back((int64_t)ci[k] - (r0 + r));
+    std::sort(offs.begin(), offs.end());
+    std::vector<int64_t> common;
+    for (size_t a = 0; a < offs.size();) {
+        size_t b = a;
+        while (b < offs.size() && offs[b] == offs[a]) ++b;
+        if ((int64_t)(b - a) * 2 >= S && offs[a] > 0) common.push_back(offs[a]);
+        a = b;
+    }
+    if (common.empty() || common[0] != 1) return 0;
+    int ns = 1;
+    stride[0] = 1;
+    for (size_t a = 1; a < common.size() && ns < 3; ++a)
+        if (common[a] % stride[ns - 1] == 0 && common[a] / stride[ns - 1] >= 8) stride[ns++] = common[a];
+    return ns;
+}
+
+// Builds the X-window schedule of an unsplit, unsharded, square CSR operator once (first panel product).  Sets
+// xs_state = 1 when every chunk got a window, -1 otherwise; the launch code checks xs_max_wrows against the shared
+// memory of its panel width.
 int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
 {
     if (Ac->xs_state != 0) return LZ_OK;
     lz_matrix *A = const_cast<lz_matrix *>(Ac);
     A->xs_state = -1;
-    if (ctx->knobs.no_xs || !A->rowptr || A->vrowptr || A->csr_nnz <= 0 || A->max_row_nnz > LZ_XS_ECAP - LZ_XS_TILE) return LZ_OK;
-    const int64_t nnz = A->csr_nnz;
-    const int64_t nch = (nnz + LZ_XS_TILE - 1) / LZ_XS_TILE;
-    if (nch >= (int64_t)1 << 30) return LZ_OK;
+    if (ctx->knobs.no_xs || !A->rowptr || A->vrowptr || A->csr_nnz <= 0 || A->max_row_nnz > 64 || A->max_row_nnz < 1 || A->n_rows != A->n_cols ||
+        A->halo_lo || A->halo_hi)
+        return LZ_OK;
+    const int64_t nnz = A->csr_nnz, n = A->n_rows;
     int *stats = ctx->flags + 16;                           // 4 ints of the context's flag bank
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
     LZ_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int), ctx->stream));
+
+    // ---- chunks: boxes of grid points when the operator has nested strides, runs of rows otherwise ----
+    int64_t stride[3] = {1, 0, 0};
+    const int ns = ctx->knobs.xs_no_tiles ? 1 : xs_detect_strides(ctx, A, stride);
+    const int avg = (int)std::max<int64_t>(1, nnz / std::max<int64_t>(n, 1));
+    int rows_target = (int)std::min<int64_t>(128, std::min<int64_t>((LZ_XS_ECAP - 8) / A->max_row_nnz, ctx->knobs.xs_tile * 2 / avg));
+    rows_target &= ~7;
+    if (rows_target < 8) return LZ_OK;
+    std::vector<int32_t> rowmap, crow;
+    rowmap.reserve(n);
+    if (ns >= 2) {
+        // box shape: lx rows along the unit stride, ty runs along the second stride, tz along the third
+        const int64_t nx = stride[1], ny = ns == 3 ? stride[2] / stride[1] : (n + nx - 1) / nx, nz = ns == 3 ? (n + stride[2] - 1) / stride[2] : 1;
+        int lx = 16, ty = ns == 3 ? 4 : 8, tz = ns == 3 ? 2 : 1;
+        while (lx * ty * tz > rows_target && ty > 1) ty /= 2;
+        while (lx * ty * tz > rows_target && tz > 1) tz /= 2;
+        while (lx * ty * tz > rows_target && lx > 8) lx /= 2;
+        if (const char *e = getenv("LZ_XS_BOX")) {
+            int a, b, c2;
+            if (sscanf(e, "%d,%d,%d", &a, &b, &c2) == 3 && a >= 8 && b >= 1 && c2 >= 1 && a * b * c2 <= rows_target) { lx = a; ty = b; tz = c2; }
+        }
+        if (ns < 3) tz = 1;
+        A->xs_tile_dims[0] = lx; A->xs_tile_dims[1] = ty; A->xs_tile_dims[2] = tz;
+        for (int64_t kz = 0; kz < nz; kz += tz)
+            for (int64_t jy = 0; jy < ny; jy += ty)
+                for (int64_t ix = 0; ix < nx; ix += lx) {
+                    const size_t before = rowmap.size();
+                    for (int64_t k = kz; k < std::min<int64_t>(kz + tz, nz); ++k)
+                        for (int64_t j = jy; j < std::min<int64_t>(jy + ty, ny); ++j) {
+                            const int64_t line = (ns == 3 ? k * stride[2] : 0) + j * nx;
+                            const int64_t base = line + ix, end = std::min<int64_t>(std::min<int64_t>(base + lx, line + nx), n);
+                            for (int64_t r = base; r < end; ++r) rowmap.push_back((int32_t)r);
+                        }
+                    if (rowmap.size() > before) crow.push_back((int32_t)before);
+                }
+        if ((int64_t)rowmap.size() != n) return LZ_OK;                 // (cannot happen for nested strides; keep the gathering kernel)
+    } else {
+        for (int64_t r = 0; r < n; ++r) { if (r % rows_target == 0) crow.push_back((int32_t)r); rowmap.push_back((int32_t)r); }
+    }
+    crow.push_back((int32_t)n);
+    const int64_t nch = (int64_t)crow.size() - 1;
+    LZ_CUDA(cudaMalloc(&A->xs_rowmap, sizeof(int32_t) * ((size_t)n + 8)));
+    LZ_CUDA(cudaMemset(A->xs_rowmap, 0, sizeof(int32_t) * ((size_t)n + 8)));
+    LZ_CUDA(cudaMemcpy(A->xs_rowmap, rowmap.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
     LZ_CUDA(cudaMalloc(&A->xs_chunk_row, sizeof(int32_t) * (nch + 1)));
+    LZ_CUDA(cudaMemcpy(A->xs_chunk_row, crow.data(), sizeof(int32_t) * (nch + 1), cudaMemcpyHostToDevice));
+    // the operator's rows in chunk order, every chunk padded to a multiple of 8 entries: lengths, scan, copy
+    int32_t *lens;
+    LZ_CUDA(cudaMalloc(&lens, sizeof(int32_t) * (n + 1)));
+    LZ_CUDA(cudaMalloc(&A->xs_rowptr, sizeof(int32_t) * ((size_t)n + 8)));
+    k_xs_perm_lens<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->rowptr, A->xs_rowmap, lens);
+    LZ_LAUNCH_CHECK(ctx);
+    k_xs_pad_lens<<<(unsigned)((nch + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->xs_chunk_row, lens);
+    LZ_LAUNCH_CHECK(ctx);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens, A->xs_rowptr, (int)(n + 1), ctx->stream);
+    void *tmp;
+    LZ_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lens, A->xs_rowptr, (int)(n + 1), ctx->stream);
+    ctx->launches++;
+    int32_t nnz2 = 0;
+    LZ_CUDA(cudaMemcpyAsync(&nnz2, A->xs_rowptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    LZ_CUDA(cudaFree(tmp)); LZ_CUDA(cudaFree(lens));
+    int32_t *cols2;
+    LZ_CUDA(cudaMalloc(&cols2, sizeof(int32_t) * ((size_t)nnz2 + 8)));
+    LZ_CUDA(cudaMalloc(&A->xs_vals, sizeof(double) * ((size_t)nnz2 + 8)));
+    k_xs_copy<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(n, A->rowptr, A->xs_rowptr, A->xs_rowmap, A->colidx, A->vals, cols2, A->xs_vals);
+    LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaMalloc(&A->xs_chunk_ptr, sizeof(int32_t) * (nch + 1)));
+    LZ_CUDA(cudaMalloc(&A->xs_desc, sizeof(int4) * nch));
+    LZ_CUDA(cudaMalloc(&A->xs_oseg, sizeof(int32_t) * nch * LZ_XS_OGROUPS));
+    k_xs_desc<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->xs_chunk_row, A->xs_rowptr, A->xs_rowmap, A->xs_chunk_ptr, A->xs_desc,
+                                                                          A->xs_oseg);
+    LZ_LAUNCH_CHECK(ctx);
     LZ_CUDA(cudaMalloc(&A->xs_meta, sizeof(int2) * nch));
     LZ_CUDA(cudaMalloc(&A->xs_seg, sizeof(int2) * nch * LZ_XS_SEGCAP));
-    LZ_CUDA(cudaMalloc(&A->xs_lidx, sizeof(uint16_t) * ((size_t)nnz + 16)));
-    LZ_CUDA(cudaMemsetAsync(A->xs_lidx, 0, sizeof(uint16_t) * ((size_t)nnz + 16), ctx->stream));
-    k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, nnz, A->rowptr, (int)nch, LZ_XS_TILE, A->xs_chunk_row, A->xs_chunk_ptr);
-    LZ_LAUNCH_CHECK(ctx);
+    LZ_CUDA(cudaMalloc(&A->xs_lidx, sizeof(uint16_t) * ((size_t)nnz2 + 16)));
+    LZ_CUDA(cudaMemsetAsync(A->xs_lidx, 0, sizeof(uint16_t) * ((size_t)nnz2 + 16), ctx->stream));
     k_xs_max_rows<<<(unsigned)((nch + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->xs_chunk_row, A->xs_chunk_ptr, stats);
     LZ_LAUNCH_CHECK(ctx);
-    k_xs_build<<<(unsigned)nch, 256, 0, ctx->stream>>>(A->xs_chunk_ptr, A->colidx, A->xs_meta, A->xs_seg, A->xs_lidx, stats);
+    k_xs_build<<<(unsigned)nch, 256, 0, ctx->stream>>>(A->xs_chunk_ptr, cols2, A->xs_meta, A->xs_seg, A->xs_lidx, stats);
     LZ_LAUNCH_CHECK(ctx);
     int h[4];
     LZ_CUDA(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(cols2);                                        // the product streams window indices, not columns
     A->xs_n_chunks = (int)nch; A->xs_max_wrows = h[0]; A->xs_max_rows = h[2]; A->xs_max_entries = h[3];
     if (h[1] == 0 && h[0] > 0) { A->xs_state = 1; return LZ_OK; }
     cudaFree(A->xs_chunk_row); cudaFree(A->xs_chunk_ptr); cudaFree(A->xs_meta); cudaFree(A->xs_seg); cudaFree(A->xs_lidx);
+    cudaFree(A->xs_rowptr); cudaFree(A->xs_rowmap); cudaFree(A->xs_vals); cudaFree(A->xs_desc); cudaFree(A->xs_oseg);
     A->xs_chunk_row = A->xs_chunk_ptr = nullptr; A->xs_meta = A->xs_seg = nullptr; A->xs_lidx = nullptr;
+    A->xs_rowptr = A->xs_rowmap = nullptr; A->xs_vals = nullptr; A->xs_desc = nullptr; A->xs_oseg = nullptr;
     return LZ_OK;
 }
 
@@ -369,7 +530,7 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
     LZ_CUDA(cudaMalloc(&A->chunk_ulen, sizeof(int32_t) * (nch + 1)));
     A->k_colidx = A->bin_colidx ? A->bin_colidx : A->colidx;       // what the SpMV kernels stream
     A->k_vals = A->bin_vals ? A->bin_vals : A->vals;
-    A->tma_ok = ((uintptr_t)A->k_vals % 16 == 0) && ((uintptr_t)A->k_colidx % 16 == 0);
+    A->tma_ok = ((uintptr_t)A->k_vals % 16 == 0) && ((uintptr_t)A->k_colidx % 16 == 0) && ((uintptr_t)rp % 16 == 0);   // bulk copies: 16-byte sources
     k_chunk_rows<<<(unsigned)((nch + 1 + 255) / 256), 256, 0, ctx->stream>>>(rows, nnz, rp, (int)nch, A->tile, A->chunk_row, A->chunk_ptr);
     LZ_LAUNCH_CHECK(ctx);
     k_chunk_ulen<<<(unsigned)((nch + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->chunk_row, rp, A->chunk_ulen);
@@ -776,6 +937,7 @@ int lz_matrix_destroy(lz_matrix *A)
     cudaFree(A->bin_colidx);
     cudaFree(A->bin_vals);
     cudaFree(A->xs_chunk_row); cudaFree(A->xs_chunk_ptr); cudaFree(A->xs_meta); cudaFree(A->xs_seg); cudaFree(A->xs_lidx);
+    cudaFree(A->xs_rowptr); cudaFree(A->xs_rowmap); cudaFree(A->xs_vals); cudaFree(A->xs_desc); cudaFree(A->xs_oseg);
     if (!A->mm_shared) {
         cudaFree(A->mm.vstart); cudaFree(A->mm.vrowptr); cudaFree(A->mm.vpos);
         cudaFree(A->mm.bin_colidx); cudaFree(A->mm.bin_vals);

@@ -19,7 +19,7 @@
 // kernel has registers to spare at one CTA per SM), so their latency overlaps the shared-memory gathers.
 #pragma once
 
-#define LZ_XS_ES 784            // entries staged per ring slot (chunk entries + alignment slack), multiple of 8
+#define LZ_XS_ES 1040           // entries staged per ring slot (chunk entries + alignment slack), multiple of 8
 #define LZ_XS_RCAP 640          // row pointers staged per ring slot
 #define LZ_XS_CW 15             // compute warps per CTA (one CTA per SM)
 
@@ -37,19 +37,20 @@ __device__ __forceinline__ void lz_mbar_wait_bounded(uint64_t *bar, uint32_t par
 
 template <int BW, int CW, bool FSUB, bool GRAM>
 __global__ void __launch_bounds__((1 + CW) * 32, 1)
-k_spmm_xs(const int n_chunks, const int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
-          const int2 *__restrict__ meta, const int2 *__restrict__ seg, const int32_t *__restrict__ rowptr,
-          const uint16_t *__restrict__ lidx, const double *__restrict__ vals, const double *__restrict__ X, double *__restrict__ W,
-          const double *__restrict__ Q0, const double *__restrict__ Bm, const int stages, const int stage_bytes, const int xw_bytes,
-          const int hint, const double *__restrict__ Xown, double *__restrict__ gpart)
+k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ desc, const int2 *__restrict__ meta, const int2 *__restrict__ seg,
+          const int32_t *__restrict__ rowptr, const uint16_t *__restrict__ lidx, const double *__restrict__ vals, const int32_t *__restrict__ rowmap,
+          const double *__restrict__ X, double *__restrict__ W, const double *__restrict__ Q0, const double *__restrict__ Bm, const int stages,
+          const int stage_bytes, const int xw_bytes, const int hint, const double *__restrict__ Xown, double *__restrict__ gpart,
+          const int32_t *__restrict__ oseg)
 {
     static_assert(!GRAM || FSUB, "the fused Gram rides on the 8-row trips of the fused subtraction");
     static_assert(!FSUB || BW == 16, "the fused subtraction is written for 16-column panels");
     constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // ring slot s: [ X window (xw_bytes) | values (ES*8) | window indices (ES*2) | row pointers (RCAP*4) ]
+    // ring slot s: [ X window (xw_bytes) | values (ES*8) | window indices (ES*2) | row pointers (RCAP*4) | row map (RCAP*4) | chunk descriptor ]
+    // rowmap: row i of the walked (chunk-ordered, padded) operator is row rowmap[i] of W / Q0 / Xown
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * stage_bytes);
-    uint64_t *freeb = full + 4;
+    uint64_t *freeb = full + 8;
     __shared__ double sbs[FSUB ? 8 * 32 : 1];                             // -B in fragment order (see k_spmm_ws)
     __shared__ __align__(16) double gst[GRAM ? CW * 8 * SPMM_GST : 1];    // per-warp 8 x 16 tile of W for the Gram fragments
     double gacc[GRAM ? 2 : 1][GRAM ? 2 : 1][2];
@@ -79,57 +80,66 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int32_t *__restrict__ 
 
     if (warp == 0) {
         // ------------------------------------------------------------------ producer warp
-        int p0 = 0, p1 = 0, r0 = 0, r1 = 0;
-        int2 mt = make_int2(0, 0), sg = make_int2(0, 0);
-        int c = vchunk(0);
-        if (c < n_chunks) {
-            p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1];
-            mt = meta[c];
-            if (lane < LZ_XS_SEGCAP) sg = seg[(size_t)c * LZ_XS_SEGCAP + lane];
-        }
+        // descriptors, segment tables: fetched TWO chunks ahead (nothing in an iteration waits for a load it issued itself)
+        int4 d0 = make_int4(0, 0, 0, 0), d1 = d0;
+        int2 m0 = make_int2(0, 0), m1 = m0, s0 = m0, s1 = m0;
+        int o0 = -1, o1 = -1;               // FSUB: first original row of this lane's 8-row output group (lanes < LZ_XS_OGROUPS)
+        auto fetch = [&](int c, int4 &d, int2 &m, int2 &sg, int &og) {
+            if (c < n_chunks) {
+                d = desc[c]; m = meta[c]; sg = seg[(size_t)c * LZ_XS_SEGCAP + lane];
+                if (FSUB && lane < LZ_XS_OGROUPS) og = oseg[(size_t)c * LZ_XS_OGROUPS + lane];
+            }
+        };
+        fetch(vchunk(0), d0, m0, s0, o0);
+        fetch(vchunk(1), d1, m1, s1, o1);
         const uint64_t pol = lz_policy_evict_first();
         int slot = 0;
         uint32_t phase = 0;
-        for (int it = 0; c < n_chunks; ++it) {
-            const int cp0 = p0, cp1 = p1, cr0 = r0, cr1 = r1;
-            const int2 cmt = mt, csg = sg;
-            c = vchunk(it + 1);
-            if (c < n_chunks) {
-                p0 = chunk_ptr[c]; p1 = chunk_ptr[c + 1]; r0 = chunk_row[c]; r1 = chunk_row[c + 1];
-                mt = meta[c];
-                if (lane < LZ_XS_SEGCAP) sg = seg[(size_t)c * LZ_XS_SEGCAP + lane];
-            }
+        for (int it = 0; vchunk(it) < n_chunks; ++it) {
+            const int c = vchunk(it);
+            const int4 cd = d0;
+            const int2 cmt = m0, csg = s0;
+            const int cog = o0;
+            d0 = d1; m0 = m1; s0 = s1; o0 = o1; o1 = -1;
+            fetch(vchunk(it + 2), d1, m1, s1, o1);
             unsigned char *st = smem_raw + (size_t)slot * stage_bytes;
             lz_mbar_wait_bounded(&freeb[slot], phase ^ 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const int a0 = cp0 & ~7, cnt8 = (cp1 - a0) & ~7;
-            const int ra = cr0 & ~3;
-            const int rcnt = ((cr1 + 1 - ra) + 3) & ~3;
+            const int a0 = cd.x, cnt = cd.y - cd.x;                 // multiples of 8 (the chunks are padded)
+            const int ra = cd.z & ~3;
+            const int rcnt = ((cd.w + 1 - ra) + 3) & ~3;
             const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
             // window offset of this lane's segment: exclusive prefix of the segment sizes
             const int rows = lane < cmt.x ? csg.y : 0;
             int incl = rows;
 #pragma unroll
-            for (int o = 1; o < LZ_XS_SEGCAP; o <<= 1) {
+            for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
             const int off = incl - rows;
             if (lane == 0)
-                lz_mbar_expect_tx(&full[slot], (uint32_t)cnt8 * 10u + (rows_ok ? (uint32_t)rcnt * 4u : 0u) + (uint32_t)cmt.y * (uint32_t)(BW * 8));
+                lz_mbar_expect_tx(&full[slot], (uint32_t)cnt * 10u + (rows_ok ? (uint32_t)rcnt * 8u : 0u) + 16u + (uint32_t)cmt.y * (uint32_t)(BW * 8));
             __syncwarp();
-            if (lane == 0 && cnt8 > 0) {
+            unsigned char *sm = st + xw_bytes;
+            if (lane == 0 && cnt > 0) {
                 if (hint & 1) {
-                    lz_bulk_g2s_hint(st + xw_bytes, vals + a0, (uint32_t)cnt8 * 8u, &full[slot], pol);
-                    lz_bulk_g2s_hint(st + xw_bytes + LZ_XS_ES * 8, lidx + a0, (uint32_t)cnt8 * 2u, &full[slot], pol);
+                    lz_bulk_g2s_hint(sm, vals + a0, (uint32_t)cnt * 8u, &full[slot], pol);
+                    lz_bulk_g2s_hint(sm + LZ_XS_ES * 8, lidx + a0, (uint32_t)cnt * 2u, &full[slot], pol);
                 } else {
-                    lz_bulk_g2s(st + xw_bytes, vals + a0, (uint32_t)cnt8 * 8u, &full[slot]);
-                    lz_bulk_g2s(st + xw_bytes + LZ_XS_ES * 8, lidx + a0, (uint32_t)cnt8 * 2u, &full[slot]);
+                    lz_bulk_g2s(sm, vals + a0, (uint32_t)cnt * 8u, &full[slot]);
+                    lz_bulk_g2s(sm + LZ_XS_ES * 8, lidx + a0, (uint32_t)cnt * 2u, &full[slot]);
                 }
             }
-            if (lane == 1 && rows_ok) lz_bulk_g2s(st + xw_bytes + LZ_XS_ES * 10, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot]);
+            if (lane == 1 && rows_ok) lz_bulk_g2s(sm + LZ_XS_ES * 10, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot]);
+            if (lane == 2 && rows_ok) lz_bulk_g2s(sm + LZ_XS_ES * 10 + LZ_XS_RCAP * 4, rowmap + ra, (uint32_t)rcnt * 4u, &full[slot]);
+            if (lane == 3) lz_bulk_g2s(sm + LZ_XS_ES * 10 + LZ_XS_RCAP * 8, desc + c, 16u, &full[slot]);
             if (rows > 0)
                 lz_bulk_g2s(st + (size_t)off * (BW * 8), X + (int64_t)csg.x * BW, (uint32_t)rows * (uint32_t)(BW * 8), &full[slot]);
+            // the Q0 rows this chunk subtracts are streamed from DRAM by the compute warps a ring depth later: pull them into
+            // L2 now, so that the trips wait for an L2 hit instead of a DRAM access
+            if (FSUB && !(hint & 64) && lane < LZ_XS_OGROUPS && cog >= 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Q0 + (int64_t)cog * BW), "r"(8 * BW * 8) : "memory");
             if (++slot == stages) { slot = 0; phase ^= 1; }
         }
     } else {
@@ -137,71 +147,66 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int32_t *__restrict__ 
         const int sub = lane / LW, l = lane % LW;
         const int p = (lane >> 2) & 1;                      // bank swizzle: odd groups read their upper 16 bytes first
         const int offA = 4 * l + 2 * p, offB = 4 * l + 2 * (1 - p);
-        int nr0 = 0, nr1 = 0, np0 = 0, np1 = 0, trip_base = 0;
-        int c = vchunk(0);
-        if (c < n_chunks) { nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
+        int trip_base = 0;
         int slot = 0;
         uint32_t phase = 0;
-        for (int it = 0; c < n_chunks; ++it) {
-            const int r0 = nr0, r1 = nr1, cp0 = np0, cp1 = np1;
-            c = vchunk(it + 1);
-            if (c < n_chunks) { nr0 = chunk_row[c]; nr1 = chunk_row[c + 1]; np0 = chunk_ptr[c]; np1 = chunk_ptr[c + 1]; }
-            const int a0 = cp0 & ~7, cnt8 = (cp1 - a0) & ~7;
-            const int ra = r0 & ~3;
-            const int rcnt = ((r1 + 1 - ra) + 3) & ~3;
-            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
+        for (int it = 0; vchunk(it) < n_chunks; ++it) {
             const unsigned char *st = smem_raw + (size_t)slot * stage_bytes;
             const double *xw = reinterpret_cast<const double *>(st);
             const double *vs = reinterpret_cast<const double *>(st + xw_bytes);
             const uint16_t *ls = reinterpret_cast<const uint16_t *>(st + xw_bytes + LZ_XS_ES * 8);
             const int *rs = reinterpret_cast<const int *>(st + xw_bytes + LZ_XS_ES * 10);
+            const int *rm = reinterpret_cast<const int *>(st + xw_bytes + LZ_XS_ES * 10 + LZ_XS_RCAP * 4);
+            lz_mbar_wait_bounded(&full[slot], phase);
+            const int4 cd = *reinterpret_cast<const int4 *>(st + xw_bytes + LZ_XS_ES * 10 + LZ_XS_RCAP * 8);   // the chunk's descriptor rode along
+            const int a0 = cd.x, r0 = cd.z, r1 = cd.w;
+            const int ra = r0 & ~3;
+            const int rcnt = ((r1 + 1 - ra) + 3) & ~3;
+            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
             const int trips = (int)((r1 - r0 + RPW - 1) / RPW);
             const int t0 = (((warp - 1) - trip_base) % CW + CW) % CW;     // trips of all chunks dealt round-robin to the warps
             trip_base = (trip_base + trips) % CW;
-            // operands of the first trip that live in global memory: issued before the wait on the ring
             const int64_t rb0 = (int64_t)r0 + (int64_t)t0 * RPW;
-            lz_mbar_wait_bounded(&full[slot], phase);
-            for (int64_t rb = rb0; rb < r1; rb += NG) {
+            for (int64_t rb = (hint & 32) ? (int64_t)r1 : rb0; rb < r1; rb += NG) {     // hint bit 32 (dev): copies only, no compute
                 const int64_t r = rb + sub;
                 const bool valid = r < r1;
+                // output row (tiled schedules walk a row-permuted operator; the map is in the slot, or read from global when
+                // the chunk's rows did not fit the staging area)
+                int64_t ro = 0;
+                if (valid) ro = rows_ok ? rm[r - ra] : rowmap[r];
                 double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-                if (FSUB && valid) lz_ld256_stream_pol(Q0 + r * BW + 4 * l, q0, q1, q2, q3, lz_policy_evict_first());
+                if (FSUB && valid) lz_ld256_stream_pol(Q0 + ro * BW + 4 * l, q0, q1, q2, q3, lz_policy_evict_first());
                 double xa[2][2];
                 if (GRAM) {
                     const int kk = lane & 3, mm = lane >> 2;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const int64_t rr = rb + 4 * ks + kk;
+                        int64_t rro = 0;
+                        if (rr < r1) rro = rows_ok ? rm[rr - ra] : rowmap[rr];
 #pragma unroll
-                        for (int a = 0; a < 2; ++a) xa[ks][a] = rr < r1 ? __ldg(Xown + rr * BW + 8 * a + mm) : 0.0;
+                        for (int a = 0; a < 2; ++a) xa[ks][a] = rr < r1 ? __ldg(Xown + rro * BW + 8 * a + mm) : 0.0;
                     }
                 }
-                int s = 0, e = 0;
+                int s = 0, e = 0;                         // this row's entries, as slot indices
                 if (valid) {
-                    if (rows_ok) { s = rs[r - ra]; e = rs[r - ra + 1]; }
-                    else { s = rowptr[r]; e = rowptr[r + 1]; }
+                    if (rows_ok) { s = rs[r - ra] - a0; e = rs[r - ra + 1] - a0; }
+                    else { s = rowptr[r] - a0; e = rowptr[r + 1] - a0; }
                 }
                 double aA0 = 0.0, aA1 = 0.0, aB0 = 0.0, aB1 = 0.0;
+                // every entry of the chunk is in the slot: no guards inside the loop.  Slots past the row's end re-read its
+                // last entry with a zero value (adds exactly nothing; the order of the real products is the row's own)
                 for (int k0 = s; k0 < e; k0 += G) {
-                    int li[G]; double vv[G];
+                    double vv[G]; double2 xA[G], xB[G];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        const int k = k0 + g, ks = k - a0;
-                        li[g] = -1; vv[g] = 0.0;
-                        if (k < e) {
-                            if (ks < cnt8) { li[g] = ls[ks]; vv[g] = vs[ks]; }
-                            else { li[g] = lidx[k]; vv[g] = __ldcs(vals + k); }       // the (<= 7) entries the 16-byte copies cannot carry
-                        }
-                    }
-                    double2 xA[G], xB[G];
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        xA[g] = xB[g] = make_double2(0.0, 0.0);
-                        if (li[g] >= 0) {
-                            const double *row = xw + (size_t)li[g] * BW;
-                            xA[g] = *reinterpret_cast<const double2 *>(row + offA);
-                            xB[g] = *reinterpret_cast<const double2 *>(row + offB);
-                        }
+                        const int kk = min(k0 + g, e - 1);
+                        const unsigned li = ls[kk];
+                        const double v = vs[kk];
+                        vv[g] = (k0 + g < e) ? v : 0.0;
+                        const double *row = xw + li * (unsigned)BW;
+                        xA[g] = *reinterpret_cast<const double2 *>(row + offA);
+                        xB[g] = *reinterpret_cast<const double2 *>(row + offB);
                     }
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
@@ -218,8 +223,8 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int32_t *__restrict__ 
                     lz_dmma(acc0, acc1, q3, sbs[(3 * 2 + 0) * 32 + lane]); lz_dmma(acc2, acc3, q3, sbs[(3 * 2 + 1) * 32 + lane]);
                 }
                 if (valid) {
-                    if (FSUB) lz_st256_pol(W + r * BW + 4 * l, acc0, acc1, acc2, acc3, lz_policy_evict_first());
-                    else lz_st256(W + r * BW + 4 * l, acc0, acc1, acc2, acc3);
+                    if (FSUB) lz_st256_pol(W + ro * BW + 4 * l, acc0, acc1, acc2, acc3, lz_policy_evict_first());
+                    else lz_st256(W + ro * BW + 4 * l, acc0, acc1, acc2, acc3);
                 }
                 if (GRAM) {
                     // G += Xown[rb .. rb+8, :]^T W[rb .. rb+8, :]   (rows past the chunk contribute zeros: their acc is 0)
@@ -274,12 +279,12 @@ static bool spmm_xs_plan(lz_ctx *ctx, const lz_matrix *A, int bw, const double *
     if (part != 0 || ctx->knobs.no_xs || ctx->spmv_variant == 9 || !A->tma_ok) return false;
     if (lz_matrix_prepare_xs(ctx, A) != LZ_OK || A->xs_state != 1) return false;
     if (((uintptr_t)X % 16) || ((uintptr_t)W % 32)) return false;
-    if (A->xs_max_entries + 8 > LZ_XS_ES) return false;
+    if (A->xs_max_entries + 8 > LZ_XS_ES || A->xs_max_rows + 8 > LZ_XS_RCAP) return false;
     const int xw = ((A->xs_max_wrows * bw * 8) + 127) & ~127;
-    const int sb = (xw + LZ_XS_ES * 10 + LZ_XS_RCAP * 4 + 127) & ~127;
+    const int sb = (xw + LZ_XS_ES * 10 + LZ_XS_RCAP * 8 + 16 + 127) & ~127;
     const int budget = 200 * 1024;                    // dynamic shared memory left beside the static Gram / fragment tiles
     int st = budget / sb;
-    if (st > 4) st = 4;
+    if (st > 8) st = 8;
     if (ctx->knobs.xs_stages >= 2 && ctx->knobs.xs_stages < st) st = ctx->knobs.xs_stages;
     if (st < 2) return false;
     *stages = st; *stage_bytes = sb; *xw_bytes = xw;
@@ -290,13 +295,13 @@ template <int BW, bool FSUB, bool GRAM>
 static int launch_spmm_xs(lz_ctx *ctx, const lz_matrix *A, const double *X, double *W, const double *Q0, const double *Bm, int stages,
                           int stage_bytes, int xw_bytes, const double *Xown = nullptr, double *gpart = nullptr, int *grid_out = nullptr)
 {
-    const size_t smem = (size_t)stages * stage_bytes + 64;
-    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_xs<BW, LZ_XS_CW, FSUB, GRAM>, (int)smem));
+    const size_t smem = (size_t)stages * stage_bytes + 128;
+    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_xs<BW, LZ_XS_CW, FSUB, GRAM>, 200 * 1024 + 128));   // (the size varies with the operator)
     int grid = ctx->sm_count;
     if (grid > A->xs_n_chunks) grid = A->xs_n_chunks;
     if (grid_out) *grid_out = grid;
     k_spmm_xs<BW, LZ_XS_CW, FSUB, GRAM><<<grid, (1 + LZ_XS_CW) * 32, smem, ctx->stream>>>(
-        A->xs_n_chunks, A->n_rows, A->xs_chunk_row, A->xs_chunk_ptr, A->xs_meta, A->xs_seg, A->rowptr, A->xs_lidx, A->vals, X, W, Q0, Bm,
-        stages, stage_bytes, xw_bytes, ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, Xown, gpart);
+        A->xs_n_chunks, A->n_rows, A->xs_desc, A->xs_meta, A->xs_seg, A->xs_rowptr, A->xs_lidx, A->xs_vals, A->xs_rowmap, X, W, Q0, Bm,
+        stages, stage_bytes, xw_bytes, ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, Xown, gpart, A->xs_oseg);
     return LZ_OK;
 }
