@@ -180,6 +180,7 @@ def fp64_dgemm_peak():
 def cfg5_leg(ctx, lz, world, rank, dist, barrier):
     """BASELINE configs[4] (512^3, 100 steps, no reorth) at THIS world size, outside the headline timed region:
     1 warm-up + 2 timed solves, device-timed, max over ranks."""
+    import numpy as np
     import torch
     wl = WORKLOADS["cfg5"]
     m = wl["m"]

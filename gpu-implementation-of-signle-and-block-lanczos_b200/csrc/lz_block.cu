@@ -971,6 +971,7 @@ int lz_block_lanczos_workspace(lz_ctx *ctx, const lz_matrix *A, int bw, int m, i
         LZ_TRY(lz_matrix_prepare_mm(ctx, A));
         scratch = std::max(scratch, (size_t)A->mm.n_virtual * bw + 64);
     }
+    if (bw == 16 || ctx->knobs.xs_force) LZ_TRY(lz_matrix_prepare_xs(ctx, A));      // the staged SpMM's window schedule (built once per operator)
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * scratch, &p));
     return LZ_OK;
 }

@@ -63,6 +63,7 @@ struct LzKnobs {
     int split_l;            // LZ_SPLIT_L: longest virtual row of a row-split (power-law) operator, SpMV
     int no_xs;              // LZ_NO_XS: never use the operand-staging SpMM
     int xs_stages;          // LZ_XS_STAGES: ring depth of the operand-staging SpMM (0 = as many as fit, <= 8)
+    int xs_force;           // LZ_XS_FORCE: use the operand-staging SpMM wherever it can run (default: b = 16 on structured-grid operators)
     int xs_no_tiles;        // LZ_XS_NO_TILES: chunks of consecutive rows even on structured-grid operators
     int xs_tile;            // LZ_XS_TILE: target entries per chunk of its schedule (128..512, default 512)
     int split_l_mm;         // LZ_SPLIT_L_MM: the same for the SpMM's own split (default 32)
@@ -294,6 +295,7 @@ struct lz_matrix {
     int32_t *xs_rowptr, *xs_rowmap;
     double *xs_vals;
     int4 *xs_desc;                     // per chunk: (first entry, end entry, first row, end row) of the walked operator
+    uint16_t *xs_dli;                  // per walked row: window row of X[its own row] (0xFFFF: not in the chunk's window)
     int32_t *xs_oseg;                  // [chunk][LZ_XS_OGROUPS]: original row of every 8th walked row (-1 past the chunk): L2 prefetch of Q0
     int xs_tile_dims[3];               // lx, ty, tz (0: not tiled)
     // sharded operators: local rows only, columns in [0, n_local + halo_lo + halo_hi)

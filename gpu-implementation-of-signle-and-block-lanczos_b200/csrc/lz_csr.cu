@@ -219,7 +219,8 @@ static int build_mm_schedule(lz_ctx *ctx, lz_matrix *A)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_xs_build(const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ colidx, int2 *__restrict__ meta, int2 *__restrict__ seg,
-           uint16_t *__restrict__ lidx, int *__restrict__ stats /* [0] max window rows, [1] failures */)
+           uint16_t *__restrict__ lidx, int *__restrict__ stats /* [0] max window rows, [1] failures */,
+           const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ rowmap, uint16_t *__restrict__ dli)
 {
     constexpr int IPT = LZ_XS_ECAP / 256;
     typedef cub::BlockRadixSort<int, 256, IPT> Sort;
@@ -281,6 +282,14 @@ k_xs_build(const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ co
         int s2 = 0;
         while (s2 + 1 < nseg && col >= sfirst[s2 + 1]) ++s2;
         lidx[p0 + e] = (uint16_t)(soff[s2] + col - sfirst[s2]);
+    }
+    // window row of every walked row's OWN row of X (the Gram epilogue's A fragments), when the chunk references it
+    const int r0 = chunk_row[c], r1 = chunk_row[c + 1];
+    for (int i = r0 + tid; i < r1; i += 256) {
+        const int col = rowmap[i];
+        int s2 = 0;
+        while (s2 + 1 < nseg && col >= sfirst[s2 + 1]) ++s2;
+        dli[i] = (nseg > 0 && col >= sfirst[s2] && col <= slast[s2]) ? (uint16_t)(soff[s2] + col - sfirst[s2]) : (uint16_t)0xFFFF;
     }
 }
 
@@ -394,6 +403,10 @@ int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
     // ---- chunks: boxes of grid points when the operator has nested strides, runs of rows otherwise ----
     int64_t stride[3] = {1, 0, 0};
     const int ns = ctx->knobs.xs_no_tiles ? 1 : xs_detect_strides(ctx, A, stride);
+    // Measured (profiles/r02_spmm.md): with chunks that are runs of rows the staged kernel is no faster than the gathering
+    // one (the same 5x window traffic, now through the copy engine) and slower on the Maxwell operator; only box-shaped
+    // chunks pay.  Operators without nested strides keep the gathering kernel unless LZ_XS_FORCE is set.
+    if (ns < 2 && !ctx->knobs.xs_force) return LZ_OK;
     const int avg = (int)std::max<int64_t>(1, nnz / std::max<int64_t>(n, 1));
     int rows_target = (int)std::min<int64_t>(128, std::min<int64_t>((LZ_XS_ECAP - 8) / A->max_row_nnz, ctx->knobs.xs_tile * 2 / avg));
     rows_target &= ~7;
@@ -403,7 +416,7 @@ int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
     if (ns >= 2) {
         // box shape: lx rows along the unit stride, ty runs along the second stride, tz along the third
         const int64_t nx = stride[1], ny = ns == 3 ? stride[2] / stride[1] : (n + nx - 1) / nx, nz = ns == 3 ? (n + stride[2] - 1) / stride[2] : 1;
-        int lx = 16, ty = ns == 3 ? 4 : 8, tz = ns == 3 ? 2 : 1;
+        int lx = ns == 3 ? 32 : 16, ty = ns == 3 ? 2 : 8, tz = ns == 3 ? 2 : 1;      // (profiles/r02_spmm.md: box sweep)
         while (lx * ty * tz > rows_target && ty > 1) ty /= 2;
         while (lx * ty * tz > rows_target && tz > 1) tz /= 2;
         while (lx * ty * tz > rows_target && lx > 8) lx /= 2;
@@ -471,7 +484,10 @@ int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
     LZ_CUDA(cudaMemsetAsync(A->xs_lidx, 0, sizeof(uint16_t) * ((size_t)nnz2 + 16), ctx->stream));
     k_xs_max_rows<<<(unsigned)((nch + 255) / 256), 256, 0, ctx->stream>>>((int)nch, A->xs_chunk_row, A->xs_chunk_ptr, stats);
     LZ_LAUNCH_CHECK(ctx);
-    k_xs_build<<<(unsigned)nch, 256, 0, ctx->stream>>>(A->xs_chunk_ptr, cols2, A->xs_meta, A->xs_seg, A->xs_lidx, stats);
+    LZ_CUDA(cudaMalloc(&A->xs_dli, sizeof(uint16_t) * ((size_t)n + 16)));
+    LZ_CUDA(cudaMemsetAsync(A->xs_dli, 0xFF, sizeof(uint16_t) * ((size_t)n + 16), ctx->stream));
+    k_xs_build<<<(unsigned)nch, 256, 0, ctx->stream>>>(A->xs_chunk_ptr, cols2, A->xs_meta, A->xs_seg, A->xs_lidx, stats, A->xs_chunk_row, A->xs_rowmap,
+                                                       A->xs_dli);
     LZ_LAUNCH_CHECK(ctx);
     int h[4];
     LZ_CUDA(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -480,9 +496,9 @@ int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
     A->xs_n_chunks = (int)nch; A->xs_max_wrows = h[0]; A->xs_max_rows = h[2]; A->xs_max_entries = h[3];
     if (h[1] == 0 && h[0] > 0) { A->xs_state = 1; return LZ_OK; }
     cudaFree(A->xs_chunk_row); cudaFree(A->xs_chunk_ptr); cudaFree(A->xs_meta); cudaFree(A->xs_seg); cudaFree(A->xs_lidx);
-    cudaFree(A->xs_rowptr); cudaFree(A->xs_rowmap); cudaFree(A->xs_vals); cudaFree(A->xs_desc); cudaFree(A->xs_oseg);
+    cudaFree(A->xs_rowptr); cudaFree(A->xs_rowmap); cudaFree(A->xs_vals); cudaFree(A->xs_desc); cudaFree(A->xs_oseg); cudaFree(A->xs_dli);
     A->xs_chunk_row = A->xs_chunk_ptr = nullptr; A->xs_meta = A->xs_seg = nullptr; A->xs_lidx = nullptr;
-    A->xs_rowptr = A->xs_rowmap = nullptr; A->xs_vals = nullptr; A->xs_desc = nullptr; A->xs_oseg = nullptr;
+    A->xs_rowptr = A->xs_rowmap = nullptr; A->xs_vals = nullptr; A->xs_desc = nullptr; A->xs_oseg = nullptr; A->xs_dli = nullptr;
     return LZ_OK;
 }
 
@@ -937,7 +953,7 @@ int lz_matrix_destroy(lz_matrix *A)
     cudaFree(A->bin_colidx);
     cudaFree(A->bin_vals);
     cudaFree(A->xs_chunk_row); cudaFree(A->xs_chunk_ptr); cudaFree(A->xs_meta); cudaFree(A->xs_seg); cudaFree(A->xs_lidx);
-    cudaFree(A->xs_rowptr); cudaFree(A->xs_rowmap); cudaFree(A->xs_vals); cudaFree(A->xs_desc); cudaFree(A->xs_oseg);
+    cudaFree(A->xs_rowptr); cudaFree(A->xs_rowmap); cudaFree(A->xs_vals); cudaFree(A->xs_desc); cudaFree(A->xs_oseg); cudaFree(A->xs_dli);
     if (!A->mm_shared) {
         cudaFree(A->mm.vstart); cudaFree(A->mm.vrowptr); cudaFree(A->mm.vpos);
         cudaFree(A->mm.bin_colidx); cudaFree(A->mm.bin_vals);

@@ -20,7 +20,7 @@
 #pragma once
 
 #define LZ_XS_ES 1040           // entries staged per ring slot (chunk entries + alignment slack), multiple of 8
-#define LZ_XS_RCAP 640          // row pointers staged per ring slot
+#define LZ_XS_RCAP 160          // row pointers staged per ring slot
 #define LZ_XS_CW 15             // compute warps per CTA (one CTA per SM)
 
 __device__ __forceinline__ void lz_mbar_wait_bounded(uint64_t *bar, uint32_t parity)
@@ -41,13 +41,13 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ des
           const int32_t *__restrict__ rowptr, const uint16_t *__restrict__ lidx, const double *__restrict__ vals, const int32_t *__restrict__ rowmap,
           const double *__restrict__ X, double *__restrict__ W, const double *__restrict__ Q0, const double *__restrict__ Bm, const int stages,
           const int stage_bytes, const int xw_bytes, const int hint, const double *__restrict__ Xown, double *__restrict__ gpart,
-          const int32_t *__restrict__ oseg)
+          const int32_t *__restrict__ oseg, const uint16_t *__restrict__ dli)
 {
     static_assert(!GRAM || FSUB, "the fused Gram rides on the 8-row trips of the fused subtraction");
     static_assert(!FSUB || BW == 16, "the fused subtraction is written for 16-column panels");
     constexpr int LW = BW / 4, RPW = 32 / LW, NG = CW * RPW, G = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // ring slot s: [ X window (xw_bytes) | values (ES*8) | window indices (ES*2) | row pointers (RCAP*4) | row map (RCAP*4) | chunk descriptor ]
+    // ring slot s: [ X window (xw_bytes) | values (ES*8) | window indices (ES*2) | row pointers (RCAP*4) | row map (RCAP*4) | own-row window index (RCAP*2) | chunk descriptor ]
     // rowmap: row i of the walked (chunk-ordered, padded) operator is row rowmap[i] of W / Q0 / Xown
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * stage_bytes);
     uint64_t *freeb = full + 8;
@@ -106,9 +106,9 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ des
             lz_mbar_wait_bounded(&freeb[slot], phase ^ 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             const int a0 = cd.x, cnt = cd.y - cd.x;                 // multiples of 8 (the chunks are padded)
-            const int ra = cd.z & ~3;
-            const int rcnt = ((cd.w + 1 - ra) + 3) & ~3;
-            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
+            const int ra = cd.z & ~7;
+            const int rcnt = ((cd.w + 1 - ra) + 7) & ~7;
+            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 8;     // (the row arrays carry 8 spare entries)
             // window offset of this lane's segment: exclusive prefix of the segment sizes
             const int rows = lane < cmt.x ? csg.y : 0;
             int incl = rows;
@@ -119,7 +119,7 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ des
             }
             const int off = incl - rows;
             if (lane == 0)
-                lz_mbar_expect_tx(&full[slot], (uint32_t)cnt * 10u + (rows_ok ? (uint32_t)rcnt * 8u : 0u) + 16u + (uint32_t)cmt.y * (uint32_t)(BW * 8));
+                lz_mbar_expect_tx(&full[slot], (uint32_t)cnt * 10u + (rows_ok ? (uint32_t)rcnt * (GRAM ? 10u : 8u) : 0u) + 16u + (uint32_t)cmt.y * (uint32_t)(BW * 8));
             __syncwarp();
             unsigned char *sm = st + xw_bytes;
             if (lane == 0 && cnt > 0) {
@@ -133,7 +133,8 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ des
             }
             if (lane == 1 && rows_ok) lz_bulk_g2s(sm + LZ_XS_ES * 10, rowptr + ra, (uint32_t)rcnt * 4u, &full[slot]);
             if (lane == 2 && rows_ok) lz_bulk_g2s(sm + LZ_XS_ES * 10 + LZ_XS_RCAP * 4, rowmap + ra, (uint32_t)rcnt * 4u, &full[slot]);
-            if (lane == 3) lz_bulk_g2s(sm + LZ_XS_ES * 10 + LZ_XS_RCAP * 8, desc + c, 16u, &full[slot]);
+            if (lane == 3) lz_bulk_g2s(sm + LZ_XS_ES * 10 + LZ_XS_RCAP * 10, desc + c, 16u, &full[slot]);
+            if (GRAM && lane == 4 && rows_ok) lz_bulk_g2s(sm + LZ_XS_ES * 10 + LZ_XS_RCAP * 8, dli + ra, (uint32_t)rcnt * 2u, &full[slot]);
             if (rows > 0)
                 lz_bulk_g2s(st + (size_t)off * (BW * 8), X + (int64_t)csg.x * BW, (uint32_t)rows * (uint32_t)(BW * 8), &full[slot]);
             // the Q0 rows this chunk subtracts are streamed from DRAM by the compute warps a ring depth later: pull them into
@@ -158,11 +159,12 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ des
             const int *rs = reinterpret_cast<const int *>(st + xw_bytes + LZ_XS_ES * 10);
             const int *rm = reinterpret_cast<const int *>(st + xw_bytes + LZ_XS_ES * 10 + LZ_XS_RCAP * 4);
             lz_mbar_wait_bounded(&full[slot], phase);
-            const int4 cd = *reinterpret_cast<const int4 *>(st + xw_bytes + LZ_XS_ES * 10 + LZ_XS_RCAP * 8);   // the chunk's descriptor rode along
+            const uint16_t *ds = reinterpret_cast<const uint16_t *>(st + xw_bytes + LZ_XS_ES * 10 + LZ_XS_RCAP * 8);
+            const int4 cd = *reinterpret_cast<const int4 *>(st + xw_bytes + LZ_XS_ES * 10 + LZ_XS_RCAP * 10);   // the chunk's descriptor rode along
             const int a0 = cd.x, r0 = cd.z, r1 = cd.w;
-            const int ra = r0 & ~3;
-            const int rcnt = ((r1 + 1 - ra) + 3) & ~3;
-            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 1;
+            const int ra = r0 & ~7;
+            const int rcnt = ((r1 + 1 - ra) + 7) & ~7;
+            const bool rows_ok = rcnt <= LZ_XS_RCAP && (int64_t)ra + rcnt <= n_rows + 8;     // (the row arrays carry 8 spare entries)
             const int trips = (int)((r1 - r0 + RPW - 1) / RPW);
             const int t0 = (((warp - 1) - trip_base) % CW + CW) % CW;     // trips of all chunks dealt round-robin to the warps
             trip_base = (trip_base + trips) % CW;
@@ -182,10 +184,17 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ des
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const int64_t rr = rb + 4 * ks + kk;
-                        int64_t rro = 0;
-                        if (rr < r1) rro = rows_ok ? rm[rr - ra] : rowmap[rr];
+                        // the row's own row of X: from the window when the chunk references it (an operator with a diagonal), else global
+                        const unsigned dw = (rr < r1 && rows_ok) ? ds[rr - ra] : 0xFFFFu;
+                        if (dw != 0xFFFFu) {
 #pragma unroll
-                        for (int a = 0; a < 2; ++a) xa[ks][a] = rr < r1 ? __ldg(Xown + rro * BW + 8 * a + mm) : 0.0;
+                            for (int a = 0; a < 2; ++a) xa[ks][a] = xw[dw * (unsigned)BW + 8 * a + mm];
+                        } else {
+                            int64_t rro = 0;
+                            if (rr < r1) rro = rows_ok ? rm[rr - ra] : rowmap[rr];
+#pragma unroll
+                            for (int a = 0; a < 2; ++a) xa[ks][a] = rr < r1 ? __ldg(Xown + rro * BW + 8 * a + mm) : 0.0;
+                        }
                     }
                 }
                 int s = 0, e = 0;                         // this row's entries, as slot indices
@@ -194,19 +203,20 @@ k_spmm_xs(const int n_chunks, const int64_t n_rows, const int4 *__restrict__ des
                     else { s = rowptr[r] - a0; e = rowptr[r + 1] - a0; }
                 }
                 double aA0 = 0.0, aA1 = 0.0, aB0 = 0.0, aB1 = 0.0;
-                // every entry of the chunk is in the slot: no guards inside the loop.  Slots past the row's end re-read its
-                // last entry with a zero value (adds exactly nothing; the order of the real products is the row's own)
+                // every entry of the chunk is in the slot.  Slots past the row's end carry a zero value and a zero row (they add
+                // exactly nothing; the order of the real products is the row's own)
                 for (int k0 = s; k0 < e; k0 += G) {
                     double vv[G]; double2 xA[G], xB[G];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
+                        const bool on = k0 + g < e;
                         const int kk = min(k0 + g, e - 1);
                         const unsigned li = ls[kk];
-                        const double v = vs[kk];
-                        vv[g] = (k0 + g < e) ? v : 0.0;
+                        vv[g] = on ? vs[kk] : 0.0;
                         const double *row = xw + li * (unsigned)BW;
-                        xA[g] = *reinterpret_cast<const double2 *>(row + offA);
-                        xB[g] = *reinterpret_cast<const double2 *>(row + offB);
+                        // (predicated: the shared-memory data pipe is what bounds this kernel, a dead slot must not cost wavefronts)
+                        xA[g] = on ? *reinterpret_cast<const double2 *>(row + offA) : make_double2(0.0, 0.0);
+                        xB[g] = on ? *reinterpret_cast<const double2 *>(row + offB) : make_double2(0.0, 0.0);
                     }
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
@@ -277,11 +287,12 @@ static bool spmm_xs_plan(lz_ctx *ctx, const lz_matrix *A, int bw, const double *
                          int *xw_bytes)
 {
     if (part != 0 || ctx->knobs.no_xs || ctx->spmv_variant == 9 || !A->tma_ok) return false;
+    if (bw != 16 && !ctx->knobs.xs_force) return false;       // narrower panels: the per-chunk cost outweighs the gathers saved (measured)
     if (lz_matrix_prepare_xs(ctx, A) != LZ_OK || A->xs_state != 1) return false;
     if (((uintptr_t)X % 16) || ((uintptr_t)W % 32)) return false;
     if (A->xs_max_entries + 8 > LZ_XS_ES || A->xs_max_rows + 8 > LZ_XS_RCAP) return false;
     const int xw = ((A->xs_max_wrows * bw * 8) + 127) & ~127;
-    const int sb = (xw + LZ_XS_ES * 10 + LZ_XS_RCAP * 8 + 16 + 127) & ~127;
+    const int sb = (xw + LZ_XS_ES * 10 + LZ_XS_RCAP * 10 + 16 + 127) & ~127;
     const int budget = 200 * 1024;                    // dynamic shared memory left beside the static Gram / fragment tiles
     int st = budget / sb;
     if (st > 8) st = 8;
@@ -302,6 +313,6 @@ static int launch_spmm_xs(lz_ctx *ctx, const lz_matrix *A, const double *X, doub
     if (grid_out) *grid_out = grid;
     k_spmm_xs<BW, LZ_XS_CW, FSUB, GRAM><<<grid, (1 + LZ_XS_CW) * 32, smem, ctx->stream>>>(
         A->xs_n_chunks, A->n_rows, A->xs_desc, A->xs_meta, A->xs_seg, A->xs_rowptr, A->xs_lidx, A->xs_vals, A->xs_rowmap, X, W, Q0, Bm,
-        stages, stage_bytes, xw_bytes, ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, Xown, gpart, A->xs_oseg);
+        stages, stage_bytes, xw_bytes, ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, Xown, gpart, A->xs_oseg, A->xs_dli);
     return LZ_OK;
 }

@@ -33,3 +33,17 @@ def test_reference_arm_only_rank0_prints():
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29650")
     lines = run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--workload", "small", "--steps", "1", "--warmup", "0"], env)
     assert lines == []
+
+
+def test_bench_functions_import_what_they_use():
+    """bench.py imports numpy / torch lazily inside its functions (the reference arm must not need torch): every top-level
+    function that names `np` or `torch` has to import it itself -- a leg that only runs on the GPU box would otherwise
+    fail there with a NameError (this happened to the cfg5 leg)."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    module_imports = {a.asname or a.name for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom)) for a in n.names}
+    for f in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        names = {n.id for n in ast.walk(f) if isinstance(n, ast.Name)}
+        imps = {a.asname or a.name for n in ast.walk(f) if isinstance(n, (ast.Import, ast.ImportFrom)) for a in n.names}
+        for alias in ("np", "torch"):
+            assert alias not in names or alias in imps or alias in module_imports, "%s uses %s without importing it" % (f.name, alias)

@@ -65,6 +65,8 @@ for tag, env in (("peer+overlap", {}), ("nccl+overlap", {"LZ_COMM": "1"}), ("pee
             # every rank holds the same coefficients bit for bit
             t = al.clone(); dist.broadcast(t, 0); assert torch.equal(t, al), (tag, kind, reorth)
             results[(tag, kind, dims, reorth)] = (ea, eb)
+            if reorth == 1:
+                al_cgs2, be_cgs2 = al.clone(), be.clone()
         # the same slab through the host-array entry point (lz_csr_create_shard_host): identical coefficients
         rp, ci, va = A.csr_to_host()
         hlo = gran if rank > 0 else 0; hhi = gran if rank < world - 1 else 0
@@ -72,7 +74,7 @@ for tag, env in (("peer+overlap", {}), ("nccl+overlap", {"LZ_COMM": "1"}), ("pee
         al2 = torch.zeros(m, dtype=torch.float64, device="cuda"); be2 = torch.zeros(m, dtype=torch.float64, device="cuda")
         lz.check(lz.lib().lz_vector_lanczos_sharded(ctx.h, A2.h, b.data_ptr(), m, 1, al2.data_ptr(), be2.data_ptr()))
         ctx.sync()
-        assert torch.equal(al2, al) and torch.equal(be2, be), (tag, "shard_host")
+        assert torch.equal(al2, al_cgs2) and torch.equal(be2, be_cgs2), (tag, "shard_host")
         A2.close(); A.close()
     # block path, row-sharded: panels carry halo rows, every Gram matrix is all-reduced
     for bw, dims, m in ((8, (24, 20, 16), 10), (16, (24, 20, 16), 8)):

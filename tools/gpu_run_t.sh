@@ -8,7 +8,7 @@ print("$1", {k:(round(v.get("it_per_s",0),2), {c:round(x["ms"]/max(x["launches"]
 PY
 }
 {
-for env in "LZ_X=1" "LZ_SPMM_HINT=64" "LZ_XS_BOX=32,2,2" "LZ_XS_BOX=8,4,4" "LZ_XS_STAGES=2"; do
+for env in "LZ_X=1" "LZ_SPMM_HINT=32" "LZ_XS_BOX=16,4,2" "LZ_XS_BOX=64,1,2" "LZ_XS_BOX=32,1,4"; do
   env $env timeout 300 python tools/run_configs.py cfg3 > /tmp/o.log 2>&1 || tail -5 /tmp/o.log; show "cfg3 $env"
 done
 } 2>&1 | tee gpurun_out/t_sweeps.log
