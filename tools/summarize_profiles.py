@@ -72,11 +72,12 @@ def sass(kernel_regex, name):
 
 def block_kernels():
     """round 2: the block-path captures (256^3, b = 16) -> one table: time, DRAM bytes, hit rates, pipe utilisation"""
-    names = ["k_spmm_ws_plain", "k_spmm_ws_fused", "k_spmm_ws_fused_gram", "k_gram_dmma", "k_gram2_dmma", "k_panel_dmma", "k_panel2_dmma",
+    names = ["k_spmm_ws_plain", "k_spmm_ws_fused", "k_spmm_ws_fused_gram", "k_spmm_xs", "rmat_k_spmm_ws", "rmat_k_csr_spmv_ws", "k_gram_dmma", "k_gram2_dmma", "k_panel_dmma", "k_panel2_dmma",
              "k_block_project_w", "k_block_update_w", "k_csr_spmv_ws_3d"]
     cols = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_read"), ("dram__bytes_write.sum", "dram_write"),
             ("lts__t_sector_hit_rate.pct", "l2_hit_pct"), ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+            ("l1tex__m_xbar2l1tex_read_bytes.sum", "l2_to_sm_read"),
             ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1_pct"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
             ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_active_pct"),
             ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_active_pct"),
@@ -119,7 +120,7 @@ def main():
     res["sass"] = {n: sass(rx, n) for rx, n in ((r"_Z20k_cgs_update_project", "k_cgs_update_project"), (r"_Z12k_cgs_update", "k_cgs_update"),
                                                (r"_Z13k_cgs_project", "k_cgs_project"), (r"_Z13k_csr_spmv_wsILi1ELi3ELi5", "k_csr_spmv_ws"),
                                                (r"_Z9k_spmm_wsILi16ELi12ELi2ELi2048ELi2ELb0", "k_spmm_ws16"), (r"_Z9k_spmm_wsILi16ELi11ELi2ELi2048ELi2ELb1ELb1", "k_spmm_ws16_fused_gram"),
-                                               (r"_Z11k_gram_dmmaILi16", "k_gram_dmma16"),
+                                               (r"_Z9k_spmm_xsILi16ELi15ELb1ELb1", "k_spmm_xs16_fused_gram"), (r"_Z11k_gram_dmmaILi16", "k_gram_dmma16"),
                                                (r"_Z17k_block_project_wILi16", "k_block_project_w16"), (r"_Z16k_block_update_wILi16", "k_block_update_w16"),
                                                (r"_Z13k_panel2_dmmaILi16ELb1", "k_panel2_dmma16"), (r"_Z14k_basis_rotateILi8", "k_basis_rotate8"),
                                                (r"_Z16k_peer_allreduce", "k_peer_allreduce"))}
