@@ -976,6 +976,21 @@ int lz_block_lanczos_workspace(lz_ctx *ctx, const lz_matrix *A, int bw, int m, i
     return LZ_OK;
 }
 
+int lz_matrix_spmm_schedule(lz_ctx *ctx, const lz_matrix *A, int bw, int *kind, int box[3], int *window_rows)
+{
+    LZ_CHECK(ctx && A && kind && bw >= 1 && bw <= 32, LZ_ERR_INVALID, "lz_matrix_spmm_schedule: bad arguments");
+    LZ_CHECK(A->ctx == ctx, LZ_ERR_INVALID, "lz_matrix_spmm_schedule: the operator belongs to another (or a destroyed) context");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    int st = 0, sb = 0, xw = 0;
+    // (aligned dummy panel pointers: the plan only looks at their alignment)
+    const bool xs = A->rowptr && (bw == 4 || bw == 8 || bw == 16 || bw == 32) &&
+                    spmm_xs_plan(ctx, A, bw, (const double *)(uintptr_t)256, (const double *)(uintptr_t)256, 0, &st, &sb, &xw);
+    *kind = xs ? (A->xs_tile_dims[0] > 0 ? 2 : 1) : 0;
+    if (box) { box[0] = xs ? A->xs_tile_dims[0] : 0; box[1] = xs ? A->xs_tile_dims[1] : 0; box[2] = xs ? A->xs_tile_dims[2] : 0; }
+    if (window_rows) *window_rows = xs ? A->xs_max_wrows : 0;
+    return LZ_OK;
+}
+
 // Number of valid blocks of the last lz_block_lanczos run on this context: m when every W^T W was positive
 // definite to working precision, otherwise the index j of the first beta_j that was singular or not finite
 // (alpha[0..j), beta[0..j] are valid, LZ_ERR_BREAKDOWN is returned).  Synchronises.

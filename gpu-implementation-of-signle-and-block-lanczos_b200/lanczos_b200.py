@@ -54,6 +54,7 @@ def lib():
         "lz_ell_create": (i32, [vp, i64, i64, i32, i32, vp, vp, P(vp)]),
         "lz_matrix_destroy": (i32, [vp]),
         "lz_matrix_info": (i32, [vp, P(i64), P(i64), P(i64)]),
+        "lz_matrix_spmm_schedule": (i32, [vp, vp, i32, P(i32), P(i32), P(i32)]),
         "lz_matrix_csr_view": (i32, [vp, P(vp), P(vp), P(vp)]),
         "lz_gen_maxwell": (i32, [vp, i32, i32, i32, P(vp)]),
         "lz_matrix_ell_view": (i32, [vp, P(vp), P(vp)]),
@@ -404,6 +405,15 @@ def block_eigs_thick_restart(ctx, A, B, ldb, bw, k, which=0, p_blocks=None, tol=
 
 def block_lanczos(ctx, A, B, ldb, bw, m, alpha, beta, q, lc=0, reorth=REORTH_NONE):
     check(lib().lz_block_lanczos(ctx.h, A.h, _ptr(B), ldb, bw, m, lc, reorth, _ptr(alpha), _ptr(beta), _ptr(q)))
+
+
+def spmm_schedule(ctx, A, bw):
+    """(kind, box, window_rows) of the panel-product kernel the block drivers run on A at width bw:
+    kind 0 gathering kernel, 1 operand-staging with runs of rows, 2 operand-staging with box-shaped chunks."""
+    kind, win = C.c_int(0), C.c_int(0)
+    box = (C.c_int * 3)()
+    check(lib().lz_matrix_spmm_schedule(ctx.h, A.h, bw, C.byref(kind), box, C.byref(win)))
+    return kind.value, tuple(box), win.value
 
 
 def block_status(ctx, m):

@@ -99,6 +99,11 @@ int lz_ell_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int width, int la
                   const double *data, const uint32_t *idx, lz_matrix **out);
 int lz_matrix_destroy(lz_matrix *A);
 int lz_matrix_info(const lz_matrix *A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
+/* Which panel-product kernel lz_block_lanczos / lz_fdtd_block run on A at width bw (new; the reference has one SpMM,
+ * kernels/spmv_spmm.hpp:137-199).  Builds the lazily built schedules if needed.  kind: 0 gathering kernel, 1 operand-
+ * staging kernel with chunks of consecutive rows, 2 operand-staging kernel with box-shaped chunks (box[3] = rows along the
+ * unit stride, runs along the 2nd and 3rd stride; window_rows = largest number of X rows a chunk stages). */
+int lz_matrix_spmm_schedule(lz_ctx *ctx, const lz_matrix *A, int bw, int *kind, int box[3], int *window_rows);
 /* borrowed views of the CSR arrays held by A (NULL for a native ELL4 operator) */
 int lz_matrix_csr_view(const lz_matrix *A, const int32_t **rowptr, const int32_t **colidx,
                        const double **vals);

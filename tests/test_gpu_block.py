@@ -338,3 +338,35 @@ def _rmat_case(lz, ctx, orc, scale, m, mv):
     ov = orc.vector_lanczos((rp, ci, va), B[:, 0].copy(), mv, reorth=1)
     assert np.max(np.abs(al - ov["alpha"])) < 1e-10 * np.abs(ov["alpha"]).max()
     assert np.max(np.abs(be - ov["beta"]) / ov["beta"]) < 1e-10
+
+
+@pytest.mark.parametrize("dims", [(40, 36, 24), (64, 24, 18), (96, 80)])
+def test_box_chunk_staged_spmm_on_ragged_grids(lz, ctx, orc, dims):
+    """Operand-staging SpMM (lz_spmm_xs.cuh) with box-shaped chunks on grids whose sides are NOT multiples of the box
+    (clipped boxes, chunk padding, row map): the schedule must engage (kind 2), the block recurrence (fused subtraction +
+    Gram epilogue), the reorthogonalised one (fused subtraction only) and the plain product (block fdtd) must agree with
+    the oracle; with LZ_NO_XS the same coefficients come from the gathering kernel (tests/test_gpu_paths.py)."""
+    bw, m = 16, 6
+    if len(dims) == 3:
+        A = lz.Matrix.laplacian3d(ctx, *dims); csr = orc.lap3d(*dims)
+    else:
+        A = lz.Matrix.laplacian2d(ctx, *dims); csr = orc.lap2d(*dims)
+    n = int(np.prod(dims))
+    kind, box, win = lz.spmm_schedule(ctx, A, bw)
+    assert kind == 2 and box[0] >= 8 and win > 0, (kind, box, win)
+    assert lz.spmm_schedule(ctx, A, 8)[0] == 0            # narrower panels keep the gathering kernel (measured slower)
+    B = orc.start_block(n, bw)
+    for reorth in (0, 1):
+        ref = orc.block_lanczos(csr, B, m, lc=7, reorth=reorth)
+        a, b, q = run_block(lz, ctx, A, B, m, 7, reorth=reorth)
+        assert block_err(a, ref["alpha"], m) < 1e-10 and block_err(b, ref["beta"], m) < 1e-10, (dims, reorth)
+        assert np.max(np.abs(q - ref["q"])) < 1e-10 * np.abs(ref["q"]).max()
+    # plain product: 40 explicit Euler steps of U' = -0.05 A U against the oracle's loop
+    rp, ci, va = csr
+    As = lz.Matrix.from_csr(ctx, torch.from_numpy(rp).cuda(), torch.from_numpy(ci).cuda(), torch.from_numpy(-0.05 * va).cuda())
+    assert lz.spmm_schedule(ctx, As, bw)[0] == 2
+    U0 = orc.start_block(n, bw)
+    want = orc.fdtd_block((rp, ci, -0.05 * va), U0, 40, 1.0)
+    got = lz.fdtd_block(ctx, As, cm(U0), n, bw, 40, 1.0, lc=n // 3)
+    assert np.max(np.abs(got - want[n // 3])) < 1e-12 * np.max(np.abs(want[n // 3]))
+    As.close(); A.close()

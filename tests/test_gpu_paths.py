@@ -67,10 +67,13 @@ def test_dgks_mode_matches_cgs2_oracle(lz, ctx, orc, problem):
     A.close()
 
 
-@pytest.mark.parametrize("env", [{}, {"LZ_NO_SPMM_GRAM": "1"}, {"LZ_NO_SPMM_FUSE": "1"}, {"LZ_SPMV_VARIANT": "9"}])
+@pytest.mark.parametrize("env", [{}, {"LZ_NO_SPMM_GRAM": "1"}, {"LZ_NO_SPMM_FUSE": "1"}, {"LZ_SPMV_VARIANT": "9"}, {"LZ_NO_XS": "1"},
+                                 {"LZ_NO_XS": "1", "LZ_NO_SPMM_GRAM": "1"}, {"LZ_XS_NO_TILES": "1", "LZ_XS_FORCE": "1"},
+                                 {"LZ_XS_BOX": "16,4,2"}, {"LZ_XS_BOX": "8,2,1", "LZ_XS_STAGES": "2"}])
 def test_block_paths_agree_with_oracle(lz, orc, monkeypatch, env):
-    """b = 16: the staged SpMM with the fused DMMA subtraction and Gram epilogue (default), the same with a separate
-    Gram pass, the plain staged SpMM + two-Gram formulation, and the LDG SpMM + two-Gram formulation."""
+    """b = 16: the operand-staging SpMM with box-shaped chunks, fused DMMA subtraction and Gram epilogue (default), the same
+    with a separate Gram pass, the plain SpMM + two-Gram formulation, the LDG SpMM + two-Gram formulation, the gathering
+    kernel (LZ_NO_XS) with and without the Gram epilogue, the staged kernel on runs of rows, other box shapes / ring depths."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     for k, v in env.items():
