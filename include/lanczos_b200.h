@@ -83,7 +83,11 @@ int lz_fill(lz_ctx *ctx, int64_t n, double value, double *x);   /* v::set_entrie
 /* ---- sparse operators ------------------------------------------------------------------ */
 /* CSR (new container in the reference's style).  Arrays are borrowed device
  * pointers: rowptr[n_rows+1], colidx[nnz] (int32), vals[nnz] (fp64).  Builds the row-block
- * schedule (short rows streamed through shared memory, long rows split). */
+ * schedule (short rows streamed through shared memory, long rows split).
+ * The arrays must stay alive AND UNCHANGED while the operator exists: the operator keeps derived, re-ordered copies of
+ * them (length-binned virtual rows of power-law operators; the chunk-ordered copy of the operand-staging SpMM, built by
+ * the first panel product), some of them lazily -- re-create the operator after changing a value.  One operator is used
+ * from one host thread at a time (the lazily built schedules are not locked). */
 int lz_csr_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *rowptr,
                   const int32_t *colidx, const double *vals, lz_matrix **out);
 /* same from HOST arrays: the library owns the device copy (Csr_matrix::copy_to_device role) */
