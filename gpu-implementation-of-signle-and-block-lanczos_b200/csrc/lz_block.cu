@@ -213,14 +213,18 @@ __device__ __forceinline__ uint64_t lz_policy_evict_last()
 // accumulator layout), the A fragments are the trip's own rows of X read straight from global (L1 hits: a stencil row
 // has just gathered its diagonal neighbour), 8 more DMMAs per trip.
 #define SPMM_GST 20            // row stride (doubles) of the per-warp Gram staging tile: conflict-free fragment reads
-template <int BW, int CW, int STAGES, int CAP, int MINB, bool FSUB, bool GRAM = false, int GIN = 4>
+// DST (row-split operators): row r of the walked operator goes to row dst[r] of Wd when dst[r] >= 0 (a row that was not
+// cut: no partial row, no combine), to row r of W (the partial-row buffer) otherwise.
+template <int BW, int CW, int STAGES, int CAP, int MINB, bool FSUB, bool GRAM = false, int GIN = 4, bool DST = false>
 __global__ void __launch_bounds__((1 + CW) * 32, MINB)
 k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ chunk_ptr,
           const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
           const double *__restrict__ X, double *__restrict__ W, const double *__restrict__ Q0, const double *__restrict__ Bm,
           const LzChunkRange cr, const int run, const int hint, const int64_t ldx, const int64_t ldw,
-          const double *__restrict__ Xown = nullptr, double *__restrict__ gpart = nullptr)
+          const double *__restrict__ Xown = nullptr, double *__restrict__ gpart = nullptr,
+          const int32_t *__restrict__ dst = nullptr, double *__restrict__ Wd = nullptr)
 {
+    static_assert(!DST || !FSUB, "direct rows are for the plain product");
     static_assert(!GRAM || FSUB, "the fused Gram rides on the 8-row trips of the fused subtraction");
     // ldx / ldw: doubles between consecutive rows of X / W (= BW for a whole panel; a BW-column slice of a wider
     // row-major panel otherwise: power-law operators run wide panels slice by slice so that the rows gathered again
@@ -337,6 +341,8 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                     if (rows_ok) { s = rs[r - ra]; e = rs[r - ra + 1]; }
                     else { s = rowptr[r]; e = rowptr[r + 1]; }
                 }
+                int drow = -1;
+                if (DST && valid) drow = dst[r];
                 double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
                 const double *Xl = X + 4 * l;
                 const int64_t ldx_ = FSUB ? (int64_t)BW : ldx, ldw_ = FSUB ? (int64_t)BW : ldw;
@@ -377,6 +383,7 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
                 }
                 if (valid) {
                     if (FSUB) lz_st256_pol(W + r * ldw_ + 4 * l, acc0, acc1, acc2, acc3, lz_policy_evict_first());
+                    else if (DST && drow >= 0) lz_st256(Wd + (int64_t)drow * ldw_ + 4 * l, acc0, acc1, acc2, acc3);
                     else lz_st256(W + r * ldw_ + 4 * l, acc0, acc1, acc2, acc3);
                 }
                 if (GRAM) {
@@ -430,14 +437,15 @@ k_spmm_ws(int n_chunks, int64_t n_rows, const int32_t *__restrict__ chunk_row, c
     }
 }
 
-template <int BW, int CW, int STAGES, int MINB, bool FSUB, bool GRAM = false, int GIN = 4>
+template <int BW, int CW, int STAGES, int MINB, bool FSUB, bool GRAM = false, int GIN = 4, bool DST = false>
 static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *rowptr, int64_t n_rows, const double *X, double *W,
                                 const double *Q0, const double *Bm, int run, int part, int64_t ldx = BW, int64_t ldw = BW,
-                                const double *Xown = nullptr, double *gpart = nullptr, int *grid_out = nullptr)
+                                const double *Xown = nullptr, double *gpart = nullptr, int *grid_out = nullptr,
+                                const int32_t *dst = nullptr, double *Wd = nullptr)
 {
     constexpr int CAP = 2048;
     const size_t smem = (size_t)STAGES * (CAP * 12 + SPMM_WS_RCAP * 4) + 16 * STAGES;
-    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM, GIN>, (int)smem));
+    LZ_TRY(lz_func_smem_optin(ctx, (const void *)k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM, GIN, DST>, (int)smem));
     const int nch = A->mm_n_chunks;
     LzChunkRange cr = {0, nch, 0, nch};
     if (part == 1) cr = {A->mm_bnd_lo, A->mm_bnd_hi - A->mm_bnd_lo, 0, A->mm_bnd_hi - A->mm_bnd_lo};
@@ -447,9 +455,9 @@ static int launch_spmm_ws_shape(lz_ctx *ctx, const lz_matrix *A, const int32_t *
     if (grid > cr.total) grid = cr.total;
     const int per_cta = (cr.total + grid - 1) / grid;
     if (grid_out) *grid_out = grid;
-    k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM, GIN><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
+    k_spmm_ws<BW, CW, STAGES, CAP, MINB, FSUB, GRAM, GIN, DST><<<grid, (1 + CW) * 32, smem, ctx->stream>>>(
         nch, n_rows, A->mm_chunk_row, A->mm_chunk_ptr, rowptr, A->mm_k_colidx, A->mm_k_vals, X, W, Q0, Bm, cr, run > 0 ? run : per_cta,
-        ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, ldx, ldw, Xown, gpart);   // hint bit 1: evict-first on the matrix streams
+        ctx->knobs.spmm_hint >= 0 ? ctx->knobs.spmm_hint : 0, ldx, ldw, Xown, gpart, dst, Wd);   // hint bit 1: evict-first on the matrix streams
     return LZ_OK;
 }
 
@@ -693,6 +701,81 @@ k_split_combine_rows(int64_t n_rows, int bw, const int32_t *__restrict__ vstart,
     }
 }
 
+// the same for the panel widths the block drivers use: BW threads per row (no division per element), four rows per thread
+// in flight -- the chain vstart -> vpos -> Wbar is three dependent loads, and one row at a time left the kernel waiting
+// on them (R-MAT scale 24, b = 32: the combine cost as much as half of the product it follows)
+template <int BW>
+__global__ void __launch_bounds__(256)
+k_split_combine_rows_t(int64_t n_rows, const int32_t *__restrict__ vstart, const int32_t *__restrict__ vpos,
+                       const double *__restrict__ Wbar, double *__restrict__ W, const int skip_single)
+{
+    constexpr int RPB = 256 / BW, U = 4;
+    const int c = threadIdx.x % BW, sub = threadIdx.x / BW;
+    for (int64_t rb = (int64_t)blockIdx.x * (RPB * U); rb < n_rows; rb += (int64_t)gridDim.x * (RPB * U)) {
+        int v0[U], v1[U];
+        int64_t pos[U];
+        double t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = rb + u * RPB + sub;
+            v0[u] = v1[u] = 0;
+            if (r < n_rows) { v0[u] = vstart[r]; v1[u] = vstart[r + 1]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (v1[u] - v0[u] > LZ_LONG_PIECES) v1[u] = v0[u];             // hub rows: k_split_combine_long
+            if (skip_single && v1[u] - v0[u] == 1) v1[u] = v0[u];          // uncut rows: the product wrote them itself
+            pos[u] = v1[u] > v0[u] ? (vpos ? (int64_t)vpos[v0[u]] : (int64_t)v0[u]) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = pos[u] >= 0 ? __ldcs(Wbar + pos[u] * BW + c) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            for (int v = v0[u] + 1; v < v1[u]; v += 4) {                    // pieces in row order, four loads in flight
+                double x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = v + j < v1[u] ? __ldcs(Wbar + (int64_t)(vpos ? vpos[v + j] : v + j) * BW + c) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (v + j < v1[u]) t[u] += x[j];
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = rb + u * RPB + sub;
+            if (r < n_rows && pos[u] >= 0) W[r * BW + c] = t[u];
+        }
+    }
+}
+
+// hub rows: one CTA per row, warp w adds the pieces v0 + w, v0 + w + 8, ... (four loads in flight), the eight partial rows
+// are added in warp order -- a fixed order, so the result does not depend on the launch
+__global__ void __launch_bounds__(256)
+k_split_combine_long(int bw, const int32_t *__restrict__ long_rows, const int32_t *__restrict__ vstart, const int32_t *__restrict__ vpos,
+                     const double *__restrict__ Wbar, double *__restrict__ W)
+{
+    __shared__ double part[8][32];
+    const int64_t r = long_rows[blockIdx.x];
+    const int v0 = vstart[r], v1 = vstart[r + 1];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double t = 0.0;
+    if (lane < bw) {
+        for (int v = v0 + w; v < v1; v += 32) {
+            double x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = v + 8 * j < v1 ? __ldcs(Wbar + (int64_t)(vpos ? vpos[v + 8 * j] : v + 8 * j) * bw + lane) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t += x[j];
+        }
+    }
+    part[w][lane] = t;
+    __syncthreads();
+    if (w == 0 && lane < bw) {
+        double s = part[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s += part[k][lane];
+        W[r * bw + lane] = s;
+    }
+}
+
 static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, double *W, const double *Q0, const double *Bm, int part = 0)
 {
     if (!A->vrowptr) return spmm_rm_rows(ctx, A, A->rowptr, A->n_rows, bw, X, W, Q0, Bm, part);
@@ -701,6 +784,7 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
     // row-split operator: partial rows per virtual row, then an ordered combine
     LZ_CHECK(Q0 == nullptr, LZ_ERR_UNSUPPORTED, "fused subtraction is not available on a row-split operator");
     void *wbar;
+    int direct = 0;
     LZ_TRY(lz_ctx_scratch(ctx, sizeof(double) * (size_t)A->mm.n_virtual * bw + 64, &wbar));
     // Power-law operator, wide panel: the gathered rows are random.  Running the panel in 8-column slices (64-byte row
     // pieces, four times as many hub rows resident in L2, the matrix streamed once per slice) was measured: every slice
@@ -716,10 +800,33 @@ static int spmm_rm(lz_ctx *ctx, const lz_matrix *A, int bw, const double *X, dou
             LZ_LAUNCH_CHECK(ctx);
         }
         lz_prof_end(ctx);
+    } else if ((bw == 8 || bw == 16 || bw == 32) && A->mm.dst && A->tma_ok && A->mm_chunk_row && ctx->spmv_variant != 9 && !ctx->knobs.no_direct_rows &&
+               ((uintptr_t)X % 32 == 0) && ((uintptr_t)wbar % 32 == 0) && ((uintptr_t)W % 32 == 0)) {
+        // rows that were not cut (three quarters of an R-MAT operator's) go straight to W: no partial row, no combine
+        lz_prof_begin(ctx, LZ_K_SPMM, 12.0 * (double)A->nnz + 8.0 * (double)A->mm.n_virtual + 16.0 * (double)A->mm.n_virtual * bw);
+        const int run = ctx->knobs.spmm_run;
+        if (bw == 8) LZ_TRY((launch_spmm_ws_shape<8, 12, 2, 2, false, false, 4, true>(ctx, A, A->mm.vrowptr, A->mm.n_virtual, X, (double *)wbar, nullptr, nullptr, run, 0, 8, 8, nullptr, nullptr, nullptr, A->mm.dst, W)));
+        else if (bw == 16) LZ_TRY((launch_spmm_ws_shape<16, 12, 2, 2, false, false, 4, true>(ctx, A, A->mm.vrowptr, A->mm.n_virtual, X, (double *)wbar, nullptr, nullptr, run, 0, 16, 16, nullptr, nullptr, nullptr, A->mm.dst, W)));
+        else LZ_TRY((launch_spmm_ws_shape<32, 12, 2, 2, false, false, 4, true>(ctx, A, A->mm.vrowptr, A->mm.n_virtual, X, (double *)wbar, nullptr, nullptr, run, 0, 32, 32, nullptr, nullptr, nullptr, A->mm.dst, W)));
+        LZ_LAUNCH_CHECK(ctx);
+        lz_prof_end(ctx);
+        direct = 1;
     } else
     LZ_TRY(spmm_rm_rows(ctx, A, A->mm.vrowptr, A->mm.n_virtual, bw, X, (double *)wbar, nullptr, nullptr));
-    k_split_combine_rows<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A->n_rows, bw, A->mm.vstart, A->mm.vpos, (const double *)wbar, W);
+    // ordered combine of the partial rows (counted in the SpMM class: it is part of the product on such operators)
+    lz_prof_begin(ctx, LZ_K_SPMM, 8.0 * ((double)A->mm.n_virtual + (double)A->n_rows) * bw);
+    const unsigned cg = (unsigned)ctx->sm_count * 8;
+    if (bw == 32) k_split_combine_rows_t<32><<<cg, 256, 0, ctx->stream>>>(A->n_rows, A->mm.vstart, A->mm.vpos, (const double *)wbar, W, direct);
+    else if (bw == 16) k_split_combine_rows_t<16><<<cg, 256, 0, ctx->stream>>>(A->n_rows, A->mm.vstart, A->mm.vpos, (const double *)wbar, W, direct);
+    else if (bw == 8) k_split_combine_rows_t<8><<<cg, 256, 0, ctx->stream>>>(A->n_rows, A->mm.vstart, A->mm.vpos, (const double *)wbar, W, direct);
+    else if (bw == 4) k_split_combine_rows_t<4><<<cg, 256, 0, ctx->stream>>>(A->n_rows, A->mm.vstart, A->mm.vpos, (const double *)wbar, W, direct);
+    else k_split_combine_rows<<<cg, 256, 0, ctx->stream>>>(A->n_rows, bw, A->mm.vstart, A->mm.vpos, (const double *)wbar, W);
     LZ_LAUNCH_CHECK(ctx);
+    if (A->mm.n_long > 0 && (bw == 32 || bw == 16 || bw == 8 || bw == 4)) {
+        k_split_combine_long<<<A->mm.n_long, 256, 0, ctx->stream>>>(bw, A->mm.long_rows, A->mm.vstart, A->mm.vpos, (const double *)wbar, W);
+        LZ_LAUNCH_CHECK(ctx);
+    }
+    lz_prof_end(ctx);
     return LZ_OK;
 }
 

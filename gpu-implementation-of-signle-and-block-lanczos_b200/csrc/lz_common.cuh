@@ -63,6 +63,7 @@ struct LzKnobs {
     int split_l;            // LZ_SPLIT_L: longest virtual row of a row-split (power-law) operator, SpMV
     int no_xs;              // LZ_NO_XS: never use the operand-staging SpMM
     int xs_stages;          // LZ_XS_STAGES: ring depth of the operand-staging SpMM (0 = as many as fit, <= 8)
+    int no_direct_rows;     // LZ_NO_DIRECT_ROWS: row-split SpMM writes every row as a partial row (A/B)
     int xs_force;           // LZ_XS_FORCE: use the operand-staging SpMM wherever it can run (default: b = 16 on structured-grid operators)
     int xs_no_tiles;        // LZ_XS_NO_TILES: chunks of consecutive rows even on structured-grid operators
     int xs_tile;            // LZ_XS_TILE: target entries per chunk of its schedule (128..512, default 512)
@@ -233,7 +234,15 @@ struct LzSplit {
     int n_virtual;
     int32_t *vstart, *vrowptr, *vpos, *bin_colidx;
     double *bin_vals;
+    // rows cut into more than LZ_LONG_PIECES pieces (the hubs): their ordered combine gets a CTA each, a thread walking
+    // 12 000 pieces one after the other was the longest thing in the whole product
+    int32_t *long_rows;
+    int n_long;
+    // where the product's row at (binned) position i goes: >= 0 the operator row it IS (a row that was not cut: written
+    // straight into W), < 0 position ~i of the partial-row buffer (combined afterwards)
+    int32_t *dst;
 };
+#define LZ_LONG_PIECES 32
 
 struct lz_matrix {
     lz_ctx *ctx;             // NULL once the owning context has been destroyed (orphaned: only destroy is legal)
@@ -274,6 +283,7 @@ struct lz_matrix {
     // gathers one 128..256-byte panel row per entry and a 256-entry row leaves the other groups of its chunk idle), the
     // SpMV wants long ones (fewer partial sums).  Built on the first panel product unless both lengths agree (then shared).
     LzSplit mm;
+    int32_t *sv_long_rows, *sv_dst;
     int mm_pending, mm_shared;
     const int32_t *mm_k_colidx;
     const double *mm_k_vals;

@@ -124,6 +124,34 @@ k_bin_copy(int64_t nv, const int32_t *__restrict__ old_ptr, const int32_t *__res
     for (int k = lane; k < len; k += 32) { ncol[dst + k] = colidx[src + k]; nval[dst + k] = vals[src + k]; }
 }
 
+__global__ void k_long_rows(int64_t n_rows, const int32_t *__restrict__ vstart, int32_t *__restrict__ list, int cap, int *__restrict__ counter)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    if (vstart[r + 1] - vstart[r] > LZ_LONG_PIECES) {
+        const int i = atomicAdd(counter, 1);
+        if (i < cap) list[i] = (int32_t)r;
+    }
+}
+
+__global__ void k_split_dst(int64_t n_rows, const int32_t *__restrict__ vstart, const int32_t *__restrict__ vpos, int32_t *__restrict__ dst)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int v0 = vstart[r], v1 = vstart[r + 1];
+    for (int v = v0; v < v1; ++v) {
+        const int i = vpos ? vpos[v] : v;
+        dst[i] = (v1 - v0 == 1) ? (int32_t)r : ~i;
+    }
+}
+static int build_split_dst(lz_ctx *ctx, const lz_matrix *A, LzSplit *S)
+{
+    LZ_CUDA(cudaMalloc(&S->dst, sizeof(int32_t) * ((size_t)S->n_virtual + 8)));
+    k_split_dst<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, S->vstart, S->vpos, S->dst);
+    LZ_LAUNCH_CHECK(ctx);
+    return LZ_OK;
+}
+
 // One row split of A with virtual rows of <= split_l entries into S (all arrays owned by S; bin_* stay NULL when the
 // length binning is switched off)
 static int build_split(lz_ctx *ctx, const lz_matrix *A, int split_l, LzSplit *S)
@@ -147,10 +175,21 @@ static int build_split(lz_ctx *ctx, const lz_matrix *A, int split_l, LzSplit *S)
     LZ_CUDA(cudaFree(tmp));
     LZ_CUDA(cudaFree(pieces));
     S->n_virtual = nv;
+    {   // the hub rows (more than LZ_LONG_PIECES pieces), in no particular order
+        const int cap = nv / LZ_LONG_PIECES + 1;
+        int *counter = ctx->flags + 20;
+        LZ_CUDA(cudaMalloc(&S->long_rows, sizeof(int32_t) * (size_t)cap));
+        LZ_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+        k_long_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, S->vstart, S->long_rows, cap, counter);
+        LZ_LAUNCH_CHECK(ctx);
+        LZ_CUDA(cudaMemcpyAsync(&S->n_long, counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (S->n_long > cap) S->n_long = cap;
+    }
     LZ_CUDA(cudaMalloc(&S->vrowptr, sizeof(int32_t) * ((size_t)nv + 8)));
     k_split_fill<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->csr_nnz, A->rowptr, S->vstart, S->vrowptr, split_l);
     LZ_LAUNCH_CHECK(ctx);
-    if (!ctx->knobs.rmat_reorder || (int64_t)nv / LZ_BIN_WINDOW >= (1 << 22)) return LZ_OK;
+    if (!ctx->knobs.rmat_reorder || (int64_t)nv / LZ_BIN_WINDOW >= (1 << 22)) return build_split_dst(ctx, A, S);
     // ---- length binning of the virtual rows (see above) ----
     const unsigned gv = (unsigned)(((int64_t)nv + 1 + 255) / 256);
     uint32_t *keys, *keys2;
@@ -185,7 +224,7 @@ static int build_split(lz_ctx *ctx, const lz_matrix *A, int split_l, LzSplit *S)
     LZ_CUDA(cudaFree(S->vrowptr));
     S->vrowptr = nptr;              // virtual row pointers in binned order, over the binned copies below
     S->bin_colidx = ncol; S->bin_vals = nval;
-    return LZ_OK;
+    return build_split_dst(ctx, A, S);
 }
 
 // the SpMM kernel amortises its per-chunk cost over wider rows: its own, coarser schedule, over the rows of ITS split
@@ -531,6 +570,7 @@ static int build_schedule(lz_ctx *ctx, lz_matrix *A)
         LZ_TRY(build_split(ctx, A, ctx->knobs.split_l, &S));
         A->n_virtual = S.n_virtual; A->vstart = S.vstart; A->vrowptr = S.vrowptr; A->vpos = S.vpos;
         A->bin_colidx = S.bin_colidx; A->bin_vals = S.bin_vals;
+        A->sv_long_rows = S.long_rows; A->sv_dst = S.dst;                                                  // (kept only to be freed: the SpMV combine does not use it)
         LZ_CUDA(cudaMalloc(&A->ybar, sizeof(double) * ((size_t)S.n_virtual + 8)));
         if (ctx->knobs.split_l_mm == ctx->knobs.split_l) { A->mm = S; A->mm_shared = 1; }
         else A->mm_pending = 1;                                                         // built by the first panel product
@@ -958,6 +998,9 @@ int lz_matrix_destroy(lz_matrix *A)
         cudaFree(A->mm.vstart); cudaFree(A->mm.vrowptr); cudaFree(A->mm.vpos);
         cudaFree(A->mm.bin_colidx); cudaFree(A->mm.bin_vals);
     }
+    cudaFree(A->mm.long_rows);          // (the SpMV's split keeps its lists in the same struct when the two are shared)
+    cudaFree(A->mm.dst);
+    if (!A->mm_shared) { cudaFree(A->sv_long_rows); cudaFree(A->sv_dst); }
     delete A;
     return LZ_OK;
 }

@@ -82,6 +82,7 @@ int lz_ctx_create(int device, void *stream, lz_ctx **out)
     if (k.split_l > 256) k.split_l = 256;
     k.no_xs = env_set("LZ_NO_XS");
     k.xs_stages = env_int("LZ_XS_STAGES", 0);
+    k.no_direct_rows = env_set("LZ_NO_DIRECT_ROWS");
     k.xs_force = env_set("LZ_XS_FORCE");
     k.xs_no_tiles = env_set("LZ_XS_NO_TILES");
     k.xs_tile = env_int("LZ_XS_TILE", LZ_XS_TILE);
