@@ -1,22 +1,28 @@
-// lz_spmm_xs.cuh -- operand-staging SpMM for operators whose chunks reference few contiguous column ranges (stencils,
-// banded operators; the reference's spmm(), kernels/spmv_spmm.hpp:137-199, on such matrices).
+// lz_spmm_xs.cuh -- operand-staging SpMM for structured-grid operators (the reference's spmm(),
+// kernels/spmv_spmm.hpp:137-199, on its stencil matrices; BASELINE config 3).
 //
-// k_spmm_ws gathers the rows of X with global loads: L1 tag look-ups and ~40 % occupancy bound it (profiles/r02_spmm.md:
-// no unit saturated, the warps wait on L2 hits).  Here the rows a chunk needs -- its X WINDOW, a handful of contiguous
-// row ranges worked out once per operator by k_xs_build (lz_csr.cu) -- are bulk-copied (cp.async.bulk, one copy per
-// segment, issued by the lanes of the producer warp) into the ring slot together with the chunk's values, row pointers
-// and 16-bit window indices, STAGES-1 chunks ahead.  The compute warps then gather from shared memory: no long-latency
-// load is left inside the entry loop, the occupancy needed drops to one 16-warp CTA per SM, and the matrix stream
-// shrinks from 12 to 10 bytes per entry (the 32-bit column index is not read at all).
+// What bounds the gathering kernel (k_spmm_ws) is not the latency of its gathers but the bytes they pull from L2 to the
+// SMs: a chunk of consecutive rows of a 7-point operator touches every row of X 5.1 times (ncu: 15.4 GB L2 -> SM for
+// 7.7 GB of algorithmic traffic; profiles/r02_spmm.md).  Two changes together, neither alone:
+//   * chunks are BOXES of grid points (lz_matrix_prepare_xs, lz_csr.cu: nested strides found from the operator itself; the
+//     product walks a chunk-ordered, 8-entry-padded copy of the operator and writes row rowmap[i]), so a row of X is needed
+//     by 3.1 chunks instead of 5.1;
+//   * the rows a chunk needs -- its X WINDOW, <= 32 contiguous row ranges worked out once per operator by k_xs_build --
+//     are bulk-copied (cp.async.bulk, one copy per segment, issued by the lanes of the producer warp) into the ring slot
+//     together with the chunk's values, row pointers, row map, 16-bit window indices and its descriptor, two or three
+//     chunks ahead; the compute warps gather from shared memory.  No load of the chunk loop waits for a load issued in
+//     the same iteration (descriptors two chunks ahead, the Q0 rows prefetched into L2 by the producer), and the matrix
+//     stream shrinks from 12 to 10 bytes per entry (the 32-bit column index is not read at all).
+// One 16-warp CTA per SM.  The kernel ends up bound by the shared-memory data pipe (81 %).
 //
 // Bank conflicts: a lane owns four adjacent columns (32 bytes) of a row and reads them as two 128-bit loads; a quarter
 // warp (one wavefront) spans two row groups, whose rows sit at arbitrary multiples of 128 bytes.  Lane groups with odd
 // (lane >> 2) read their upper 16 bytes first: the eight lanes of a wavefront then cover all 32 banks.  The accumulators
 // of those lanes are kept in the swapped order and put back once per row.
 //
-// FSUB / GRAM: the fused DMMA subtraction W = A X - Q0 B and the Gram epilogue of k_spmm_ws, unchanged (same fragment
-// labelling, same reduction order inside a CTA); the Q0 and Xown rows of a trip are fetched BEFORE the entry loop (the
-// kernel has registers to spare at one CTA per SM), so their latency overlaps the shared-memory gathers.
+// FSUB / GRAM: the fused DMMA subtraction W = A X - Q0 B and the Gram epilogue of k_spmm_ws (same fragment labelling,
+// same reduction order inside a CTA); the Q0 rows of a trip are fetched BEFORE the entry loop (L2 hits thanks to the
+// prefetch), the trip's own rows of X (Gram A fragments) come from the staged window when the chunk references them.
 #pragma once
 
 #define LZ_XS_ES 1040           // entries staged per ring slot (chunk entries + alignment slack), multiple of 8
