@@ -388,11 +388,93 @@ __global__ void k_xs_desc(int n_chunks, const int32_t *__restrict__ chunk_row, c
     for (int g = 0; g < LZ_XS_OGROUPS; ++g) oseg[(size_t)c * LZ_XS_OGROUPS + g] = r0 + 8 * g < r1 ? rowmap[r0 + 8 * g] : -1;
 }
 
-// Structured-grid detection on a sample of interior rows: the offsets (column - row) present in at least half of the
-// sampled rows.  A 7-point operator on an nx x ny x nz grid gives {0, +-1, +-nx, +-nx*ny}: strides 1 | nx | nx*ny.
-// Returns the number of nested strides found (1: only the unit stride, i.e. a banded operator).
+// ---- host logic of the box schedule (pure host code behind two C-ABI entry points, so the CPU test suite covers it) ----
+
+// Structured-grid detection on a sample of rows (HOST arrays: rowptr[0..rows] of the sample, its column indices, the
+// operator row of sample row 0): the offsets (column - row) present in at least half of the sampled rows.  A 7-point
+// operator on an nx x ny x nz grid gives {0, +-1, +-nx, +-nx*ny}: strides 1 | nx | nx*ny.  Returns the number of nested
+// strides found (1: only the unit stride, i.e. a banded operator; 0: not even that).
+static int xs_strides_from_sample(int64_t rows, int64_t row0, const int32_t *rp, const int32_t *ci, int64_t stride[3])
+{
+    if (rows < 64) return 0;
+    const int64_t cnt = (int64_t)rp[rows] - rp[0];
+    if (cnt <= 0 || cnt > rows * 64) return 0;
+    std::vector<int64_t> offs;
+    offs.reserve(cnt);
+    for (int64_t r = 0; r < rows; ++r)
+        for (int64_t k = rp[r] - rp[0]; k < rp[r + 1] - rp[0]; ++k) offs.push_back((int64_t)ci[k] - (row0 + r));
+    std::sort(offs.begin(), offs.end());
+    std::vector<int64_t> common;
+    for (size_t a = 0; a < offs.size();) {
+        size_t b = a;
+        while (b < offs.size() && offs[b] == offs[a]) ++b;
+        if ((int64_t)(b - a) * 2 >= rows && offs[a] > 0) common.push_back(offs[a]);
+        a = b;
+    }
+    if (common.empty() || common[0] != 1) return 0;
+    int ns = 1;
+    stride[0] = 1;
+    for (size_t a = 1; a < common.size() && ns < 3; ++a)
+        if (common[a] % stride[ns - 1] == 0 && common[a] / stride[ns - 1] >= 8) stride[ns++] = common[a];
+    return ns;
+}
+
+// Rows of an nx x ny x nz grid (strides 1 | stride[1] | stride[2], n rows in all) in BOX order: boxes of lx x ty x tz grid
+// points, x fastest, boxes clipped at the grid faces and at row n.  rowmap[i] = operator row of walked row i;
+// chunk_row = first walked row of every box (+ n at the end).
+static void xs_box_order(int64_t n, int ns, const int64_t stride[3], int lx, int ty, int tz, std::vector<int32_t> &rowmap, std::vector<int32_t> &chunk_row)
+{
+    const int64_t nx = stride[1], ny = ns == 3 ? stride[2] / stride[1] : (n + nx - 1) / nx, nz = ns == 3 ? (n + stride[2] - 1) / stride[2] : 1;
+    if (ns < 3) tz = 1;
+    rowmap.clear(); chunk_row.clear();
+    rowmap.reserve(n);
+    for (int64_t kz = 0; kz < nz; kz += tz)
+        for (int64_t jy = 0; jy < ny; jy += ty)
+            for (int64_t ix = 0; ix < nx; ix += lx) {
+                const size_t before = rowmap.size();
+                for (int64_t k = kz; k < std::min<int64_t>(kz + tz, nz); ++k)
+                    for (int64_t j = jy; j < std::min<int64_t>(jy + ty, ny); ++j) {
+                        const int64_t line = (ns == 3 ? k * stride[2] : 0) + j * nx;
+                        const int64_t base = line + ix, end = std::min<int64_t>(std::min<int64_t>(base + lx, line + nx), n);
+                        for (int64_t r = base; r < end; ++r) rowmap.push_back((int32_t)r);
+                    }
+                if (rowmap.size() > before) chunk_row.push_back((int32_t)before);
+            }
+    chunk_row.push_back((int32_t)rowmap.size());
+}
+
+extern "C" {
+
+int lz_grid_strides_host(int64_t sample_rows, int64_t first_row, const int32_t *rowptr_host, const int32_t *colidx_host, int64_t strides[3])
+{
+    LZ_CHECK(rowptr_host && colidx_host && strides && sample_rows >= 0, LZ_ERR_INVALID, "lz_grid_strides_host: bad arguments");
+    strides[0] = strides[1] = strides[2] = 0;
+    return xs_strides_from_sample(sample_rows, first_row, rowptr_host, colidx_host, strides);
+}
+
+int lz_box_order_host(int64_t n_rows, int n_strides, const int64_t strides[3], int lx, int ty, int tz, int32_t *rowmap_host, int64_t chunk_cap,
+                      int32_t *chunk_row_host, int64_t *n_chunks)
+{
+    LZ_CHECK(rowmap_host && chunk_row_host && n_chunks && strides && n_rows > 0 && n_rows < ((int64_t)1 << 31), LZ_ERR_INVALID, "lz_box_order_host: bad arguments");
+    LZ_CHECK((n_strides == 2 || n_strides == 3) && strides[0] == 1 && strides[1] >= 2 && (n_strides == 2 || (strides[2] > 0 && strides[2] % strides[1] == 0)) &&
+                 lx >= 1 && ty >= 1 && tz >= 1,
+             LZ_ERR_INVALID, "lz_box_order_host: strides must be nested (1 | nx | nx*ny) and the box positive");
+    std::vector<int32_t> rowmap, crow;
+    xs_box_order(n_rows, n_strides, strides, lx, ty, tz, rowmap, crow);
+    LZ_CHECK((int64_t)rowmap.size() == n_rows, LZ_ERR_INVALID, "lz_box_order_host: the boxes do not cover the rows");
+    LZ_CHECK((int64_t)crow.size() <= chunk_cap, LZ_ERR_INVALID, "lz_box_order_host: %lld chunk boundaries do not fit %lld", (long long)crow.size(), (long long)chunk_cap);
+    memcpy(rowmap_host, rowmap.data(), sizeof(int32_t) * rowmap.size());
+    memcpy(chunk_row_host, crow.data(), sizeof(int32_t) * crow.size());
+    *n_chunks = (int64_t)crow.size() - 1;
+    return LZ_OK;
+}
+
+}  // extern "C"
+
+// the same detection on a device operator: a sample of rows from the middle goes to the host
 static int xs_detect_strides(lz_ctx *ctx, const lz_matrix *A, int64_t stride[3])
 {
+    (void)ctx;
     const int64_t n = A->n_rows;
     const int64_t S = std::min<int64_t>(4096, n / 2);
     if (S < 64) return 0;
@@ -403,24 +485,7 @@ static int xs_detect_strides(lz_ctx *ctx, const lz_matrix *A, int64_t stride[3])
     if (cnt <= 0 || cnt > S * 64) return 0;
     std::vector<int32_t> ci(cnt);
     if (cudaMemcpy(ci.data(), A->colidx + rp[0], sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-    std::vector<int64_t> offs;
-    offs.reserve(cnt);
-    for (int64_t r = 0; r < S; ++r)
-        for (int64_t k = rp[r] - rp[0]; k < rp[r + 1] - rp[0]; ++k) offs.push_back((int64_t)ci[k] - (r0 + r));
-    std::sort(offs.begin(), offs.end());
-    std::vector<int64_t> common;
-    for (size_t a = 0; a < offs.size();) {
-        size_t b = a;
-        while (b < offs.size() && offs[b] == offs[a]) ++b;
-        if ((int64_t)(b - a) * 2 >= S && offs[a] > 0) common.push_back(offs[a]);
-        a = b;
-    }
-    if (common.empty() || common[0] != 1) return 0;
-    int ns = 1;
-    stride[0] = 1;
-    for (size_t a = 1; a < common.size() && ns < 3; ++a)
-        if (common[a] % stride[ns - 1] == 0 && common[a] / stride[ns - 1] >= 8) stride[ns++] = common[a];
-    return ns;
+    return xs_strides_from_sample(S, r0, rp.data(), ci.data(), stride);
 }
 
 // Builds the X-window schedule of an unsplit, unsharded, square CSR operator once (first panel product).  Sets
@@ -454,7 +519,6 @@ int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
     rowmap.reserve(n);
     if (ns >= 2) {
         // box shape: lx rows along the unit stride, ty runs along the second stride, tz along the third
-        const int64_t nx = stride[1], ny = ns == 3 ? stride[2] / stride[1] : (n + nx - 1) / nx, nz = ns == 3 ? (n + stride[2] - 1) / stride[2] : 1;
         int lx = ns == 3 ? 32 : 16, ty = ns == 3 ? 2 : 8, tz = ns == 3 ? 2 : 1;      // (profiles/r02_spmm.md: box sweep)
         while (lx * ty * tz > rows_target && ty > 1) ty /= 2;
         while (lx * ty * tz > rows_target && tz > 1) tz /= 2;
@@ -465,18 +529,8 @@ int lz_matrix_prepare_xs(lz_ctx *ctx, const lz_matrix *Ac)
         }
         if (ns < 3) tz = 1;
         A->xs_tile_dims[0] = lx; A->xs_tile_dims[1] = ty; A->xs_tile_dims[2] = tz;
-        for (int64_t kz = 0; kz < nz; kz += tz)
-            for (int64_t jy = 0; jy < ny; jy += ty)
-                for (int64_t ix = 0; ix < nx; ix += lx) {
-                    const size_t before = rowmap.size();
-                    for (int64_t k = kz; k < std::min<int64_t>(kz + tz, nz); ++k)
-                        for (int64_t j = jy; j < std::min<int64_t>(jy + ty, ny); ++j) {
-                            const int64_t line = (ns == 3 ? k * stride[2] : 0) + j * nx;
-                            const int64_t base = line + ix, end = std::min<int64_t>(std::min<int64_t>(base + lx, line + nx), n);
-                            for (int64_t r = base; r < end; ++r) rowmap.push_back((int32_t)r);
-                        }
-                    if (rowmap.size() > before) crow.push_back((int32_t)before);
-                }
+        xs_box_order(n, ns, stride, lx, ty, tz, rowmap, crow);
+        crow.pop_back();                                                 // (the end marker is appended below for both kinds of chunks)
         if ((int64_t)rowmap.size() != n) return LZ_OK;                 // (cannot happen for nested strides; keep the gathering kernel)
     } else {
         for (int64_t r = 0; r < n; ++r) { if (r % rows_target == 0) crow.push_back((int32_t)r); rowmap.push_back((int32_t)r); }

@@ -55,6 +55,8 @@ def lib():
         "lz_matrix_destroy": (i32, [vp]),
         "lz_matrix_info": (i32, [vp, P(i64), P(i64), P(i64)]),
         "lz_matrix_spmm_schedule": (i32, [vp, vp, i32, P(i32), P(i32), P(i32)]),
+        "lz_grid_strides_host": (i32, [i64, i64, vp, vp, P(i64)]),
+        "lz_box_order_host": (i32, [i64, i32, P(i64), i32, i32, i32, vp, i64, vp, P(i64)]),
         "lz_matrix_csr_view": (i32, [vp, P(vp), P(vp), P(vp)]),
         "lz_gen_maxwell": (i32, [vp, i32, i32, i32, P(vp)]),
         "lz_matrix_ell_view": (i32, [vp, P(vp), P(vp)]),

@@ -103,6 +103,16 @@ int lz_ell_create(lz_ctx *ctx, int64_t n_rows, int64_t n_cols, int width, int la
                   const double *data, const uint32_t *idx, lz_matrix **out);
 int lz_matrix_destroy(lz_matrix *A);
 int lz_matrix_info(const lz_matrix *A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
+/* Host logic of the box-shaped chunks of the operand-staging SpMM (new; pure host code, no device needed -- exported so
+ * that it can be tested and reused).  lz_grid_strides_host: nested strides 1 | nx | nx*ny of a structured-grid operator
+ * from a SAMPLE of its rows (host CSR arrays of rows [first_row, first_row + sample_rows): rowptr_host has
+ * sample_rows + 1 entries, colidx_host[k] is the column of entry rowptr_host[0] + k); returns the number of strides found (0..3)
+ * or a negative status.  lz_box_order_host: the rows of that grid in box order (boxes of lx x ty x tz points, clipped at
+ * the faces): rowmap_host[n_rows], chunk_row_host[*n_chunks + 1] (chunk_cap entries available). */
+int lz_grid_strides_host(int64_t sample_rows, int64_t first_row, const int32_t *rowptr_host, const int32_t *colidx_host,
+                         int64_t strides[3]);
+int lz_box_order_host(int64_t n_rows, int n_strides, const int64_t strides[3], int lx, int ty, int tz, int32_t *rowmap_host,
+                      int64_t chunk_cap, int32_t *chunk_row_host, int64_t *n_chunks);
 /* Which panel-product kernel lz_block_lanczos / lz_fdtd_block run on A at width bw (new; the reference has one SpMM,
  * kernels/spmv_spmm.hpp:137-199).  Builds the lazily built schedules if needed.  kind: 0 gathering kernel, 1 operand-
  * staging kernel with chunks of consecutive rows, 2 operand-staging kernel with box-shaped chunks (box[3] = rows along the
